@@ -1,0 +1,145 @@
+/*
+ * mptcc.h -- C ABI of libmptcc.so: the B200 (sm_100a) batched mesh-vs-mesh collision checker that
+ * replaces the FCL-backed validity test of csbence/motionplanningtoolkit.
+ *
+ * Drop-in boundary.  The reference has no FFI; its innermost seam for this path is the static C++
+ * function
+ *     MeshHandler::isInCollision(const StaticEnvironmentMeshHandler&,
+ *                                const std::vector<const SimpleAgentMeshHandler*>&,
+ *                                const std::vector<std::vector<fcl::Transform3f>>& poses,
+ *                                bool checkSelfCollision = false, bool debug = false)
+ * (/root/reference/utilities/meshhandler.hpp:187-191), reached from Map3D::safeEdge / safePoses
+ * (/root/reference/workspaces/map3d.hpp:33-42).  The entry points below are what a binding of that
+ * seam needs; the headers under include/mpt_b200/ are the C++ shim that keeps the reference's class and method
+ * names on top of them.
+ *
+ * Conventions: plain C, opaque context, integer status (0 = OK), no exceptions, no C++/torch types.
+ * The caller owns every buffer it passes; inputs of set_* are copied.  One context is not re-entrant
+ * (calls on one ctx are serialised by the caller); distinct contexts are independent.  There is no
+ * CPU fallback: every check_* call fails with MPTCC_ERR_CUDA / MPTCC_ERR_NO_DEVICE when no sm_100
+ * device is usable.
+ */
+#ifndef MPTCC_H
+#define MPTCC_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPTCC_VERSION 1
+
+/* status codes */
+#define MPTCC_OK 0
+#define MPTCC_ERR_INVALID 1   /* bad argument                                   */
+#define MPTCC_ERR_STATE 2     /* environment / agent not set                    */
+#define MPTCC_ERR_NO_DEVICE 3 /* no CUDA device / not an sm_100 device          */
+#define MPTCC_ERR_CUDA 4      /* a CUDA runtime call failed (see last_error)    */
+#define MPTCC_ERR_NOMEM 5
+#define MPTCC_ERR_LIMIT 6     /* tree too deep / too many nodes for the kernel  */
+
+/* Pose record formats.  A pose-set is n_links consecutive records.
+ *  RT12: 12 doubles, R row-major (9) then T (3): fcl::Transform3f(R,T) and fcl::Transform3f(T)
+ *        (identity R) -- what the agents' getPoses produce, e.g.
+ *        /root/reference/agents/omnidirectional.hpp:224-242, agents/snake_trailers.hpp:432,455.
+ *  TQ7 : 7 doubles, x y z qw qx qy qz: fcl::Transform3f(fcl::Quaternion3f(w,x,y,z), fcl::Vec3f)
+ *        -- fcl_helpers::parseTransform (/root/reference/utilities/fcl_helpers.hpp:16-25) and the
+ *        PRMLite samples (/root/reference/discretizations/workspace/prmlite.hpp:246-258). */
+#define MPTCC_POSE_RT12 0
+#define MPTCC_POSE_TQ7 1
+
+typedef struct mptcc_ctx mptcc_ctx;
+
+/* One sub-model as handed to fcl::BVHModel::addSubModel(verts, tris)
+ * (/root/reference/utilities/meshhandler.hpp:44-47,130-133). */
+typedef struct mptcc_mesh {
+	const double *xyz;   /* [nv][3] */
+	uint32_t nv;
+	const uint32_t *tri; /* [nt][3] vertex indices */
+	uint32_t nt;
+} mptcc_mesh;
+
+typedef struct mptcc_counters {
+	uint64_t n_pose_sets;   /* pose-sets checked since the counters were last reset                */
+	uint64_t n_candidates;  /* (pose, link, env object) pairs whose world AABBs overlap            */
+	uint64_t n_bv_tests;    /* fp32 OBB-OBB tests executed by the traversal                        */
+	uint64_t n_leaf_tests;  /* fp32 triangle-triangle filter tests                                 */
+	uint64_t n_exact_tri;   /* leaf pairs re-decided in fp64 (inside the fp32 error band)          */
+	uint64_t n_path_checks; /* fp64 replays of the reference traversal path for a positive pair    */
+	uint64_t n_kernel_launches;
+} mptcc_counters;
+
+/* ---- context ------------------------------------------------------------------------------ */
+/* n_devices GPUs (1/2/4/8); device_ids may be NULL for 0..n_devices-1. */
+int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids);
+void mptcc_destroy(mptcc_ctx *ctx);
+const char *mptcc_last_error(const mptcc_ctx *ctx);
+int mptcc_num_devices(const mptcc_ctx *ctx);
+
+/* ---- scene -------------------------------------------------------------------------------- */
+/* StaticEnvironmentMeshHandler(file, pose) (/root/reference/utilities/meshhandler.hpp:18-55): one
+ * collision object per non-empty sub-mesh.  obj_pose7: [n_objects][7] x y z qw qx qy qz (the
+ * reference gives every object the same "Environment Location").  Builds the FCL-identical OBB
+ * trees on the host, flattens them and replicates them on every device of the context. */
+int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshes, const double *obj_pose7);
+
+/* Agent::getMeshes() (/root/reference/agents/omnidirectional.hpp:186-189,
+ * agents/snake_trailers.hpp:215-218): n_links models, link j of every pose-set uses link_meshes[j].
+ * Meshes with identical (xyz, tri) pointers share one device model. */
+int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes);
+
+/* ---- queries: host buffers ---------------------------------------------------------------- */
+/* One MeshHandler::isInCollision per pose-set.  poses: [n_pose_sets][n_links] records of
+ * pose_format; verdict_bits: ceil(n/32) words, bit i%32 of word i/32 = 1 <=> pose-set i collides.
+ * Pose-sets are split in contiguous slices over the context's devices. */
+int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n_pose_sets, const double *poses, int pose_format,
+                      uint32_t *verdict_bits);
+
+/* Map3D::safeEdge semantics for many edges at once (/root/reference/workspaces/map3d.hpp:33-37):
+ * segment s owns pose-sets [seg_begin[s], seg_begin[s+1]); segment_safe[s] = 1 iff none collides
+ * (an empty segment is safe). */
+int mptcc_check_segments(mptcc_ctx *ctx, uint64_t n_segments, const uint64_t *seg_begin, const double *poses,
+                         int pose_format, uint8_t *segment_safe);
+
+/* ---- queries: device buffers (inputs already resident in HBM) -------------------------------- */
+/* d_poses / d_verdict_bits are device pointers on device slot `slot` (0..n_devices-1); the launch is
+ * enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's stream) and NOT synchronised. */
+int mptcc_check_poses_device(mptcc_ctx *ctx, int slot, uint64_t n_pose_sets, const double *d_poses,
+                             int pose_format, uint32_t *d_verdict_bits, void *cuda_stream);
+int mptcc_synchronize(mptcc_ctx *ctx);
+
+/* Pinned host memory for pose / verdict buffers (full PCIe rate for the host-buffer calls). */
+void *mptcc_alloc_pinned(size_t bytes);
+void mptcc_free_pinned(void *p);
+
+/* ---- instrumentation ------------------------------------------------------------------------- */
+/* enable != 0: later launches use the counting kernel variant (slower). */
+int mptcc_enable_counters(mptcc_ctx *ctx, int enable);
+int mptcc_get_counters(mptcc_ctx *ctx, mptcc_counters *out);
+int mptcc_reset_counters(mptcc_ctx *ctx);
+/* Milliseconds of the kernels of the last host-buffer check call on device slot `slot`
+ * (CUDA events on the launching stream). */
+int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
+/* Tuning knobs: "poses_per_warp" (0 = auto, 1..32 power of two), "stack_entries", "ctas_per_sm". */
+int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
+
+/* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */
+typedef struct mptcc_bvh mptcc_bvh;
+int mptcc_bvh_build(const mptcc_mesh *mesh, mptcc_bvh **out);
+void mptcc_bvh_free(mptcc_bvh *b);
+uint32_t mptcc_bvh_num_nodes(const mptcc_bvh *b);
+uint32_t mptcc_bvh_depth(const mptcc_bvh *b);
+/* axis [n][9], To [n][3], extent [n][3], first_child [n], first_primitive [n], num_primitives [n];
+ * any pointer may be NULL. */
+void mptcc_bvh_get_nodes(const mptcc_bvh *b, double *axis, double *To, double *extent, int32_t *first_child,
+                         int32_t *first_primitive, int32_t *num_primitives);
+void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out);
+/* aabb6 = min xyz, max xyz */
+void mptcc_bvh_get_local_aabb(const mptcc_bvh *b, double *aabb6, double *center3, double *radius);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPTCC_H */

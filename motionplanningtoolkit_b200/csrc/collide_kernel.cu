@@ -1,0 +1,753 @@
+// collide_kernel.cu -- sm_100a kernel of libmptcc: batched agent-mesh vs environment-mesh collision.
+//
+// Replaces, per pose-set, one MeshHandler::isInCollision (/root/reference/utilities/meshhandler.hpp:187-243):
+//   broadphase  : world-AABB overlap of every (environment object, agent link) pair, fp64, the exact
+//                 arithmetic of fcl::CollisionObject::computeAABB + AABB::overlap  [FCL-recalled C.5, C.6]
+//   narrowphase : BVH-vs-BVH traversal.  The traversal itself is a CONSERVATIVE fp32 pass (it may only
+//                 visit more pairs than FCL, never fewer); a leaf pair that the fp32 triangle test cannot
+//                 prove separated is re-decided in fp64 with FCL's operation order (no FMA), and a
+//                 positive pair additionally replays FCL's own root-to-leaf sequence of fp64 OBB tests
+//                 [FCL-recalled C.7-C.9], so the verdict bit equals FCL's.
+//
+// Mapping: one warp owns `ppw` consecutive pose-sets (persistent warps, dynamic fetch).  Phase 1 is
+// lane-per-pose (pose decode, AABB broadphase); phase 2 is warp-per-candidate: the 32 lanes pop up to
+// 32 node pairs from a shared-memory stack, test them, and push the children of the survivors.
+// Leaf pairs are queued and tested 32 at a time.  First contact ends the pose-set.
+//
+// Error bounds of the fp32 pass are derived in DESIGN.md ("fp32 filter bounds").
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "device_layout.hpp"
+
+namespace mptcc {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr float kU = 5.9604645e-8f;  // 2^-24, fp32 unit round-off
+
+// ------------------------------------------------------------------------------------------------
+// fp64 helpers with FCL's evaluation order and no FMA contraction
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dadd_rn(a, -b); }
+// a0*b0 + a1*b1 + a2*b2, left to right
+__device__ __forceinline__ double ddot(double a0, double a1, double a2, double b0, double b1, double b2) {
+	return dadd(dadd(dmul(a0, b0), dmul(a1, b1)), dmul(a2, b2));
+}
+__device__ __forceinline__ double dabs(double a) { return fabs(a); }
+
+struct Quat {
+	double w, x, y, z;
+};
+
+// [FCL-recalled] Quaternion3f::operator*
+__device__ __forceinline__ Quat qmul(const Quat &a, const Quat &b) {
+	Quat r;
+	r.w = dsub(dsub(dsub(dmul(a.w, b.w), dmul(a.x, b.x)), dmul(a.y, b.y)), dmul(a.z, b.z));
+	r.x = dsub(dadd(dadd(dmul(a.w, b.x), dmul(a.x, b.w)), dmul(a.y, b.z)), dmul(a.z, b.y));
+	r.y = dadd(dadd(dsub(dmul(a.w, b.y), dmul(a.x, b.z)), dmul(a.y, b.w)), dmul(a.z, b.x));
+	r.z = dadd(dsub(dadd(dmul(a.w, b.z), dmul(a.x, b.y)), dmul(a.y, b.x)), dmul(a.z, b.w));
+	return r;
+}
+
+// [FCL-recalled] Quaternion3f::fromRotation (only what CollisionObject::computeAABB needs)
+__device__ __forceinline__ Quat quat_from_rotation(const double *R) {
+	Quat q;
+	const double trace = dadd(dadd(R[0], R[4]), R[8]);
+	if (trace > 0.0) {
+		double root = sqrt(dadd(trace, 1.0));
+		q.w = dmul(0.5, root);
+		root = 0.5 / root;
+		q.x = dmul(dsub(R[7], R[5]), root);
+		q.y = dmul(dsub(R[2], R[6]), root);
+		q.z = dmul(dsub(R[3], R[1]), root);
+	} else {
+		int i = 0;
+		if (R[4] > R[0]) i = 1;
+		if (R[8] > R[4 * i]) i = 2;
+		const int j = (i + 1) % 3, k = (j + 1) % 3;
+		double root = sqrt(dadd(dsub(dsub(R[4 * i], R[4 * j]), R[4 * k]), 1.0));
+		double v[3];
+		v[i] = dmul(0.5, root);
+		root = 0.5 / root;
+		q.w = dmul(dsub(R[3 * k + j], R[3 * j + k]), root);
+		v[j] = dmul(dadd(R[3 * j + i], R[3 * i + j]), root);
+		v[k] = dmul(dadd(R[3 * k + i], R[3 * i + k]), root);
+		q.x = v[0];
+		q.y = v[1];
+		q.z = v[2];
+	}
+	return q;
+}
+
+// [FCL-recalled] Quaternion3f::toRotation
+__device__ __forceinline__ void quat_to_rotation(const Quat &q, double *R) {
+	const double twoX = dmul(2.0, q.x), twoY = dmul(2.0, q.y), twoZ = dmul(2.0, q.z);
+	const double twoWX = dmul(twoX, q.w), twoWY = dmul(twoY, q.w), twoWZ = dmul(twoZ, q.w);
+	const double twoXX = dmul(twoX, q.x), twoXY = dmul(twoY, q.x), twoXZ = dmul(twoZ, q.x);
+	const double twoYY = dmul(twoY, q.y), twoYZ = dmul(twoZ, q.y), twoZZ = dmul(twoZ, q.z);
+	R[0] = dsub(1.0, dadd(twoYY, twoZZ));
+	R[1] = dsub(twoXY, twoWZ);
+	R[2] = dadd(twoXZ, twoWY);
+	R[3] = dadd(twoXY, twoWZ);
+	R[4] = dsub(1.0, dadd(twoXX, twoZZ));
+	R[5] = dsub(twoYZ, twoWX);
+	R[6] = dsub(twoXZ, twoWY);
+	R[7] = dadd(twoYZ, twoWX);
+	R[8] = dsub(1.0, dadd(twoXX, twoYY));
+}
+
+// Pose record -> R (9), T (3), q.  RT12: Transform3f(R,T) (q = fromRotation(R)); TQ7: Transform3f(q,T).
+__device__ __forceinline__ void decode_pose(const double *rec, uint32_t fmt, double *R, double *T, Quat &q,
+                                            bool want_q) {
+	if (fmt == 1u) {
+		T[0] = rec[0];
+		T[1] = rec[1];
+		T[2] = rec[2];
+		q.w = rec[3];
+		q.x = rec[4];
+		q.y = rec[5];
+		q.z = rec[6];
+		quat_to_rotation(q, R);
+	} else {
+#pragma unroll
+		for (int k = 0; k < 9; ++k) R[k] = rec[k];
+		T[0] = rec[9];
+		T[1] = rec[10];
+		T[2] = rec[11];
+		if (want_q) q = quat_from_rotation(R);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 exact tests (rare path)
+// ------------------------------------------------------------------------------------------------
+
+// [FCL-recalled C.8] overlap(R0,T0,b1,b2) -> obbDisjoint; n1/n2 point at 16-double node64 records.
+__device__ __noinline__ bool exact_obb_disjoint(const double *__restrict__ rel, const double *__restrict__ n1,
+                                                const double *__restrict__ n2) {
+	double A[9], Bx[9], c1[3], c2[3], a[3], b[3];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) {
+		A[k] = n1[k];
+		Bx[k] = n2[k];
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		c1[k] = n1[9 + k];
+		c2[k] = n2[9 + k];
+		a[k] = n1[12 + k];
+		b[k] = n2[12 + k];
+	}
+	const double *R0 = rel, *T0 = rel + 9;
+	// R0b2(r,c) = R0.row(r) . b2.axis[c]
+	double M[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+#pragma unroll
+		for (int c = 0; c < 3; ++c)
+			M[3 * r + c] = ddot(R0[3 * r], R0[3 * r + 1], R0[3 * r + 2], Bx[3 * c], Bx[3 * c + 1], Bx[3 * c + 2]);
+	// B(r,c) = R0b2.column(c) . b1.axis[r]
+	double B[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+#pragma unroll
+		for (int c = 0; c < 3; ++c) B[3 * r + c] = ddot(M[c], M[3 + c], M[6 + c], A[3 * r], A[3 * r + 1], A[3 * r + 2]);
+	// Ttemp = R0 * b2.To + T0 - b1.To ; T[k] = Ttemp . b1.axis[k]
+	double Tt[3], T[3];
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+		Tt[r] = dsub(dadd(ddot(R0[3 * r], R0[3 * r + 1], R0[3 * r + 2], c2[0], c2[1], c2[2]), T0[r]), c1[r]);
+#pragma unroll
+	for (int k = 0; k < 3; ++k) T[k] = ddot(Tt[0], Tt[1], Tt[2], A[3 * k], A[3 * k + 1], A[3 * k + 2]);
+	double Bf[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) Bf[k] = dadd(dabs(B[k]), 1e-6);
+
+	double t, s;
+	// A0, B0, A1, A2, B1, B2
+	t = dabs(T[0]);
+	if (t > dadd(a[0], ddot(Bf[0], Bf[1], Bf[2], b[0], b[1], b[2]))) return true;
+	s = ddot(B[0], B[3], B[6], T[0], T[1], T[2]);
+	t = dabs(s);
+	if (t > dadd(b[0], ddot(Bf[0], Bf[3], Bf[6], a[0], a[1], a[2]))) return true;
+	t = dabs(T[1]);
+	if (t > dadd(a[1], ddot(Bf[3], Bf[4], Bf[5], b[0], b[1], b[2]))) return true;
+	t = dabs(T[2]);
+	if (t > dadd(a[2], ddot(Bf[6], Bf[7], Bf[8], b[0], b[1], b[2]))) return true;
+	s = ddot(B[1], B[4], B[7], T[0], T[1], T[2]);
+	t = dabs(s);
+	if (t > dadd(b[1], ddot(Bf[1], Bf[4], Bf[7], a[0], a[1], a[2]))) return true;
+	s = ddot(B[2], B[5], B[8], T[0], T[1], T[2]);
+	t = dabs(s);
+	if (t > dadd(b[2], ddot(Bf[2], Bf[5], Bf[8], a[0], a[1], a[2]))) return true;
+
+#define BB(r, c) B[3 * (r) + (c)]
+#define BF(r, c) Bf[3 * (r) + (c)]
+#define SUM4(p, q, r_, s_) dadd(dadd(dadd(p, q), r_), s_)
+	// A0 x B0..B2
+	s = dsub(dmul(T[2], BB(1, 0)), dmul(T[1], BB(2, 0)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[1], BF(2, 0)), dmul(a[2], BF(1, 0)), dmul(b[1], BF(0, 2)), dmul(b[2], BF(0, 1)))) return true;
+	s = dsub(dmul(T[2], BB(1, 1)), dmul(T[1], BB(2, 1)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[1], BF(2, 1)), dmul(a[2], BF(1, 1)), dmul(b[0], BF(0, 2)), dmul(b[2], BF(0, 0)))) return true;
+	s = dsub(dmul(T[2], BB(1, 2)), dmul(T[1], BB(2, 2)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[1], BF(2, 2)), dmul(a[2], BF(1, 2)), dmul(b[0], BF(0, 1)), dmul(b[1], BF(0, 0)))) return true;
+	// A1 x B0..B2
+	s = dsub(dmul(T[0], BB(2, 0)), dmul(T[2], BB(0, 0)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(2, 0)), dmul(a[2], BF(0, 0)), dmul(b[1], BF(1, 2)), dmul(b[2], BF(1, 1)))) return true;
+	s = dsub(dmul(T[0], BB(2, 1)), dmul(T[2], BB(0, 1)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(2, 1)), dmul(a[2], BF(0, 1)), dmul(b[0], BF(1, 2)), dmul(b[2], BF(1, 0)))) return true;
+	s = dsub(dmul(T[0], BB(2, 2)), dmul(T[2], BB(0, 2)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(2, 2)), dmul(a[2], BF(0, 2)), dmul(b[0], BF(1, 1)), dmul(b[1], BF(1, 0)))) return true;
+	// A2 x B0..B2
+	s = dsub(dmul(T[1], BB(0, 0)), dmul(T[0], BB(1, 0)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(1, 0)), dmul(a[1], BF(0, 0)), dmul(b[1], BF(2, 2)), dmul(b[2], BF(2, 1)))) return true;
+	s = dsub(dmul(T[1], BB(0, 1)), dmul(T[0], BB(1, 1)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(1, 1)), dmul(a[1], BF(0, 1)), dmul(b[0], BF(2, 2)), dmul(b[2], BF(2, 0)))) return true;
+	s = dsub(dmul(T[1], BB(0, 2)), dmul(T[0], BB(1, 2)));
+	t = dabs(s);
+	if (t > SUM4(dmul(a[0], BF(1, 2)), dmul(a[1], BF(0, 2)), dmul(b[0], BF(2, 1)), dmul(b[1], BF(2, 0)))) return true;
+#undef BB
+#undef BF
+#undef SUM4
+	return false;
+}
+
+struct D3 {
+	double x, y, z;
+};
+__device__ __forceinline__ D3 d3sub(const D3 &a, const D3 &b) { return D3{dsub(a.x, b.x), dsub(a.y, b.y), dsub(a.z, b.z)}; }
+__device__ __forceinline__ D3 d3cross(const D3 &l, const D3 &r) {
+	return D3{dsub(dmul(l.y, r.z), dmul(l.z, r.y)), dsub(dmul(l.z, r.x), dmul(l.x, r.z)),
+	          dsub(dmul(l.x, r.y), dmul(l.y, r.x))};
+}
+__device__ __forceinline__ double d3dot(const D3 &a, const D3 &b) { return ddot(a.x, a.y, a.z, b.x, b.y, b.z); }
+__device__ __forceinline__ double dmin2(double a, double b) { return (b < a) ? b : a; }  // std::min
+__device__ __forceinline__ double dmax2(double a, double b) { return (a < b) ? b : a; }  // std::max
+
+// [FCL-recalled C.9] Intersect::intersect_Triangle(P1,P2,P3,Q1,Q2,Q3,R,T): the 17 axes are independent
+// given the shared prefix, so lane k (k < 17) evaluates axis k; all 32 lanes must call.
+// P, Q: 9 doubles each (model coordinates); rel: R (9), T (3).
+__device__ __noinline__ bool exact_tri_intersect_warp(const double *__restrict__ rel, const double *__restrict__ P,
+                                                      const double *__restrict__ Q, int lane) {
+	const double *R = rel, *T = rel + 9;
+	D3 P1{P[0], P[1], P[2]}, P2{P[3], P[4], P[5]}, P3{P[6], P[7], P[8]};
+	D3 Qw[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const double qx = Q[3 * i], qy = Q[3 * i + 1], qz = Q[3 * i + 2];
+		Qw[i].x = dadd(ddot(R[0], R[1], R[2], qx, qy, qz), T[0]);
+		Qw[i].y = dadd(ddot(R[3], R[4], R[5], qx, qy, qz), T[1]);
+		Qw[i].z = dadd(ddot(R[6], R[7], R[8], qx, qy, qz), T[2]);
+	}
+	const D3 p1 = d3sub(P1, P1), p2 = d3sub(P2, P1), p3 = d3sub(P3, P1);
+	const D3 q1 = d3sub(Qw[0], P1), q2 = d3sub(Qw[1], P1), q3 = d3sub(Qw[2], P1);
+	const D3 e1 = d3sub(p2, p1), e2 = d3sub(p3, p2), e3 = d3sub(p1, p3);
+	const D3 f1 = d3sub(q2, q1), f2 = d3sub(q3, q2), f3 = d3sub(q1, q3);
+	const D3 n1 = d3cross(e1, e2), m1 = d3cross(f1, f2);
+
+	D3 ax;
+	if (lane == 0) ax = n1;
+	else if (lane == 1) ax = m1;
+	else {
+		// lanes 2..10: e_a x f_b ; 11..13: e_a x n1 ; 14..16: f_a x m1
+		D3 l, r;
+		if (lane <= 10) {
+			const int a = (lane - 2) / 3, b = (lane - 2) % 3;
+			l = (a == 0) ? e1 : (a == 1) ? e2 : e3;
+			r = (b == 0) ? f1 : (b == 1) ? f2 : f3;
+		} else if (lane <= 13) {
+			const int a = lane - 11;
+			l = (a == 0) ? e1 : (a == 1) ? e2 : e3;
+			r = n1;
+		} else {
+			const int a = (lane - 14) % 3;
+			l = (a == 0) ? f1 : (a == 1) ? f2 : f3;
+			r = m1;
+		}
+		ax = d3cross(l, r);
+	}
+	// project6
+	const double a1 = d3dot(ax, p1), a2 = d3dot(ax, p2), a3 = d3dot(ax, p3);
+	const double b1 = d3dot(ax, q1), b2 = d3dot(ax, q2), b3 = d3dot(ax, q3);
+	const double mn1 = dmin2(a1, dmin2(a2, a3)), mx2 = dmax2(b1, dmax2(b2, b3));
+	const double mx1 = dmax2(a1, dmax2(a2, a3)), mn2 = dmin2(b1, dmin2(b2, b3));
+	const bool separated = (lane < 17) && ((mn1 > mx2) || (mn2 > mx1));
+	return __ballot_sync(FULL, separated) == 0u;
+}
+
+// Replays FCL's collisionRecurse descent from (root, root) to the leaf pair holding primitives
+// (prim1, prim2) and evaluates every OBB test on the way in fp64 [FCL-recalled C.7, C.8].
+// Returns true iff none of them reports "disjoint", i.e. iff FCL's traversal reaches that leaf pair.
+__device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const DevModel &m1, const DevModel &m2,
+                                                const double *__restrict__ rel, uint32_t prim1, uint32_t prim2,
+                                                int lane) {
+	const uint32_t pos1 = p.env.prim_pos[m1.tri_base + prim1];
+	const uint32_t pos2 = p.agent.prim_pos[m2.tri_base + prim2];
+	const double *__restrict__ n64a = p.env.node64 + 16ull * m1.node_base;
+	const double *__restrict__ n64b = p.agent.node64 + 16ull * m2.node_base;
+	uint32_t b1 = 0, b2 = 0;
+	uint32_t my1 = 0, my2 = 0;
+	bool have = false;
+	int k = 0;
+	bool disjoint_any = false;
+	while (true) {
+		if ((k & 31) == lane) {
+			my1 = b1;
+			my2 = b2;
+			have = true;
+		}
+		++k;
+		const int2 t1 = p.env.topo[m1.node_base + b1];
+		const int2 t2 = p.agent.topo[m2.node_base + b2];
+		const bool l1 = t1.x < 0, l2 = t2.x < 0;
+		const bool last = l1 && l2;
+		if ((k & 31) == 0 || last) {
+			bool dj = false;
+			if (have)
+				dj = exact_obb_disjoint(rel, n64a + 16ull * my1, n64b + 16ull * my2);
+			have = false;
+			if (__any_sync(FULL, dj)) disjoint_any = true;
+			if (disjoint_any || last) break;
+		}
+		const double sz1 = n64a[16ull * b1 + 15];
+		const double sz2 = n64b[16ull * b2 + 15];
+		if (l2 || (!l1 && (sz1 > sz2))) b1 = (uint32_t)t1.x + (pos1 >= (uint32_t)t1.y ? 1u : 0u);
+		else b2 = (uint32_t)t2.x + (pos2 >= (uint32_t)t2.y ? 1u : 0u);
+	}
+	return !disjoint_any;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 conservative tests (hot path)
+// ------------------------------------------------------------------------------------------------
+
+struct RelF {
+	float R[9];
+	float T[3];
+	float Tabs1;  // |T|_1
+	float S;      // tri filter scale (see tri_maybe)
+};
+
+// true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
+// n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
+__device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,
+                                                 const float4 b0, const float4 b1, const float4 b2, const float4 b3,
+                                                 const RelF &x) {
+	// M = R * [b axes as columns]
+	float M[9];
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		M[3 * r + 0] = x.R[3 * r] * b0.x + x.R[3 * r + 1] * b0.y + x.R[3 * r + 2] * b0.z;
+		M[3 * r + 1] = x.R[3 * r] * b1.x + x.R[3 * r + 1] * b1.y + x.R[3 * r + 2] * b1.z;
+		M[3 * r + 2] = x.R[3 * r] * b2.x + x.R[3 * r + 1] * b2.y + x.R[3 * r + 2] * b2.z;
+	}
+	// B(r,c) = a_r . M(:,c)
+	float B[9];
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		B[0 + c] = a0.x * M[c] + a0.y * M[3 + c] + a0.z * M[6 + c];
+		B[3 + c] = a1.x * M[c] + a1.y * M[3 + c] + a1.z * M[6 + c];
+		B[6 + c] = a2.x * M[c] + a2.y * M[3 + c] + a2.z * M[6 + c];
+	}
+	// Tt = R*c2 + T - c1 ; T = A^T Tt
+	const float c2x = b0.w, c2y = b1.w, c2z = b2.w;
+	const float c1x = a0.w, c1y = a1.w, c1z = a2.w;
+	const float tx = x.R[0] * c2x + x.R[1] * c2y + x.R[2] * c2z + (x.T[0] - c1x);
+	const float ty = x.R[3] * c2x + x.R[4] * c2y + x.R[5] * c2z + (x.T[1] - c1y);
+	const float tz = x.R[6] * c2x + x.R[7] * c2y + x.R[8] * c2z + (x.T[2] - c1z);
+	const float T0 = tx * a0.x + ty * a0.y + tz * a0.z;
+	const float T1 = tx * a1.x + ty * a1.y + tz * a1.z;
+	const float T2 = tx * a2.x + ty * a2.y + tz * a2.z;
+	// margin = 128 u (|T|_1 + |c1|_1 + |c2|_1)
+	const float S1 = x.Tabs1 + (fabsf(c1x) + fabsf(c1y) + fabsf(c1z)) + (fabsf(c2x) + fabsf(c2y) + fabsf(c2z));
+	const float mg = (128.0f * kU) * S1;
+	float F[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) F[k] = fabsf(B[k]) + 2e-6f;
+	const float ea0 = a3.x, ea1 = a3.y, ea2 = a3.z, eb0 = b3.x, eb1 = b3.y, eb2 = b3.z;
+
+	bool dj = false;
+	dj |= fabsf(T0) > ea0 + (F[0] * eb0 + F[1] * eb1 + F[2] * eb2) + mg;
+	dj |= fabsf(T1) > ea1 + (F[3] * eb0 + F[4] * eb1 + F[5] * eb2) + mg;
+	dj |= fabsf(T2) > ea2 + (F[6] * eb0 + F[7] * eb1 + F[8] * eb2) + mg;
+	dj |= fabsf(T0 * B[0] + T1 * B[3] + T2 * B[6]) > eb0 + (F[0] * ea0 + F[3] * ea1 + F[6] * ea2) + mg;
+	dj |= fabsf(T0 * B[1] + T1 * B[4] + T2 * B[7]) > eb1 + (F[1] * ea0 + F[4] * ea1 + F[7] * ea2) + mg;
+	dj |= fabsf(T0 * B[2] + T1 * B[5] + T2 * B[8]) > eb2 + (F[2] * ea0 + F[5] * ea1 + F[8] * ea2) + mg;
+	// A0 x B0..2
+	dj |= fabsf(T2 * B[3] - T1 * B[6]) > ea1 * F[6] + ea2 * F[3] + eb1 * F[2] + eb2 * F[1] + mg;
+	dj |= fabsf(T2 * B[4] - T1 * B[7]) > ea1 * F[7] + ea2 * F[4] + eb0 * F[2] + eb2 * F[0] + mg;
+	dj |= fabsf(T2 * B[5] - T1 * B[8]) > ea1 * F[8] + ea2 * F[5] + eb0 * F[1] + eb1 * F[0] + mg;
+	// A1 x B0..2
+	dj |= fabsf(T0 * B[6] - T2 * B[0]) > ea0 * F[6] + ea2 * F[0] + eb1 * F[5] + eb2 * F[4] + mg;
+	dj |= fabsf(T0 * B[7] - T2 * B[1]) > ea0 * F[7] + ea2 * F[1] + eb0 * F[5] + eb2 * F[3] + mg;
+	dj |= fabsf(T0 * B[8] - T2 * B[2]) > ea0 * F[8] + ea2 * F[2] + eb0 * F[4] + eb1 * F[3] + mg;
+	// A2 x B0..2
+	dj |= fabsf(T1 * B[0] - T0 * B[3]) > ea0 * F[3] + ea1 * F[0] + eb1 * F[8] + eb2 * F[7] + mg;
+	dj |= fabsf(T1 * B[1] - T0 * B[4]) > ea0 * F[4] + ea1 * F[1] + eb0 * F[8] + eb2 * F[6] + mg;
+	dj |= fabsf(T1 * B[2] - T0 * B[5]) > ea0 * F[5] + ea1 * F[2] + eb0 * F[7] + eb1 * F[6] + mg;
+	return dj;
+}
+
+struct F3 {
+	float x, y, z;
+};
+__device__ __forceinline__ F3 f3sub(const F3 &a, const F3 &b) { return F3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ F3 f3cross(const F3 &l, const F3 &r) {
+	return F3{l.y * r.z - l.z * r.y, l.z * r.x - l.x * r.z, l.x * r.y - l.y * r.x};
+}
+__device__ __forceinline__ float f3dot(const F3 &a, const F3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ float f3maxabs(const F3 &a) { return fmaxf(fabsf(a.x), fmaxf(fabsf(a.y), fabsf(a.z))); }
+
+// One SAT axis of the fp32 filter: true => separated by more than eps along ax.  p1 is the origin.
+__device__ __forceinline__ bool axis_separates(const F3 &ax, const F3 &p2, const F3 &p3, const F3 &q1, const F3 &q2,
+                                               const F3 &q3, float eps) {
+	const float a2 = f3dot(ax, p2), a3 = f3dot(ax, p3);
+	const float b1 = f3dot(ax, q1), b2 = f3dot(ax, q2), b3 = f3dot(ax, q3);
+	const float mnP = fminf(0.0f, fminf(a2, a3)), mxP = fmaxf(0.0f, fmaxf(a2, a3));
+	const float mnQ = fminf(b1, fminf(b2, b3)), mxQ = fmaxf(b1, fmaxf(b2, b3));
+	return (mnP - mxQ > eps) || (mnQ - mxP > eps);
+}
+
+// fp32 triangle filter: false => the fp64 test of FCL certainly finds a separating axis (no contact);
+// true => undecided, the pair must be re-decided in fp64.
+__device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, const float4 P3, const float4 Q1,
+                                              const float4 Q2, const float4 Q3, const RelF &x) {
+	const F3 o{P1.x, P1.y, P1.z};
+	const F3 p2 = f3sub(F3{P2.x, P2.y, P2.z}, o), p3 = f3sub(F3{P3.x, P3.y, P3.z}, o);
+	F3 q1, q2, q3;
+	q1.x = x.R[0] * Q1.x + x.R[1] * Q1.y + x.R[2] * Q1.z + x.T[0];
+	q1.y = x.R[3] * Q1.x + x.R[4] * Q1.y + x.R[5] * Q1.z + x.T[1];
+	q1.z = x.R[6] * Q1.x + x.R[7] * Q1.y + x.R[8] * Q1.z + x.T[2];
+	q2.x = x.R[0] * Q2.x + x.R[1] * Q2.y + x.R[2] * Q2.z + x.T[0];
+	q2.y = x.R[3] * Q2.x + x.R[4] * Q2.y + x.R[5] * Q2.z + x.T[1];
+	q2.z = x.R[6] * Q2.x + x.R[7] * Q2.y + x.R[8] * Q2.z + x.T[2];
+	q3.x = x.R[0] * Q3.x + x.R[1] * Q3.y + x.R[2] * Q3.z + x.T[0];
+	q3.y = x.R[3] * Q3.x + x.R[4] * Q3.y + x.R[5] * Q3.z + x.T[1];
+	q3.z = x.R[6] * Q3.x + x.R[7] * Q3.y + x.R[8] * Q3.z + x.T[2];
+	q1 = f3sub(q1, o);
+	q2 = f3sub(q2, o);
+	q3 = f3sub(q3, o);
+	const float D = fmaxf(fmaxf(f3maxabs(p2), f3maxabs(p3)), fmaxf(f3maxabs(q1), fmaxf(f3maxabs(q2), f3maxabs(q3))));
+	// DESIGN.md "fp32 filter bounds": eps2 = u D^2 (160 S + 512 D), eps3 = u D^3 (832 S + 2688 D)
+	const float uD2 = kU * D * D;
+	const float eps2 = uD2 * (160.0f * x.S + 512.0f * D);
+	const float eps3 = uD2 * D * (832.0f * x.S + 2688.0f * D);
+
+	const F3 e1 = p2, e2 = f3sub(p3, p2), e3 = F3{-p3.x, -p3.y, -p3.z};
+	const F3 f1 = f3sub(q2, q1), f2 = f3sub(q3, q2), f3 = f3sub(q1, q3);
+	const F3 n1 = f3cross(e1, e2), m1 = f3cross(f1, f2);
+	bool sep = false;
+	sep |= axis_separates(n1, p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(m1, p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e1, f1), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e1, f2), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e1, f3), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e2, f1), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e2, f2), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e2, f3), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e3, f1), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e3, f2), p2, p3, q1, q2, q3, eps2);
+	sep |= axis_separates(f3cross(e3, f3), p2, p3, q1, q2, q3, eps2);
+	if (!sep) {
+		sep |= axis_separates(f3cross(e1, n1), p2, p3, q1, q2, q3, eps3);
+		sep |= axis_separates(f3cross(e2, n1), p2, p3, q1, q2, q3, eps3);
+		sep |= axis_separates(f3cross(e3, n1), p2, p3, q1, q2, q3, eps3);
+		sep |= axis_separates(f3cross(f1, m1), p2, p3, q1, q2, q3, eps3);
+		sep |= axis_separates(f3cross(f2, m1), p2, p3, q1, q2, q3, eps3);
+		sep |= axis_separates(f3cross(f3, m1), p2, p3, q1, q2, q3, eps3);
+	}
+	return !sep;
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp-cooperative traversal of one (environment object, agent link, pose) candidate
+// ------------------------------------------------------------------------------------------------
+struct WarpMem {
+	uint2 *leafq;     // [kLeafQueueCap]
+	uint32_t *candq;  // [kCandQueueCap]
+	double *rel;      // [12] fp64 R, T of the current candidate (+4 spare)
+	uint2 *stack;     // [stack_cap]
+};
+
+template <bool COUNT>
+__device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevModel &m1, const DevModel &m2,
+                         const RelF &x, int lane, unsigned long long *ctr) {
+	const float4 *__restrict__ nodes1 = p.env.node32 + 4ull * m1.node_base;
+	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
+	const float4 *__restrict__ tris1 = p.env.tri32 + 3ull * m1.tri_base;
+	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
+	const unsigned lt = (1u << lane) - 1u;
+	const int wide_limit = (int)p.stack_cap - (int)p.stack_guard;
+
+	int sp = 1, lq = 0;
+	if (lane == 0) wm.stack[0] = make_uint2(0u, 0u);
+	__syncwarp();
+
+	while (sp > 0 || lq > 0) {
+		if (lq >= 32 || sp == 0) {
+			// ---- leaf phase: up to 32 triangle pairs -------------------------------------------
+			const int k = lq < 32 ? lq : 32;
+			lq -= k;
+			bool maybe = false;
+			uint2 pr = make_uint2(0u, 0u);
+			if (lane < k) {
+				pr = wm.leafq[lq + lane];
+				const float4 P1 = __ldg(tris1 + 3ull * pr.x), P2 = __ldg(tris1 + 3ull * pr.x + 1),
+				             P3 = __ldg(tris1 + 3ull * pr.x + 2);
+				const float4 Q1 = __ldg(tris2 + 3ull * pr.y), Q2 = __ldg(tris2 + 3ull * pr.y + 1),
+				             Q3 = __ldg(tris2 + 3ull * pr.y + 2);
+				maybe = tri_maybe_f32(P1, P2, P3, Q1, Q2, Q3, x);
+			}
+			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
+			unsigned mm = __ballot_sync(FULL, maybe);
+			while (mm) {
+				const int src = __ffs(mm) - 1;
+				mm &= mm - 1;
+				const uint32_t t1 = __shfl_sync(FULL, pr.x, src), t2 = __shfl_sync(FULL, pr.y, src);
+				if (COUNT) ctr[CTR_EXACT] += 1;
+				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
+				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
+				if (hit) {
+					if (COUNT) ctr[CTR_PATH] += 1;
+					if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) return true;
+				}
+			}
+			__syncwarp();
+			continue;
+		}
+		// ---- node phase: pop up to 32 pairs, test, push children of the survivors ---------------
+		int k = sp < 32 ? sp : 32;
+		const int room = wide_limit - sp;  // wide mode keeps sp <= wide_limit; else depth-first
+		if (k > room) k = room < 1 ? 1 : room;
+		sp -= k;
+		bool push_leaf = false, push_nodes = false;
+		uint2 cA = make_uint2(0u, 0u), cB = make_uint2(0u, 0u);
+		if (lane < k) {
+			const uint2 pr = wm.stack[sp + lane];
+			const float4 *n1 = nodes1 + 4ull * pr.x;
+			const float4 *n2 = nodes2 + 4ull * pr.y;
+			const float4 a0 = __ldg(n1), a1 = __ldg(n1 + 1), a2 = __ldg(n1 + 2), a3 = __ldg(n1 + 3);
+			const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), b2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
+			if (!obb_disjoint_f32(a0, a1, a2, a3, b0, b1, b2, b3, x)) {
+				const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
+				const bool l1 = link1 < 0, l2 = link2 < 0;
+				if (l1 && l2) {
+					push_leaf = true;
+					cA = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)));
+				} else {
+					push_nodes = true;
+					const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
+					const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
+					if (l2 || (!l1 && s1 > s2)) {
+						cA = make_uint2((uint32_t)link1, pr.y);
+						cB = make_uint2((uint32_t)link1 + 1u, pr.y);
+					} else {
+						cA = make_uint2(pr.x, (uint32_t)link2);
+						cB = make_uint2(pr.x, (uint32_t)link2 + 1u);
+					}
+				}
+			}
+		}
+		if (COUNT) ctr[CTR_BV] += (unsigned)k;
+		__syncwarp();
+		const unsigned lm = __ballot_sync(FULL, push_leaf);
+		const unsigned nm = __ballot_sync(FULL, push_nodes);
+		if (push_leaf) wm.leafq[lq + __popc(lm & lt)] = cA;
+		if (push_nodes) {
+			const int at = sp + 2 * __popc(nm & lt);
+			wm.stack[at] = cB;      // right child below ...
+			wm.stack[at + 1] = cA;  // ... left child on top (visited first, like FCL)
+		}
+		lq += __popc(lm);
+		sp += 2 * __popc(nm);
+		__syncwarp();
+	}
+	return false;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32) collide_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes(p.stack_cap);
+	WarpMem wm;
+	wm.leafq = reinterpret_cast<uint2 *>(base);
+	wm.candq = reinterpret_cast<uint32_t *>(base + kLeafQueueCap * 8);
+	wm.rel = reinterpret_cast<double *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4);
+	wm.stack = reinterpret_cast<uint2 *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8);
+
+	const unsigned ppw = 1u << p.ppw_log2;
+	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
+	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const unsigned lt = (1u << lane) - 1u;
+	unsigned long long ctr[CTR_N];
+#pragma unroll
+	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
+
+	while (true) {
+		unsigned chunk = 0;
+		if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
+		chunk = __shfl_sync(FULL, chunk, 0);
+		if (chunk >= n_chunks) break;
+		const unsigned long long pose0 = (unsigned long long)chunk << p.ppw_log2;
+		const unsigned long long my_pose = pose0 + (unsigned)lane;
+		const bool valid = (unsigned)lane < ppw && my_pose < p.n_pose_sets;
+		unsigned hitmask = 0;
+
+		for (unsigned j = 0; j < p.n_links; ++j) {
+			const DevModel &m2 = p.agent.models[p.link_model[j]];
+			// ---- phase 1: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
+			double bmin[3], bmax[3];
+			if (valid) {
+				double R[9], T[3];
+				Quat q;
+				decode_pose(p.poses + (my_pose * p.n_links + j) * rec_len, p.pose_format, R, T, q, true);
+				if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
+#pragma unroll
+					for (int k = 0; k < 3; ++k) {
+						bmin[k] = dadd(m2.aabb_min[k], T[k]);
+						bmax[k] = dadd(m2.aabb_max[k], T[k]);
+					}
+				} else {
+					// Transform3f::transform(c) = q.transform(c) + T, q.transform(c) = (q (0,c) q*).xyz
+					const Quat c{0.0, m2.aabb_center[0], m2.aabb_center[1], m2.aabb_center[2]};
+					const Quat qc{q.w, -q.x, -q.y, -q.z};
+					const Quat r = qmul(qmul(q, c), qc);
+					const double cw[3] = {dadd(r.x, T[0]), dadd(r.y, T[1]), dadd(r.z, T[2])};
+#pragma unroll
+					for (int k = 0; k < 3; ++k) {
+						bmin[k] = dsub(cw[k], m2.aabb_radius);
+						bmax[k] = dadd(cw[k], m2.aabb_radius);
+					}
+				}
+			}
+			// ---- broadphase over the environment objects + drain of the candidate queue ---------
+			int ncand = 0;
+			for (unsigned e0 = 0; e0 <= p.n_objects; ++e0) {
+				if (e0 < p.n_objects) {
+					bool ov = false;
+					if (valid && !((hitmask >> lane) & 1u)) {
+						const double *bb = p.objects[e0].aabb;  // AABB::overlap(env, agent), closed
+						ov = !(bb[0] > bmax[0] || bb[1] > bmax[1] || bb[2] > bmax[2] || bb[3] < bmin[0] ||
+						       bb[4] < bmin[1] || bb[5] < bmin[2]);
+					}
+					const unsigned m = __ballot_sync(FULL, ov);
+					if (m) {
+						if (ov) wm.candq[ncand + __popc(m & lt)] = ((unsigned)lane << 27) | e0;
+						ncand += __popc(m);
+					}
+					if (ncand <= kCandQueueCap - 32 && e0 + 1 < p.n_objects) continue;
+				}
+				if (ncand == 0) continue;
+				__syncwarp();
+				if (COUNT) ctr[CTR_CAND] += (unsigned)ncand;
+				for (int c = 0; c < ncand; ++c) {
+					const unsigned ent = wm.candq[c];
+					const unsigned src = ent >> 27, e = ent & 0x7ffffffu;
+					if ((hitmask >> src) & 1u) continue;
+					const DevObject &ob = p.objects[e];
+					const DevModel &m1 = p.env.models[ob.model];
+					// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1); lane r*3+c -> R(r,c),
+					// lanes 9..11 -> T.  [FCL-recalled C.7]
+					__syncwarp();
+					if (lane < 12) {
+						double R2[9], T2[3];
+						Quat q;
+						decode_pose(p.poses + ((pose0 + src) * p.n_links + j) * rec_len, p.pose_format, R2, T2, q,
+						            false);
+						if (lane < 9) {
+							const int r = lane / 3, cc = lane % 3;
+							wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
+						} else {
+							const int r = lane - 9;
+							const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
+							wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
+						}
+					}
+					__syncwarp();
+					RelF x;
+#pragma unroll
+					for (int k = 0; k < 9; ++k) x.R[k] = (float)wm.rel[k];
+					// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
+					float tinf = 0.0f;
+#pragma unroll
+					for (int r = 0; r < 3; ++r) {
+						const double tc = wm.rel[3 * r] * m2.ctr[0] + wm.rel[3 * r + 1] * m2.ctr[1] +
+						                  wm.rel[3 * r + 2] * m2.ctr[2] + wm.rel[9 + r] - m1.ctr[r];
+						x.T[r] = (float)tc;
+						tinf = fmaxf(tinf, fabsf(x.T[r]));
+					}
+					x.Tabs1 = fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2]);
+					// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
+					x.S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
+					if (traverse<COUNT>(p, wm, m1, m2, x, lane, ctr)) hitmask |= 1u << src;
+				}
+				ncand = 0;
+				__syncwarp();
+			}
+			if (__ballot_sync(FULL, valid) == hitmask) break;  // every pose-set of this warp already collides
+		}
+		// ---- verdict bits ----------------------------------------------------------------------
+		if (lane == 0) {
+			const unsigned long long word = pose0 >> 5;
+			if (ppw == 32u) p.verdict_bits[word] = hitmask;
+			else if (hitmask) atomicOr(p.verdict_bits + word, hitmask << (unsigned)(pose0 & 31ull));
+		}
+	}
+	if (COUNT && lane == 0) {
+#pragma unroll
+		for (int i = 0; i < CTR_N; ++i)
+			if (ctr[i]) atomicAdd(p.counters + i, ctr[i]);
+	}
+}
+
+}  // namespace
+
+int collide_max_ctas_per_sm(unsigned stack_cap, bool count) {
+	int n = 0;
+	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes(stack_cap);
+	cudaError_t e;
+	if (count) {
+		cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, collide_kernel<true>, kWarpsPerCta * 32, smem);
+	} else {
+		cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, collide_kernel<false>, kWarpsPerCta * 32, smem);
+	}
+	if (e != cudaSuccess) {
+		cudaGetLastError();
+		return 0;
+	}
+	return n;
+}
+
+int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream) {
+	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes(p.stack_cap);
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	cudaError_t e;
+	if (count) {
+		e = cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		collide_kernel<true><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
+	} else {
+		e = cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		if (e != cudaSuccess) return (int)e;
+		collide_kernel<false><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
+	}
+	return (int)cudaGetLastError();
+}
+
+}  // namespace mptcc

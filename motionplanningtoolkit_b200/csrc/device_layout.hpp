@@ -1,0 +1,98 @@
+// device_layout.hpp -- HBM layout of the flattened scene, shared by the host flattener (scene.cpp)
+// and the kernels (collide_kernel.cu).  See DESIGN.md "Data layout in HBM".
+//
+// The environment's models (one per object) and the agent's models (one per distinct link mesh) are
+// two ModelPacks; inside a pack all models share the arrays and a model is a (node_base, tri_base)
+// window.  Node and primitive ids on the traversal stack are model-local.
+//
+//   node32 : float4[4] per node, 64 B, fast-pass OBB in the model's RECENTRED frame (origin = the
+//            model's local AABB centre):
+//              [0] = (axis0.xyz, centre.x)  [1] = (axis1.xyz, centre.y)  [2] = (axis2.xyz, centre.z)
+//              [3] = (extent.xyz rounded up and inflated by 1e-6, int-bits link)
+//            link >= 0: first child (children are link, link+1); link < 0: leaf, primitive = -(link+1).
+//            node_base is odd, so every sibling pair (2k+1, 2k+2) shares one 128-byte line.
+//   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.
+//   node64 : double[16] per node: FCL's OBB verbatim -- axis (9), To (3), extent (3), size =
+//            extent.sqrLength() (1).  Only read when a positive leaf pair replays FCL's path.
+//   topo   : int2 per node: (first_child, split_pos); split_pos = first_primitive + size of the left
+//            child: a primitive at position pos in primitive_indices lies in the right child iff
+//            pos >= split_pos.
+//   tri64  : double[9] per triangle, model coordinates verbatim (exact pass).
+//   prim_pos : uint32 per triangle: position of the primitive in FCL's primitive_indices permutation.
+#pragma once
+
+#include <cstdint>
+
+namespace mptcc {
+
+struct DevModel {
+	uint32_t node_base;
+	uint32_t tri_base;
+	uint32_t num_tris;
+	uint32_t depth;
+	double ctr[3];         // recentring origin (fp64)
+	double aabb_min[3];    // BVHModel::computeLocalAABB (model frame, not recentred)
+	double aabb_max[3];
+	double aabb_center[3];
+	double aabb_radius;
+	float r2;              // max |v - ctr|_2 over the vertices, rounded up
+	float rinf;            // max |v - ctr|_inf over the vertices, rounded up
+	uint32_t pad[2];
+};
+
+struct DevObject {
+	double R[9];     // tf1 rotation (row-major)
+	double T[3];     // tf1 translation
+	double aabb[6];  // world AABB: min xyz, max xyz (CollisionObject::computeAABB)
+	uint32_t model;
+	uint32_t pad;
+};
+
+// One set of flattened models (the environment's, or the agent's).
+struct ModelPack {
+	const float4 *node32;
+	const float4 *tri32;
+	const double *node64;
+	const int2 *topo;
+	const double *tri64;
+	const uint32_t *prim_pos;
+	const DevModel *models;
+};
+
+struct KernelParams {
+	ModelPack env;    // models referenced by DevObject::model
+	ModelPack agent;  // models referenced by link_model[]
+	const DevObject *objects;
+	const uint32_t *link_model;  // [n_links] agent-pack model id of link j
+	uint32_t n_objects;
+	uint32_t n_links;
+	const double *poses;
+	uint32_t pose_format;
+	uint32_t ppw_log2;  // poses per warp = 1 << ppw_log2
+	unsigned long long n_pose_sets;
+	uint32_t *verdict_bits;
+	uint32_t *work_counter;
+	uint32_t stack_cap;    // entries per warp
+	uint32_t stack_guard;  // head-room kept for the depth-first fall-back (>= depth1 + depth2 + 2)
+	unsigned long long *counters;  // [6] or nullptr
+};
+
+// index of the counters in KernelParams::counters
+enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_N = 5 };
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kLeafQueueCap = 64;
+constexpr int kCandQueueCap = 64;
+// per-warp shared memory: leaf queue + candidate queue + fp64 relative transform + stack
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline constexpr unsigned warp_smem_bytes(unsigned stack_cap) {
+	return kLeafQueueCap * 8u + kCandQueueCap * 4u + 16u * 8u + stack_cap * 8u;
+}
+
+// Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.
+int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
+int collide_max_ctas_per_sm(unsigned stack_cap, bool count);
+
+}  // namespace mptcc

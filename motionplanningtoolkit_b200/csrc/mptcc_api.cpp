@@ -1,0 +1,719 @@
+// mptcc_api.cpp -- C ABI of libmptcc (include/mptcc.h): context, scene flattening, device replication,
+// pose sharding over 1/2/4/8 GPUs, host<->device pipelining.  Host-side exact arithmetic (environment
+// object transforms and world AABBs) restates fcl::Transform3f / fcl::CollisionObject [FCL-recalled
+// C.1, C.5]; build with -ffp-contract=off.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/mptcc.h"
+#include "bvh.hpp"
+#include "device_layout.hpp"
+
+using namespace mptcc;
+
+namespace {
+
+// ---- small host helpers -------------------------------------------------------------------------
+inline float round_up_f32(double x) {
+	float f = (float)x;
+	if ((double)f < x) f = std::nextafterf(f, INFINITY);
+	return f;
+}
+
+// [FCL-recalled] Quaternion3f::operator* / transform
+inline void qmul(const double a[4], const double b[4], double o[4]) {
+	const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+	const double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+	const double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+	const double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+	o[0] = w;
+	o[1] = x;
+	o[2] = y;
+	o[3] = z;
+}
+
+inline void quat_rotate(const double q[4], const double v[3], double o[3]) {
+	const double p[4] = {0.0, v[0], v[1], v[2]};
+	const double c[4] = {q[0], -q[1], -q[2], -q[3]};
+	double t[4], r[4];
+	qmul(q, p, t);
+	qmul(t, c, r);
+	o[0] = r[1];
+	o[1] = r[2];
+	o[2] = r[3];
+}
+
+// Host image of one ModelPack.
+struct HostPack {
+	std::vector<float4> node32;
+	std::vector<float4> tri32;
+	std::vector<double> node64;
+	std::vector<int2> topo;
+	std::vector<double> tri64;
+	std::vector<uint32_t> prim_pos;
+	std::vector<DevModel> models;
+	uint32_t max_depth = 0;
+
+	void clear() { *this = HostPack(); }
+
+	// Appends one model; returns its id.
+	uint32_t add(const HostBvh &b) {
+		DevModel m;
+		std::memset(&m, 0, sizeof m);
+		if ((node32.size() / 4) % 2 == 0) {  // node_base must be odd: pad one node slot
+			for (int k = 0; k < 4; ++k) node32.push_back(make_float4(0, 0, 0, 0));
+			for (int k = 0; k < 16; ++k) node64.push_back(0.0);
+			topo.push_back(make_int2(0, 0));
+		}
+		m.node_base = (uint32_t)(node32.size() / 4);
+		m.tri_base = (uint32_t)(tri32.size() / 3);
+		m.num_tris = b.num_tris();
+		m.depth = b.depth;
+		max_depth = std::max(max_depth, b.depth);
+		for (int k = 0; k < 3; ++k) {
+			m.ctr[k] = b.aabb_center[k];
+			m.aabb_min[k] = b.aabb_min[k];
+			m.aabb_max[k] = b.aabb_max[k];
+			m.aabb_center[k] = b.aabb_center[k];
+		}
+		m.aabb_radius = b.aabb_radius;
+		double r2 = 0, rinf = 0;
+		const uint32_t nv = (uint32_t)(b.xyz.size() / 3);
+		for (uint32_t i = 0; i < nv; ++i) {
+			double d2 = 0;
+			for (int k = 0; k < 3; ++k) {
+				const double d = b.xyz[3 * (size_t)i + k] - m.ctr[k];
+				d2 += d * d;
+				rinf = std::max(rinf, std::fabs(d));
+			}
+			r2 = std::max(r2, d2);
+		}
+		m.r2 = round_up_f32(std::sqrt(r2) * (1.0 + 1e-6));
+		m.rinf = round_up_f32(rinf * (1.0 + 1e-6));
+
+		const uint32_t nn = b.num_nodes();
+		for (uint32_t i = 0; i < nn; ++i) {
+			const double *A = &b.axis[9 * (size_t)i];
+			const double *C = &b.center[3 * (size_t)i];
+			const double *E = &b.extent[3 * (size_t)i];
+			for (int k = 0; k < 3; ++k)
+				node32.push_back(make_float4((float)A[3 * k], (float)A[3 * k + 1], (float)A[3 * k + 2], (float)(C[k] - m.ctr[k])));
+			float4 last;
+			last.x = round_up_f32(E[0] * (1.0 + 1e-6));
+			last.y = round_up_f32(E[1] * (1.0 + 1e-6));
+			last.z = round_up_f32(E[2] * (1.0 + 1e-6));
+			const int32_t link = b.first_child[i];
+			std::memcpy(&last.w, &link, 4);
+			node32.push_back(last);
+
+			for (int k = 0; k < 9; ++k) node64.push_back(A[k]);
+			for (int k = 0; k < 3; ++k) node64.push_back(C[k]);
+			for (int k = 0; k < 3; ++k) node64.push_back(E[k]);
+			node64.push_back(E[0] * E[0] + E[1] * E[1] + E[2] * E[2]);  // Vec3f::sqrLength, OBB::size()
+
+			int split = 0;
+			if (link >= 0) split = b.first_primitive[i] + b.num_primitives[link];
+			topo.push_back(make_int2(link, split));
+		}
+		const uint32_t nt = b.num_tris();
+		const size_t pos_base = prim_pos.size();
+		prim_pos.resize(pos_base + nt);
+		for (uint32_t i = 0; i < nt; ++i) prim_pos[pos_base + b.primitive_indices[i]] = i;
+		for (uint32_t t = 0; t < nt; ++t) {
+			for (int c = 0; c < 3; ++c) {
+				const double *v = &b.xyz[3 * (size_t)b.tri[3 * (size_t)t + c]];
+				tri32.push_back(make_float4((float)(v[0] - m.ctr[0]), (float)(v[1] - m.ctr[1]), (float)(v[2] - m.ctr[2]), 0.f));
+				tri64.push_back(v[0]);
+				tri64.push_back(v[1]);
+				tri64.push_back(v[2]);
+			}
+		}
+		models.push_back(m);
+		return (uint32_t)(models.size() - 1);
+	}
+};
+
+template <class T>
+struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	cudaError_t upload(const std::vector<T> &h, cudaStream_t s) {
+		cudaError_t e = reserve(h.size());
+		if (e != cudaSuccess) return e;
+		if (h.empty()) return cudaSuccess;
+		return cudaMemcpyAsync(p, h.data(), sizeof(T) * h.size(), cudaMemcpyHostToDevice, s);
+	}
+	cudaError_t reserve(size_t count) {
+		if (count <= n && p) return cudaSuccess;
+		if (p) cudaFree(p);
+		p = nullptr;
+		n = 0;
+		const size_t bytes = sizeof(T) * std::max<size_t>(count, 1);
+		cudaError_t e = cudaMalloc((void **)&p, bytes);
+		if (e == cudaSuccess) n = std::max<size_t>(count, 1);
+		return e;
+	}
+	void release() {
+		if (p) cudaFree(p);
+		p = nullptr;
+		n = 0;
+	}
+};
+
+struct DevPack {
+	DevBuf<float4> node32, tri32;
+	DevBuf<double> node64, tri64;
+	DevBuf<int2> topo;
+	DevBuf<uint32_t> prim_pos;
+	DevBuf<DevModel> models;
+	cudaError_t upload(const HostPack &h, cudaStream_t s) {
+		cudaError_t e;
+		if ((e = node32.upload(h.node32, s)) != cudaSuccess) return e;
+		if ((e = tri32.upload(h.tri32, s)) != cudaSuccess) return e;
+		if ((e = node64.upload(h.node64, s)) != cudaSuccess) return e;
+		if ((e = tri64.upload(h.tri64, s)) != cudaSuccess) return e;
+		if ((e = topo.upload(h.topo, s)) != cudaSuccess) return e;
+		if ((e = prim_pos.upload(h.prim_pos, s)) != cudaSuccess) return e;
+		return models.upload(h.models, s);
+	}
+	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, topo.p, tri64.p, prim_pos.p, models.p}; }
+	void release() {
+		node32.release();
+		tri32.release();
+		node64.release();
+		tri64.release();
+		topo.release();
+		prim_pos.release();
+		models.release();
+	}
+};
+
+constexpr int kPipe = 2;  // ping-pong staging sets per device
+
+struct Device {
+	int id = 0;
+	int sm_count = 0;
+	cudaStream_t stream[kPipe] = {nullptr, nullptr};
+	cudaEvent_t ev0[kPipe] = {nullptr, nullptr}, ev1[kPipe] = {nullptr, nullptr};
+	DevPack env, agent;
+	DevBuf<DevObject> objects;
+	DevBuf<uint32_t> link_model;
+	DevBuf<double> poses[kPipe];
+	DevBuf<uint32_t> bits[kPipe];
+	DevBuf<uint32_t> work[kPipe];
+	DevBuf<unsigned long long> counters;
+	DevBuf<uint32_t> work_user;  // work counter of the device-buffer entry point
+	float last_ms = 0.f;
+};
+
+}  // namespace
+
+struct mptcc_ctx {
+	std::vector<Device> devs;
+	HostPack env_h, agent_h;
+	std::vector<DevObject> objects_h;
+	std::vector<uint32_t> link_model_h;
+	bool env_set = false, agent_set = false;
+	std::string err;
+	bool count = false;
+	long opt_ppw = 0;           // 0 = auto
+	long opt_stack = 512;       // stack entries per warp
+	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
+	long opt_sub_batch = 1 << 18;
+	mptcc_counters ctr{};
+	int ctas_per_sm_cached = -1;
+	long ctas_cached_stack = -1;
+	bool ctas_cached_count = false;
+};
+
+struct mptcc_bvh {
+	HostBvh b;
+};
+
+namespace {
+
+int fail(mptcc_ctx *c, int code, const std::string &msg) {
+	if (c) c->err = msg;
+	return code;
+}
+
+int cuda_fail(mptcc_ctx *c, cudaError_t e, const char *what) {
+	cudaGetLastError();
+	return fail(c, MPTCC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+#define CU(call)                                                 \
+	do {                                                         \
+		cudaError_t e__ = (call);                                \
+		if (e__ != cudaSuccess) return cuda_fail(ctx, e__, #call); \
+	} while (0)
+
+unsigned stack_guard_for(const mptcc_ctx *c) { return c->env_h.max_depth + c->agent_h.max_depth + 2; }
+
+int grid_for(mptcc_ctx *ctx, const Device &d) {
+	if (ctx->ctas_per_sm_cached < 0 || ctx->ctas_cached_stack != ctx->opt_stack || ctx->ctas_cached_count != ctx->count) {
+		ctx->ctas_per_sm_cached = collide_max_ctas_per_sm((unsigned)ctx->opt_stack, ctx->count);
+		ctx->ctas_cached_stack = ctx->opt_stack;
+		ctx->ctas_cached_count = ctx->count;
+	}
+	int per_sm = ctx->ctas_per_sm_cached;
+	if (per_sm < 1) per_sm = 1;
+	if (ctx->opt_ctas_per_sm > 0 && ctx->opt_ctas_per_sm < per_sm) per_sm = (int)ctx->opt_ctas_per_sm;
+	return d.sm_count * per_sm;
+}
+
+unsigned pick_ppw_log2(const mptcc_ctx *ctx, uint64_t n, int grid) {
+	if (ctx->opt_ppw > 0) {
+		unsigned l = 0;
+		while ((1l << (l + 1)) <= ctx->opt_ppw && l < 5) ++l;
+		return l;
+	}
+	// enough chunks for ~2 per resident warp, else fewer poses per warp
+	const uint64_t warps = (uint64_t)grid * kWarpsPerCta;
+	unsigned l = 5;
+	while (l > 0 && (n >> l) < 2 * warps) --l;
+	return l;
+}
+
+int upload_scene_part(mptcc_ctx *ctx, bool env) {
+	for (auto &d : ctx->devs) {
+		CU(cudaSetDevice(d.id));
+		if (env) {
+			CU(d.env.upload(ctx->env_h, d.stream[0]));
+			CU(d.objects.upload(ctx->objects_h, d.stream[0]));
+		} else {
+			CU(d.agent.upload(ctx->agent_h, d.stream[0]));
+			CU(d.link_model.upload(ctx->link_model_h, d.stream[0]));
+		}
+		CU(cudaStreamSynchronize(d.stream[0]));
+	}
+	return MPTCC_OK;
+}
+
+int check_ready(mptcc_ctx *ctx) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	if (!ctx->env_set) return fail(ctx, MPTCC_ERR_STATE, "environment not set (mptcc_set_environment)");
+	if (!ctx->agent_set) return fail(ctx, MPTCC_ERR_STATE, "agent not set (mptcc_set_agent)");
+	if (ctx->devs.empty()) return fail(ctx, MPTCC_ERR_NO_DEVICE, "context has no CUDA device");
+	const unsigned guard = stack_guard_for(ctx);
+	if ((long)guard + 64 > ctx->opt_stack)
+		return fail(ctx, MPTCC_ERR_LIMIT, "BVH depth exceeds the traversal stack head-room; raise option stack_entries");
+	return MPTCC_OK;
+}
+
+void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
+	kp.env = d.env.view();
+	kp.agent = d.agent.view();
+	kp.objects = d.objects.p;
+	kp.link_model = d.link_model.p;
+	kp.n_objects = (uint32_t)ctx->objects_h.size();
+	kp.n_links = (uint32_t)ctx->link_model_h.size();
+	kp.stack_cap = (uint32_t)ctx->opt_stack;
+	kp.stack_guard = stack_guard_for(ctx);
+	kp.counters = ctx->count ? d.counters.p : nullptr;
+}
+
+// Enqueue (memsets +) kernel for n pose-sets already on the device.
+int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
+                   uint32_t *d_work, cudaStream_t s) {
+	KernelParams kp;
+	fill_params(ctx, d, kp);
+	const int grid = grid_for(ctx, d);
+	kp.poses = d_poses;
+	kp.pose_format = (uint32_t)fmt;
+	kp.n_pose_sets = n;
+	kp.verdict_bits = d_bits;
+	kp.work_counter = d_work;
+	kp.ppw_log2 = pick_ppw_log2(ctx, n, grid);
+	CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
+	if (kp.ppw_log2 != 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
+	const uint64_t chunks = (n + (1ull << kp.ppw_log2) - 1) >> kp.ppw_log2;
+	int g = grid;
+	const uint64_t need = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
+	if ((uint64_t)g > need) g = (int)std::max<uint64_t>(need, 1);
+	const int e = launch_collide(kp, g, ctx->count, s);
+	if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel launch");
+	ctx->ctr.n_kernel_launches++;
+	ctx->ctr.n_pose_sets += n;
+	return MPTCC_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
+	if (!out || n_devices < 1) return MPTCC_ERR_INVALID;
+	*out = nullptr;
+	int avail = 0;
+	cudaError_t e = cudaGetDeviceCount(&avail);
+	if (e != cudaSuccess || avail < 1) {
+		cudaGetLastError();
+		return MPTCC_ERR_NO_DEVICE;
+	}
+	std::unique_ptr<mptcc_ctx> c(new mptcc_ctx);
+	mptcc_ctx *ctx = c.get();
+	for (int i = 0; i < n_devices; ++i) {
+		Device d;
+		d.id = device_ids ? device_ids[i] : i;
+		if (d.id < 0 || d.id >= avail) return MPTCC_ERR_NO_DEVICE;
+		cudaDeviceProp prop;
+		if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) return MPTCC_ERR_NO_DEVICE;
+		if (prop.major != 10) return MPTCC_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+		d.sm_count = prop.multiProcessorCount;
+		if (cudaSetDevice(d.id) != cudaSuccess) return MPTCC_ERR_CUDA;
+		for (int k = 0; k < kPipe; ++k) {
+			if (cudaStreamCreateWithFlags(&d.stream[k], cudaStreamNonBlocking) != cudaSuccess) return MPTCC_ERR_CUDA;
+			if (cudaEventCreate(&d.ev0[k]) != cudaSuccess || cudaEventCreate(&d.ev1[k]) != cudaSuccess) return MPTCC_ERR_CUDA;
+			if (d.work[k].reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
+		}
+		if (d.work_user.reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
+		if (d.counters.reserve(CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
+		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
+		ctx->devs.push_back(d);
+	}
+	*out = c.release();
+	return MPTCC_OK;
+}
+
+void mptcc_destroy(mptcc_ctx *ctx) {
+	if (!ctx) return;
+	for (auto &d : ctx->devs) {
+		cudaSetDevice(d.id);
+		cudaDeviceSynchronize();
+		d.env.release();
+		d.agent.release();
+		d.objects.release();
+		d.link_model.release();
+		d.counters.release();
+		d.work_user.release();
+		for (int k = 0; k < kPipe; ++k) {
+			d.poses[k].release();
+			d.bits[k].release();
+			d.work[k].release();
+			if (d.stream[k]) cudaStreamDestroy(d.stream[k]);
+			if (d.ev0[k]) cudaEventDestroy(d.ev0[k]);
+			if (d.ev1[k]) cudaEventDestroy(d.ev1[k]);
+		}
+	}
+	delete ctx;
+}
+
+const char *mptcc_last_error(const mptcc_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int mptcc_num_devices(const mptcc_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshes, const double *obj_pose7) {
+	if (!ctx || n_objects < 0 || (n_objects > 0 && (!meshes || !obj_pose7))) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
+	if (n_objects >= (1 << 27)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
+	ctx->env_h.clear();
+	ctx->objects_h.clear();
+	ctx->env_set = false;
+	for (int i = 0; i < n_objects; ++i) {
+		HostBvh b;
+		if (!build_bvh(meshes[i].xyz, meshes[i].nv, meshes[i].tri, meshes[i].nt, b))
+			return fail(ctx, MPTCC_ERR_INVALID, "environment object " + std::to_string(i) + " has an empty mesh");
+		DevObject o;
+		std::memset(&o, 0, sizeof o);
+		o.model = ctx->env_h.add(b);
+		// fcl::Transform3f(Quaternion3f(w,x,y,z), Vec3f(x,y,z)) -- fcl_helpers::parseTransform
+		const double *ps = obj_pose7 + 7 * (size_t)i;
+		const double q[4] = {ps[3], ps[4], ps[5], ps[6]};
+		o.T[0] = ps[0];
+		o.T[1] = ps[1];
+		o.T[2] = ps[2];
+		quat_to_rotation(q, o.R);
+		// fcl::CollisionObject::computeAABB
+		if (q[0] == 1.0 && q[1] == 0.0 && q[2] == 0.0 && q[3] == 0.0) {
+			for (int k = 0; k < 3; ++k) {
+				o.aabb[k] = b.aabb_min[k] + o.T[k];
+				o.aabb[3 + k] = b.aabb_max[k] + o.T[k];
+			}
+		} else {
+			double c[3];
+			quat_rotate(q, b.aabb_center, c);
+			for (int k = 0; k < 3; ++k) {
+				const double ck = c[k] + o.T[k];
+				o.aabb[k] = ck - b.aabb_radius;
+				o.aabb[3 + k] = ck + b.aabb_radius;
+			}
+		}
+		ctx->objects_h.push_back(o);
+	}
+	const int rc = upload_scene_part(ctx, true);
+	if (rc != MPTCC_OK) return rc;
+	ctx->env_set = true;
+	return MPTCC_OK;
+}
+
+int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) {
+	if (!ctx || n_links < 1 || !link_meshes) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
+	ctx->agent_h.clear();
+	ctx->link_model_h.clear();
+	ctx->agent_set = false;
+	std::map<std::pair<const void *, const void *>, uint32_t> seen;
+	for (int j = 0; j < n_links; ++j) {
+		const mptcc_mesh &m = link_meshes[j];
+		const auto key = std::make_pair((const void *)m.xyz, (const void *)m.tri);
+		auto it = seen.find(key);
+		if (it != seen.end()) {
+			ctx->link_model_h.push_back(it->second);
+			continue;
+		}
+		HostBvh b;
+		if (!build_bvh(m.xyz, m.nv, m.tri, m.nt, b))
+			return fail(ctx, MPTCC_ERR_INVALID, "agent link " + std::to_string(j) + " has an empty mesh");
+		const uint32_t id = ctx->agent_h.add(b);
+		seen[key] = id;
+		ctx->link_model_h.push_back(id);
+	}
+	const int rc = upload_scene_part(ctx, false);
+	if (rc != MPTCC_OK) return rc;
+	ctx->agent_set = true;
+	return MPTCC_OK;
+}
+
+int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, uint32_t *verdict_bits) {
+	int rc = check_ready(ctx);
+	if (rc != MPTCC_OK) return rc;
+	if (fmt != MPTCC_POSE_RT12 && fmt != MPTCC_POSE_TQ7) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
+	if (n == 0) return MPTCC_OK;
+	if (!poses || !verdict_bits) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
+	const size_t rec = (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size();  // doubles per pose-set
+	const uint64_t n_words = (n + 31) / 32;
+	const size_t nd = ctx->devs.size();
+	// contiguous word-aligned slices per device, cut into sub-batches that ping-pong over two streams
+	const uint64_t words_per_dev = (n_words + nd - 1) / nd;
+	const uint64_t sub_words = std::max<uint64_t>((uint64_t)ctx->opt_sub_batch / 32, 1);
+	struct Job {
+		size_t dev;
+		uint64_t w0, w1;
+	};
+	std::vector<std::vector<Job>> jobs(nd);
+	size_t max_jobs = 0;
+	for (size_t di = 0; di < nd; ++di) {
+		const uint64_t b = std::min(n_words, di * words_per_dev), e = std::min(n_words, (di + 1) * words_per_dev);
+		// split evenly into ceil(len/sub_words) pieces
+		const uint64_t len = e - b;
+		if (len == 0) continue;
+		const uint64_t pieces = (len + sub_words - 1) / sub_words;
+		const uint64_t per = (len + pieces - 1) / pieces;
+		for (uint64_t w = b; w < e; w += per) jobs[di].push_back(Job{di, w, std::min(e, w + per)});
+		max_jobs = std::max(max_jobs, jobs[di].size());
+		ctx->devs[di].last_ms = 0.f;
+	}
+	std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed(nd);
+	// round-robin over devices so that every GPU's queue fills concurrently
+	for (size_t ji = 0; ji < max_jobs; ++ji) {
+		for (size_t di = 0; di < nd; ++di) {
+			if (ji >= jobs[di].size()) continue;
+			Device &d = ctx->devs[di];
+			const Job &jb = jobs[di][ji];
+			const int k = (int)(ji % kPipe);
+			const uint64_t p0 = jb.w0 * 32, p1 = std::min<uint64_t>(n, jb.w1 * 32), cnt = p1 - p0;
+			CU(cudaSetDevice(d.id));
+			if (ji >= (size_t)kPipe) {
+				// staging set k is reused: its previous kernel must be done before the buffers are touched
+				CU(cudaStreamSynchronize(d.stream[k]));
+				float ms = 0.f;
+				if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms += ms;
+			}
+			CU(d.poses[k].reserve(cnt * rec));
+			CU(d.bits[k].reserve(jb.w1 - jb.w0));
+			CU(cudaMemcpyAsync(d.poses[k].p, poses + p0 * rec, sizeof(double) * cnt * rec, cudaMemcpyHostToDevice, d.stream[k]));
+			CU(cudaEventRecord(d.ev0[k], d.stream[k]));
+			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k]);
+			if (rc != MPTCC_OK) return rc;
+			CU(cudaEventRecord(d.ev1[k], d.stream[k]));
+			CU(cudaMemcpyAsync(verdict_bits + jb.w0, d.bits[k].p, sizeof(uint32_t) * (jb.w1 - jb.w0), cudaMemcpyDeviceToHost,
+			                   d.stream[k]));
+		}
+	}
+	for (size_t di = 0; di < nd; ++di) {
+		Device &d = ctx->devs[di];
+		if (jobs[di].empty()) continue;
+		CU(cudaSetDevice(d.id));
+		const size_t used = std::min<size_t>(jobs[di].size(), kPipe);
+		for (size_t k = 0; k < used; ++k) {
+			CU(cudaStreamSynchronize(d.stream[k]));
+			float ms = 0.f;
+			if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms += ms;
+		}
+	}
+	return MPTCC_OK;
+}
+
+int mptcc_check_segments(mptcc_ctx *ctx, uint64_t n_segments, const uint64_t *seg_begin, const double *poses, int fmt,
+                         uint8_t *segment_safe) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	if (n_segments == 0) return MPTCC_OK;
+	if (!seg_begin || !segment_safe) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
+	const uint64_t first = seg_begin[0], n = seg_begin[n_segments] - first;
+	for (uint64_t s = 0; s < n_segments; ++s)
+		if (seg_begin[s + 1] < seg_begin[s]) return fail(ctx, MPTCC_ERR_INVALID, "seg_begin must be non-decreasing");
+	std::vector<uint32_t> bits((n + 31) / 32, 0u);
+	const size_t rec = (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size();
+	const int rc = mptcc_check_poses(ctx, n, poses ? poses + first * rec : nullptr, fmt, bits.data());
+	if (rc != MPTCC_OK) return rc;
+	for (uint64_t s = 0; s < n_segments; ++s) {
+		uint8_t safe = 1;
+		for (uint64_t i = seg_begin[s] - first; i < seg_begin[s + 1] - first; ++i)
+			if ((bits[i >> 5] >> (i & 31)) & 1u) {
+				safe = 0;
+				break;
+			}
+		segment_safe[s] = safe;
+	}
+	return MPTCC_OK;
+}
+
+int mptcc_check_poses_device(mptcc_ctx *ctx, int slot, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
+                             void *cuda_stream) {
+	int rc = check_ready(ctx);
+	if (rc != MPTCC_OK) return rc;
+	if (slot < 0 || slot >= (int)ctx->devs.size()) return fail(ctx, MPTCC_ERR_INVALID, "bad device slot");
+	if (fmt != MPTCC_POSE_RT12 && fmt != MPTCC_POSE_TQ7) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
+	if (n == 0) return MPTCC_OK;
+	if (!d_poses || !d_bits) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
+	Device &d = ctx->devs[slot];
+	CU(cudaSetDevice(d.id));
+	cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : d.stream[0];
+	return enqueue_kernel(ctx, d, n, d_poses, fmt, d_bits, d.work_user.p, s);
+}
+
+int mptcc_synchronize(mptcc_ctx *ctx) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	for (auto &d : ctx->devs) {
+		CU(cudaSetDevice(d.id));
+		CU(cudaDeviceSynchronize());
+	}
+	return MPTCC_OK;
+}
+
+void *mptcc_alloc_pinned(size_t bytes) {
+	void *p = nullptr;
+	if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+		cudaGetLastError();
+		return nullptr;
+	}
+	return p;
+}
+
+void mptcc_free_pinned(void *p) {
+	if (p) cudaFreeHost(p);
+}
+
+int mptcc_enable_counters(mptcc_ctx *ctx, int enable) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	ctx->count = enable != 0;
+	return MPTCC_OK;
+}
+
+int mptcc_get_counters(mptcc_ctx *ctx, mptcc_counters *out) {
+	if (!ctx || !out) return MPTCC_ERR_INVALID;
+	unsigned long long sum[CTR_N] = {0};
+	for (auto &d : ctx->devs) {
+		unsigned long long h[CTR_N];
+		CU(cudaSetDevice(d.id));
+		CU(cudaDeviceSynchronize());
+		CU(cudaMemcpy(h, d.counters.p, sizeof h, cudaMemcpyDeviceToHost));
+		for (int i = 0; i < CTR_N; ++i) sum[i] += h[i];
+	}
+	*out = ctx->ctr;
+	out->n_candidates = sum[CTR_CAND];
+	out->n_bv_tests = sum[CTR_BV];
+	out->n_leaf_tests = sum[CTR_LEAF];
+	out->n_exact_tri = sum[CTR_EXACT];
+	out->n_path_checks = sum[CTR_PATH];
+	return MPTCC_OK;
+}
+
+int mptcc_reset_counters(mptcc_ctx *ctx) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	for (auto &d : ctx->devs) {
+		CU(cudaSetDevice(d.id));
+		CU(cudaDeviceSynchronize());
+		CU(cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N));
+	}
+	ctx->ctr = mptcc_counters{};
+	return MPTCC_OK;
+}
+
+int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms) {
+	if (!ctx || !ms || slot < 0 || slot >= (int)ctx->devs.size()) return MPTCC_ERR_INVALID;
+	*ms = ctx->devs[slot].last_ms;
+	return MPTCC_OK;
+}
+
+int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
+	if (!ctx || !name) return MPTCC_ERR_INVALID;
+	const std::string k(name);
+	if (k == "poses_per_warp") {
+		if (value < 0 || value > 32 || (value & (value - 1))) return fail(ctx, MPTCC_ERR_INVALID, "poses_per_warp: 0 or a power of two <= 32");
+		ctx->opt_ppw = value;
+	} else if (k == "stack_entries") {
+		if (value < 128 || value > 4096) return fail(ctx, MPTCC_ERR_INVALID, "stack_entries: 128..4096");
+		ctx->opt_stack = value;
+	} else if (k == "ctas_per_sm") {
+		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
+		ctx->opt_ctas_per_sm = value;
+	} else if (k == "sub_batch") {
+		if (value < 32) return fail(ctx, MPTCC_ERR_INVALID, "sub_batch: >= 32");
+		ctx->opt_sub_batch = value;
+	} else {
+		return fail(ctx, MPTCC_ERR_INVALID, "unknown option " + k);
+	}
+	return MPTCC_OK;
+}
+
+// ---- host-only BVH introspection -------------------------------------------------------------------
+int mptcc_bvh_build(const mptcc_mesh *mesh, mptcc_bvh **out) {
+	if (!mesh || !out) return MPTCC_ERR_INVALID;
+	std::unique_ptr<mptcc_bvh> b(new mptcc_bvh);
+	if (!build_bvh(mesh->xyz, mesh->nv, mesh->tri, mesh->nt, b->b)) return MPTCC_ERR_INVALID;
+	*out = b.release();
+	return MPTCC_OK;
+}
+
+void mptcc_bvh_free(mptcc_bvh *b) { delete b; }
+uint32_t mptcc_bvh_num_nodes(const mptcc_bvh *b) { return b ? b->b.num_nodes() : 0; }
+uint32_t mptcc_bvh_depth(const mptcc_bvh *b) { return b ? b->b.depth : 0; }
+
+void mptcc_bvh_get_nodes(const mptcc_bvh *b, double *axis, double *To, double *extent, int32_t *first_child,
+                         int32_t *first_primitive, int32_t *num_primitives) {
+	const HostBvh &h = b->b;
+	const size_t n = h.num_nodes();
+	if (axis) std::memcpy(axis, h.axis.data(), sizeof(double) * 9 * n);
+	if (To) std::memcpy(To, h.center.data(), sizeof(double) * 3 * n);
+	if (extent) std::memcpy(extent, h.extent.data(), sizeof(double) * 3 * n);
+	if (first_child) std::memcpy(first_child, h.first_child.data(), sizeof(int32_t) * n);
+	if (first_primitive) std::memcpy(first_primitive, h.first_primitive.data(), sizeof(int32_t) * n);
+	if (num_primitives) std::memcpy(num_primitives, h.num_primitives.data(), sizeof(int32_t) * n);
+}
+
+void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out) {
+	std::memcpy(out, b->b.primitive_indices.data(), sizeof(uint32_t) * b->b.primitive_indices.size());
+}
+
+void mptcc_bvh_get_local_aabb(const mptcc_bvh *b, double *aabb6, double *center3, double *radius) {
+	const HostBvh &h = b->b;
+	if (aabb6) {
+		std::memcpy(aabb6, h.aabb_min, 24);
+		std::memcpy(aabb6 + 3, h.aabb_max, 24);
+	}
+	if (center3) std::memcpy(center3, h.aabb_center, 24);
+	if (radius) *radius = h.aabb_radius;
+}
+
+}  // extern "C"

@@ -1,0 +1,219 @@
+"""Synthetic inputs for tests and bench.py: seeded pose batches and procedural environments.
+
+Nothing here is on the product path; these are the "synthetic pose batches" BASELINE.json asks for.
+RNG is splitmix64 (seeds fixed in BASELINE.md section 4) so that every box generates identical inputs.
+"""
+import numpy as np
+
+from . import meshio
+
+SEED_C1, SEED_C2, SEED_C3, SEED_C4, SEED_C5, SEED_ENV = (0x5EED0001, 0x5EED0002, 0x5EED0003, 0x5EED0004,
+                                                         0x5EED0005, 0x5EEDE1F0)
+
+
+class SplitMix64:
+    """Vectorised splitmix64: element i of a draw of n is the (counter+i)-th output of the stream."""
+
+    def __init__(self, seed):
+        self.state = np.uint64(seed)
+
+    def next_u64(self, n):
+        n = int(n)
+        with np.errstate(over="ignore"):
+            idx = np.arange(1, n + 1, dtype=np.uint64)
+            z = self.state + idx * np.uint64(0x9E3779B97F4A7C15)
+            self.state = self.state + np.uint64(n) * np.uint64(0x9E3779B97F4A7C15)
+            z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+            z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+            return z ^ (z >> np.uint64(31))
+
+    def uniform(self, n, lo=0.0, hi=1.0):
+        u = (self.next_u64(n) >> np.uint64(11)).astype(np.float64) * (1.0 / 9007199254740992.0)
+        return lo + (hi - lo) * u
+
+    def integers(self, n, hi):
+        return (self.next_u64(n) % np.uint64(hi)).astype(np.int64)
+
+
+# ---------------------------------------------------------------------------------------------------
+# poses
+# ---------------------------------------------------------------------------------------------------
+
+def random_quaternions(rng, n):
+    """PRMLite::getRandomQuaternion (/root/reference/discretizations/workspace/prmlite.hpp:246-255):
+    fcl::Quaternion3f(a,b,c,d) is (w,x,y,z)."""
+    u1, u2, u3 = rng.uniform(n), rng.uniform(n), rng.uniform(n)
+    return np.stack([np.sqrt(1 - u1) * np.sin(2 * np.pi * u2), np.sqrt(1 - u1) * np.cos(2 * np.pi * u2),
+                     np.sqrt(u1) * np.sin(2 * np.pi * u3), np.sqrt(u1) * np.cos(2 * np.pi * u3)], axis=1)
+
+
+def quat_to_matrix(q):
+    """Rotation matrices of unit quaternions (w,x,y,z) -- only used to PRODUCE RT12 inputs."""
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    R = np.empty((len(q), 3, 3))
+    R[:, 0, 0] = 1 - 2 * (y * y + z * z); R[:, 0, 1] = 2 * (x * y - w * z); R[:, 0, 2] = 2 * (x * z + w * y)
+    R[:, 1, 0] = 2 * (x * y + w * z); R[:, 1, 1] = 1 - 2 * (x * x + z * z); R[:, 1, 2] = 2 * (y * z - w * x)
+    R[:, 2, 0] = 2 * (x * z - w * y); R[:, 2, 1] = 2 * (y * z + w * x); R[:, 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def poses_rt12(R, T):
+    """[n,12] records from rotation matrices [n,3,3] and translations [n,3]."""
+    n = len(T)
+    out = np.empty((n, 12))
+    out[:, :9] = np.asarray(R).reshape(n, 9)
+    out[:, 9:] = T
+    return out
+
+
+def translation_poses(T):
+    """fcl::Transform3f(Vec3f): identity rotation (Omnidirectional::getPoses)."""
+    T = np.asarray(T, dtype=np.float64).reshape(-1, 3)
+    return poses_rt12(np.tile(np.eye(3), (len(T), 1, 1)), T)
+
+
+def random_poses_rt12(rng, n, lo, hi):
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    T = np.stack([rng.uniform(n, lo[k], hi[k]) for k in range(3)], axis=1)
+    return poses_rt12(quat_to_matrix(random_quaternions(rng, n)), T)
+
+
+def random_poses_tq7(rng, n, lo, hi):
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    T = np.stack([rng.uniform(n, lo[k], hi[k]) for k in range(3)], axis=1)
+    return np.concatenate([T, random_quaternions(rng, n)], axis=1)
+
+
+def random_poses_near_objects(rng, n, env_meshes, pad, fmt="rt12"):
+    """Translations drawn inside the (padded) AABB of a randomly chosen environment object, uniform
+    rotations: exercises the narrowphase instead of empty space."""
+    lo = np.array([m[0].min(0) for m in env_meshes]) - pad
+    hi = np.array([m[0].max(0) for m in env_meshes]) + pad
+    k = rng.integers(n, len(env_meshes))
+    T = np.stack([lo[k, a] + (hi[k, a] - lo[k, a]) * rng.uniform(n) for a in range(3)], axis=1)
+    q = random_quaternions(rng, n)
+    if fmt == "tq7":
+        return np.concatenate([T, q], axis=1)
+    return poses_rt12(quat_to_matrix(q), T)
+
+
+def omnidirectional_edge_poses(start, end, dt):
+    """Omnidirectional::getPoses (/root/reference/agents/omnidirectional.hpp:202-247): translation-only
+    interpolation; returns [P,3] translations."""
+    start, end = np.asarray(start, float), np.asarray(end, float)
+    d = end - start
+    dist = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+    iterations = int(dist / dt) if dist > 0 else 0
+    if iterations < 1:
+        return np.stack([start, end])
+    step = dt / dist
+    pts = [start + (step * float(i)) * d for i in range(iterations)]
+    if float(iterations) * dt < dist:
+        pts.append(end)
+    return np.stack(pts)
+
+
+# ---------------------------------------------------------------------------------------------------
+# procedural meshes
+# ---------------------------------------------------------------------------------------------------
+
+def icosphere(subdiv=2, radius=1.0):
+    t = (1.0 + 5 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10),
+         (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, float) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[k] = len(v) - 1
+            return cache[k]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return np.array(v) * radius, np.array(f, dtype=np.uint32)
+
+
+def grid_box(n=4, size=(1.0, 1.0, 1.0)):
+    """Axis-aligned box whose faces are n x n quads (2 triangles each): 12 n^2 triangles."""
+    verts, tris = [], []
+    sx, sy, sz = [s / 2.0 for s in size]
+    lin = np.linspace(-1, 1, n + 1)
+    for axis in range(3):
+        for sign in (-1, 1):
+            base = len(verts)
+            for i in range(n + 1):
+                for j in range(n + 1):
+                    p = [0, 0, 0]
+                    p[axis] = sign
+                    p[(axis + 1) % 3] = lin[i]
+                    p[(axis + 2) % 3] = lin[j]
+                    verts.append((p[0] * sx, p[1] * sy, p[2] * sz))
+            for i in range(n):
+                for j in range(n):
+                    a = base + i * (n + 1) + j
+                    b, c, d = a + 1, a + (n + 1), a + (n + 1) + 1
+                    tris += [(a, b, d), (a, d, c)] if sign > 0 else [(a, d, b), (a, c, d)]
+    return np.array(verts, float), np.array(tris, dtype=np.uint32)
+
+
+def transform_mesh(xyz, R, T):
+    return xyz @ np.asarray(R).T + np.asarray(T)
+
+
+def synthetic_environment(n_objects=2000, tris_per_object=500, extent=200.0, seed=SEED_ENV):
+    """n_objects randomly placed / oriented / scaled obstacles (icospheres and gridded
+    boxes), vertices baked into world coordinates (every object's pose is the identity, as in the
+    reference where all sub-meshes share one "Environment Location").  Returns a list of (xyz, tri)."""
+    rng = SplitMix64(seed)
+    # icosphere subdivision levels give 20*4^k triangles; gridded boxes 12 n^2
+    sph = {k: icosphere(k) for k in range(0, 4)}
+    objs = []
+    kinds = rng.integers(n_objects, 2)
+    q = random_quaternions(rng, n_objects)
+    R = quat_to_matrix(q)
+    T = np.stack([rng.uniform(n_objects, -extent / 2, extent / 2) for _ in range(3)], axis=1)
+    scale = np.stack([rng.uniform(n_objects, 1.0, 5.0) for _ in range(3)], axis=1)
+    for i in range(n_objects):
+        if kinds[i] == 0:
+            k = int(np.clip(np.round(np.log(max(tris_per_object, 20) / 20.0) / np.log(4.0)), 0, 3))
+            v, t = sph[k]
+        else:
+            n = max(1, int(round((tris_per_object / 12.0) ** 0.5)))
+            v, t = grid_box(n)
+            v = v * 2.0
+        v = transform_mesh(v * scale[i], R[i], T[i])
+        objs.append((np.ascontiguousarray(v), t))
+    return objs
+
+
+def terrain(nx=708, ny=708, extent=200.0, height=6.0, seed=SEED_ENV):
+    """Single-object heightfield with 2*nx*ny triangles (default ~1.0 M)."""
+    rng = SplitMix64(seed + 1)
+    xs = np.linspace(-extent / 2, extent / 2, nx + 1)
+    ys = np.linspace(-extent / 2, extent / 2, ny + 1)
+    X, Y = np.meshgrid(xs, ys, indexing="ij")
+    Z = np.zeros_like(X)
+    for _ in range(24):
+        fx, fy = rng.uniform(1, 0.02, 0.4)[0], rng.uniform(1, 0.02, 0.4)[0]
+        ph, am = rng.uniform(1, 0, 6.283)[0], rng.uniform(1, 0.1, 1.0)[0]
+        Z += am * np.sin(fx * X + fy * Y + ph)
+    Z *= height / max(1e-9, np.abs(Z).max())
+    v = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+    idx = np.arange((nx + 1) * (ny + 1)).reshape(nx + 1, ny + 1)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel()
+    t = np.concatenate([np.stack([a, b, d], 1), np.stack([a, d, c], 1)]).astype(np.uint32)
+    return np.ascontiguousarray(v), t
+
+
+def fixture(name):
+    return meshio.load_mptm(name)

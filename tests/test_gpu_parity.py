@@ -1,0 +1,168 @@
+"""GPU parity tests proper: libmptcc (through the C ABI) == CPU oracle, bit for bit, on seeded inputs."""
+import numpy as np
+import pytest
+
+from helpers import Scene, assert_bits_equal, env_bbox, unit_box
+from motionplanningtoolkit_b200 import capi, meshio, scenes
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def box_scene(built):
+    b = unit_box()
+    return Scene([b], [b])
+
+
+def test_unit_box_known_answers(box_scene):
+    """two axis-aligned unit cubes collide iff max|d| <= 1 (closed)."""
+    e = 2.0 ** -52
+    T = np.array([[0, 0, 0], [1, 0, 0], [1 + e, 0, 0], [1 - e, 0, 0], [0, 1, 0], [0, 0, -1], [0, 0, -1 - e],
+                  [1, 1, 1], [1, 1, 1 + e], [2, 0, 0], [0.3, 0.99, -1], [-1, -1, -1], [0.5, 0.5, 0.5], [5, 5, 5]], float)
+    want = np.max(np.abs(T), axis=1) <= 1.0
+    chk = box_scene.checker()
+    got = O.unpack_bits(chk.check_poses(scenes.translation_poses(T)), len(T))
+    assert np.array_equal(got, want)
+    assert np.array_equal(O.unpack_bits(box_scene.oracle_bits(scenes.translation_poses(T)), len(T)), want)
+
+
+def test_unit_box_random(box_scene):
+    rng = scenes.SplitMix64(scenes.SEED_C1)
+    n = 20000
+    poses = np.concatenate([
+        scenes.translation_poses(np.stack([rng.uniform(n, -1.6, 1.6) for _ in range(3)], 1)),
+        scenes.random_poses_rt12(rng, n, (-1.8, -1.8, -1.8), (1.8, 1.8, 1.8)),
+        scenes.random_poses_rt12(rng, 1000, (-10, -10, -10), (10, 10, 10)),
+    ])
+    chk = box_scene.checker()
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "unit_box random")
+
+
+def test_unit_box_near_touching(box_scene):
+    """Adversarial: translations within a few ulps of the touching configuration on every axis."""
+    rng = scenes.SplitMix64(7)
+    n = 4096
+    T = np.stack([rng.uniform(n, -1, 1) for _ in range(3)], 1)
+    ax = rng.integers(n, 3)
+    sign = np.where(rng.integers(n, 2) == 0, -1.0, 1.0)
+    ulps = (rng.integers(n, 9) - 4).astype(np.float64)
+    T[np.arange(n), ax] = sign * (1.0 + ulps * 2.0 ** -52)
+    poses = scenes.translation_poses(T)
+    chk = box_scene.checker()
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), n, "near touching")
+
+
+@pytest.mark.parametrize("ppw", [1, 4, 32])
+@pytest.mark.parametrize("n", [1, 31, 33, 1000])
+def test_ragged_sizes_and_poses_per_warp(box_scene, ppw, n):
+    rng = scenes.SplitMix64(100 + n)
+    poses = scenes.random_poses_rt12(rng, n, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    chk = box_scene.checker(poses_per_warp=ppw)
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), n, "ppw=%d n=%d" % (ppw, n))
+
+
+def test_empty_batch(box_scene):
+    chk = box_scene.checker()
+    assert chk.check_poses(np.zeros((0, 12))).size == 0
+
+
+def test_quaternion_pose_format(box_scene):
+    rng = scenes.SplitMix64(11)
+    poses = scenes.random_poses_tq7(rng, 5000, (-1.6, -1.6, -1.6), (1.6, 1.6, 1.6))
+    poses[:10, 3:] = (1, 0, 0, 0)      # exact identity quaternion -> tight AABB branch
+    poses[10:20, 3:] = (-1, 0, 0, 0)   # same rotation, not "identity" for FCL -> sphere AABB branch
+    chk = box_scene.checker()
+    assert_bits_equal(chk.check_poses(poses, capi.POSE_TQ7), box_scene.oracle_bits(poses, O.POSE_TQ7), len(poses), "TQ7")
+
+
+def test_blimp_vs_divider(built):
+    """C3 geometry: blimp (last sub-mesh, as the reference loads it) vs divider.dae (110 objects)."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "last")
+    sc = Scene(env, [agent])
+    lo, hi = env_bbox(env, 2.0)
+    rng = scenes.SplitMix64(scenes.SEED_C3)
+    poses = np.concatenate([scenes.random_poses_rt12(rng, 15000, lo, hi),
+                            scenes.random_poses_near_objects(rng, 15000, env, 1.0)])
+    chk = sc.checker()
+    got = chk.check_poses(poses)
+    want = sc.oracle_bits(poses)
+    assert_bits_equal(got, want, len(poses), "blimp(last) vs divider")
+    frac = O.unpack_bits(want, len(poses)).mean()
+    assert 0.01 < frac < 0.99, frac
+
+
+def test_blimp_merged_vs_model_and_divider(built):
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    for name, n in (("model", 6000), ("divider", 6000)):
+        env = meshio.environment_submeshes(meshio.load_mptm(name))
+        sc = Scene(env, [agent])
+        lo, hi = env_bbox(env, 3.0)
+        rng = scenes.SplitMix64(scenes.SEED_C3 + 1)
+        poses = np.concatenate([scenes.random_poses_rt12(rng, n // 2, lo, hi),
+                                scenes.random_poses_near_objects(rng, n - n // 2, env, 2.0)])
+        chk = sc.checker()
+        assert_bits_equal(chk.check_poses(poses), sc.oracle_bits(poses), n, "blimp(merge) vs " + name)
+
+
+def test_environment_pose_with_rotation(built):
+    """Environment Location with a non-identity quaternion: tf1 enters relativeTransform and the
+    sphere-AABB branch of CollisionObject::computeAABB."""
+    env = meshio.environment_submeshes(meshio.load_mptm("model"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "last")
+    q = np.array([0.8, 0.2, -0.4, 0.4])
+    q /= np.linalg.norm(q)
+    pose7 = np.concatenate([[10.0, -20.0, 5.0], q])
+    sc = Scene(env, [agent], pose7)
+    rng = scenes.SplitMix64(21)
+    poses = scenes.random_poses_rt12(rng, 8000, (-120, -200, -120), (200, 120, 200))
+    chk = sc.checker()
+    want = sc.oracle_bits(poses)
+    assert_bits_equal(chk.check_poses(poses), want, len(poses), "rotated environment")
+    assert O.unpack_bits(want, len(poses)).any()
+
+
+def test_snake_multi_link(built):
+    """C4 geometry: 11 links (the same unit_box model) per pose-set."""
+    b = unit_box()
+    sc = Scene([b], [b] * 11)
+    rng = scenes.SplitMix64(scenes.SEED_C4)
+    n = 4000
+    poses = np.stack([scenes.random_poses_rt12(rng, n, (-4, -4, -1), (4, 4, 1)) for _ in range(11)], axis=1)
+    chk = sc.checker()
+    want = sc.oracle_bits(poses)
+    assert_bits_equal(chk.check_poses(poses), want, n, "snake 11 links")
+    f = O.unpack_bits(want, n).mean()
+    assert 0.05 < f < 0.99
+
+
+def test_segments_match_safe_edge_semantics(box_scene):
+    rng = scenes.SplitMix64(5)
+    segs, allp = [0], []
+    for _ in range(300):
+        s = np.array([rng.uniform(1, -3, 3)[0] for _ in range(3)])
+        e = s + np.array([rng.uniform(1, -1, 1)[0] for _ in range(3)])
+        pts = scenes.omnidirectional_edge_poses(s, e, 0.1)
+        allp.append(pts)
+        segs.append(segs[-1] + len(pts))
+    segs.append(segs[-1])  # one empty segment: safe
+    poses = scenes.translation_poses(np.concatenate(allp))
+    chk = box_scene.checker()
+    safe = chk.check_segments(segs, poses)
+    for i in range(len(segs) - 1):
+        want = not O.is_in_collision(box_scene.oenv, box_scene.olinks, poses[segs[i]:segs[i + 1]]) \
+            if segs[i + 1] > segs[i] else True
+        assert bool(safe[i]) == want, i
+
+
+def test_counters_and_exact_path(box_scene):
+    rng = scenes.SplitMix64(3)
+    poses = scenes.random_poses_rt12(rng, 4096, (-1.2, -1.2, -1.2), (1.2, 1.2, 1.2))
+    chk = box_scene.checker()
+    chk.enable_counters(True)
+    bits = chk.check_poses(poses)
+    c = chk.counters()
+    assert_bits_equal(bits, box_scene.oracle_bits(poses), len(poses), "counting kernel")
+    assert c["n_pose_sets"] == 4096 and c["n_bv_tests"] > 0 and c["n_leaf_tests"] > 0
+    assert c["n_path_checks"] >= int(O.unpack_bits(bits, len(poses)).sum())
