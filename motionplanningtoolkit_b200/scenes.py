@@ -170,29 +170,24 @@ def transform_mesh(xyz, R, T):
     return xyz @ np.asarray(R).T + np.asarray(T)
 
 
-def synthetic_environment(n_objects=2000, tris_per_object=500, extent=200.0, seed=SEED_ENV):
-    """n_objects randomly placed / oriented / scaled obstacles (icospheres and gridded
-    boxes), vertices baked into world coordinates (every object's pose is the identity, as in the
-    reference where all sub-meshes share one "Environment Location").  Returns a list of (xyz, tri)."""
+def synthetic_environment(n_objects=2000, extent=200.0, seed=SEED_ENV):
+    """n_objects randomly placed / oriented / scaled obstacles, vertices baked into world
+    coordinates (every object's pose is the identity, as in the reference where all sub-meshes share one
+    "Environment Location").  Mix: 50 % gridded boxes (432 triangles), 30 % icospheres (320), 20 %
+    icospheres (1280): 568 triangles per object on average, ~1.14 M triangles for 2000 objects.
+    Returns a list of (xyz, tri)."""
     rng = SplitMix64(seed)
-    # icosphere subdivision levels give 20*4^k triangles; gridded boxes 12 n^2
-    sph = {k: icosphere(k) for k in range(0, 4)}
+    shapes = [grid_box(6), icosphere(2), icosphere(3)]
+    shapes[0] = (shapes[0][0] * 2.0, shapes[0][1])
     objs = []
-    kinds = rng.integers(n_objects, 2)
-    q = random_quaternions(rng, n_objects)
-    R = quat_to_matrix(q)
+    pick = rng.uniform(n_objects)
+    kinds = np.where(pick < 0.5, 0, np.where(pick < 0.8, 1, 2))
+    R = quat_to_matrix(random_quaternions(rng, n_objects))
     T = np.stack([rng.uniform(n_objects, -extent / 2, extent / 2) for _ in range(3)], axis=1)
     scale = np.stack([rng.uniform(n_objects, 1.0, 5.0) for _ in range(3)], axis=1)
     for i in range(n_objects):
-        if kinds[i] == 0:
-            k = int(np.clip(np.round(np.log(max(tris_per_object, 20) / 20.0) / np.log(4.0)), 0, 3))
-            v, t = sph[k]
-        else:
-            n = max(1, int(round((tris_per_object / 12.0) ** 0.5)))
-            v, t = grid_box(n)
-            v = v * 2.0
-        v = transform_mesh(v * scale[i], R[i], T[i])
-        objs.append((np.ascontiguousarray(v), t))
+        v, t = shapes[int(kinds[i])]
+        objs.append((np.ascontiguousarray(transform_mesh(v * scale[i], R[i], T[i])), t))
     return objs
 
 
