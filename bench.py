@@ -198,7 +198,9 @@ def run_ours(args):
         host_bits.append(capi.PinnedArray((n_words,), np.uint32))
         dev_poses.append(torch.from_numpy(p).cuda())
     dev_bits = torch.zeros(n_words, dtype=torch.int32, device="cuda")
-    stream = torch.cuda.current_stream()
+    # a non-default stream: its handle is non-NULL (NULL would mean "the context's own stream" to the C ABI)
+    stream = torch.cuda.Stream()
+    torch.cuda.synchronize()
 
     def step_device(i):
         chk.check_poses_device(per_gpu, dev_poses[i % N_BATCHES].data_ptr(), dev_bits.data_ptr(), capi.POSE_RT12, 0,

@@ -65,20 +65,32 @@ __device__ __forceinline__ Quat quat_from_rotation(const double *R) {
 		q.y = dmul(dsub(R[2], R[6]), root);
 		q.z = dmul(dsub(R[3], R[1]), root);
 	} else {
+		// i = argmax of the diagonal (FCL's "next[]" walk), spelled out so that R stays in registers
 		int i = 0;
 		if (R[4] > R[0]) i = 1;
-		if (R[8] > R[4 * i]) i = 2;
-		const int j = (i + 1) % 3, k = (j + 1) % 3;
-		double root = sqrt(dadd(dsub(dsub(R[4 * i], R[4 * j]), R[4 * k]), 1.0));
-		double v[3];
-		v[i] = dmul(0.5, root);
-		root = 0.5 / root;
-		q.w = dmul(dsub(R[3 * k + j], R[3 * j + k]), root);
-		v[j] = dmul(dadd(R[3 * j + i], R[3 * i + j]), root);
-		v[k] = dmul(dadd(R[3 * k + i], R[3 * i + k]), root);
-		q.x = v[0];
-		q.y = v[1];
-		q.z = v[2];
+		if (R[8] > (i == 1 ? R[4] : R[0])) i = 2;
+		if (i == 0) {  // j = 1, k = 2
+			double root = sqrt(dadd(dsub(dsub(R[0], R[4]), R[8]), 1.0));
+			q.x = dmul(0.5, root);
+			root = 0.5 / root;
+			q.w = dmul(dsub(R[7], R[5]), root);
+			q.y = dmul(dadd(R[3], R[1]), root);
+			q.z = dmul(dadd(R[6], R[2]), root);
+		} else if (i == 1) {  // j = 2, k = 0
+			double root = sqrt(dadd(dsub(dsub(R[4], R[8]), R[0]), 1.0));
+			q.y = dmul(0.5, root);
+			root = 0.5 / root;
+			q.w = dmul(dsub(R[2], R[6]), root);
+			q.z = dmul(dadd(R[7], R[5]), root);
+			q.x = dmul(dadd(R[1], R[3]), root);
+		} else {  // j = 0, k = 1
+			double root = sqrt(dadd(dsub(dsub(R[8], R[0]), R[4]), 1.0));
+			q.z = dmul(0.5, root);
+			root = 0.5 / root;
+			q.w = dmul(dsub(R[3], R[1]), root);
+			q.x = dmul(dadd(R[2], R[6]), root);
+			q.y = dmul(dadd(R[5], R[7]), root);
+		}
 	}
 	return q;
 }
@@ -478,6 +490,7 @@ struct WarpMem {
 	uint2 *leafq;     // [kLeafQueueCap]
 	uint32_t *candq;  // [kCandQueueCap]
 	double *rel;      // [12] fp64 R, T of the current candidate (+4 spare)
+	double *box;      // [6][32] world AABB of each lane's pose (min xyz, max xyz), component-major
 	uint2 *stack;     // [stack_cap]
 };
 
@@ -578,7 +591,7 @@ __device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevMode
 }
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32) collide_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -587,7 +600,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) collide_kernel(const __grid
 	wm.leafq = reinterpret_cast<uint2 *>(base);
 	wm.candq = reinterpret_cast<uint32_t *>(base + kLeafQueueCap * 8);
 	wm.rel = reinterpret_cast<double *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4);
-	wm.stack = reinterpret_cast<uint2 *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8);
+	wm.box = reinterpret_cast<double *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8);
+	wm.stack = reinterpret_cast<uint2 *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8 + 6 * 32 * 8);
 
 	const unsigned ppw = 1u << p.ppw_log2;
 	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
@@ -610,9 +624,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) collide_kernel(const __grid
 		for (unsigned j = 0; j < p.n_links; ++j) {
 			const DevModel &m2 = p.agent.models[p.link_model[j]];
 			// ---- phase 1: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
-			double bmin[3], bmax[3];
+			float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
 			if (valid) {
-				double R[9], T[3];
+				double R[9], T[3], bmin[3], bmax[3];
 				Quat q;
 				decode_pose(p.poses + (my_pose * p.n_links + j) * rec_len, p.pose_format, R, T, q, true);
 				if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
@@ -633,70 +647,109 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) collide_kernel(const __grid
 						bmax[k] = dadd(cw[k], m2.aabb_radius);
 					}
 				}
+				// ---- broadphase: lane-per-pose walk of the threaded cluster tree (fp32, conservative) --
+#pragma unroll
+				for (int k = 0; k < 3; ++k) {
+					wm.box[k * 32 + lane] = bmin[k];
+					wm.box[(3 + k) * 32 + lane] = bmax[k];
+					amin[k] = __double2float_rd(bmin[k]);
+					amax[k] = __double2float_ru(bmax[k]);
+				}
 			}
-			// ---- broadphase over the environment objects + drain of the candidate queue ---------
+			__syncwarp();
+			unsigned node = valid ? 0u : p.n_bp_nodes;
 			int ncand = 0;
-			for (unsigned e0 = 0; e0 <= p.n_objects; ++e0) {
-				if (e0 < p.n_objects) {
-					bool ov = false;
-					if (valid && !((hitmask >> lane) & 1u)) {
-						const double *bb = p.objects[e0].aabb;  // AABB::overlap(env, agent), closed
-						ov = !(bb[0] > bmax[0] || bb[1] > bmax[1] || bb[2] > bmax[2] || bb[3] < bmin[0] ||
-						       bb[4] < bmin[1] || bb[5] < bmin[2]);
+			for (;;) {
+				bool more = true;
+				while (ncand <= kCandQueueCap - 32) {
+					if ((hitmask >> lane) & 1u) node = p.n_bp_nodes;
+					const bool act = node < p.n_bp_nodes;
+					if (!__any_sync(FULL, act)) {
+						more = false;
+						break;
 					}
-					const unsigned m = __ballot_sync(FULL, ov);
+					bool leaf_hit = false;
+					unsigned cl = 0;
+					if (act) {
+						const float4 lo = __ldg(p.bp_nodes + 2ull * node), hi = __ldg(p.bp_nodes + 2ull * node + 1);
+						const bool ov = !(lo.x > amax[0] || lo.y > amax[1] || lo.z > amax[2] || hi.x < amin[0] ||
+						                  hi.y < amin[1] || hi.z < amin[2]);
+						const int esc = __float_as_int(lo.w), leaf = __float_as_int(hi.w);
+						leaf_hit = ov && leaf >= 0;
+						cl = (unsigned)leaf;
+						node = (ov && leaf < 0) ? node + 1u : (unsigned)esc;
+					}
+					const unsigned m = __ballot_sync(FULL, leaf_hit);
 					if (m) {
-						if (ov) wm.candq[ncand + __popc(m & lt)] = ((unsigned)lane << 27) | e0;
+						if (leaf_hit) wm.candq[ncand + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
 						ncand += __popc(m);
 					}
-					if (ncand <= kCandQueueCap - 32 && e0 + 1 < p.n_objects) continue;
 				}
-				if (ncand == 0) continue;
 				__syncwarp();
-				if (COUNT) ctr[CTR_CAND] += (unsigned)ncand;
+				// ---- drain: (pose, cluster) entries -> exact fp64 AABB::overlap per object -> narrowphase --
 				for (int c = 0; c < ncand; ++c) {
 					const unsigned ent = wm.candq[c];
-					const unsigned src = ent >> 27, e = ent & 0x7ffffffu;
+					const unsigned src = ent >> 27, cl = ent & 0x7ffffffu;
 					if ((hitmask >> src) & 1u) continue;
-					const DevObject &ob = p.objects[e];
-					const DevModel &m1 = p.env.models[ob.model];
-					// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1); lane r*3+c -> R(r,c),
-					// lanes 9..11 -> T.  [FCL-recalled C.7]
-					__syncwarp();
-					if (lane < 12) {
-						double R2[9], T2[3];
-						Quat q;
-						decode_pose(p.poses + ((pose0 + src) * p.n_links + j) * rec_len, p.pose_format, R2, T2, q,
-						            false);
-						if (lane < 9) {
-							const int r = lane / 3, cc = lane % 3;
-							wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
-						} else {
-							const int r = lane - 9;
-							const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
-							wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
+					double sb[6];
+#pragma unroll
+					for (int k = 0; k < 6; ++k) sb[k] = wm.box[k * 32 + src];
+					const unsigned eobj = cl * kClusterSize + (unsigned)lane;
+					bool ov = false;
+					if (eobj < p.n_objects) {
+						const double *bb = p.obj_aabb + 6ull * eobj;  // AABB::overlap(env, agent), closed
+						ov = !(bb[0] > sb[3] || bb[1] > sb[4] || bb[2] > sb[5] || bb[3] < sb[0] || bb[4] < sb[1] ||
+						       bb[5] < sb[2]);
+					}
+					unsigned om = __ballot_sync(FULL, ov);
+					if (COUNT) ctr[CTR_CAND] += (unsigned)__popc(om);
+					while (om) {
+						const unsigned e = cl * kClusterSize + (unsigned)(__ffs(om) - 1);
+						om &= om - 1;
+						const DevObject &ob = p.objects[e];
+						const DevModel &m1 = p.env.models[ob.model];
+						// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1); lane r*3+c -> R(r,c),
+						// lanes 9..11 -> T.  [FCL-recalled C.7]
+						__syncwarp();
+						if (lane < 12) {
+							double R2[9], T2[3];
+							Quat q;
+							decode_pose(p.poses + ((pose0 + src) * p.n_links + j) * rec_len, p.pose_format, R2, T2, q,
+							            false);
+							if (lane < 9) {
+								const int r = lane / 3, cc = lane % 3;
+								wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
+							} else {
+								const int r = lane - 9;
+								const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
+								wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
+							}
+						}
+						__syncwarp();
+						RelF x;
+#pragma unroll
+						for (int k = 0; k < 9; ++k) x.R[k] = (float)wm.rel[k];
+						// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
+						float tinf = 0.0f;
+#pragma unroll
+						for (int r = 0; r < 3; ++r) {
+							const double tc = wm.rel[3 * r] * m2.ctr[0] + wm.rel[3 * r + 1] * m2.ctr[1] +
+							                  wm.rel[3 * r + 2] * m2.ctr[2] + wm.rel[9 + r] - m1.ctr[r];
+							x.T[r] = (float)tc;
+							tinf = fmaxf(tinf, fabsf(x.T[r]));
+						}
+						x.Tabs1 = fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2]);
+						// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
+						x.S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
+						if (traverse<COUNT>(p, wm, m1, m2, x, lane, ctr)) {
+							hitmask |= 1u << src;
+							break;
 						}
 					}
-					__syncwarp();
-					RelF x;
-#pragma unroll
-					for (int k = 0; k < 9; ++k) x.R[k] = (float)wm.rel[k];
-					// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
-					float tinf = 0.0f;
-#pragma unroll
-					for (int r = 0; r < 3; ++r) {
-						const double tc = wm.rel[3 * r] * m2.ctr[0] + wm.rel[3 * r + 1] * m2.ctr[1] +
-						                  wm.rel[3 * r + 2] * m2.ctr[2] + wm.rel[9 + r] - m1.ctr[r];
-						x.T[r] = (float)tc;
-						tinf = fmaxf(tinf, fabsf(x.T[r]));
-					}
-					x.Tabs1 = fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2]);
-					// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
-					x.S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
-					if (traverse<COUNT>(p, wm, m1, m2, x, lane, ctr)) hitmask |= 1u << src;
 				}
 				ncand = 0;
 				__syncwarp();
+				if (!more) break;
 			}
 			if (__ballot_sync(FULL, valid) == hitmask) break;  // every pose-set of this warp already collides
 		}

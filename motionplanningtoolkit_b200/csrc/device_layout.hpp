@@ -19,6 +19,16 @@
 //            pos >= split_pos.
 //   tri64  : double[9] per triangle, model coordinates verbatim (exact pass).
 //   prim_pos : uint32 per triangle: position of the primitive in FCL's primitive_indices permutation.
+//
+// Broadphase tree (bp_nodes): the objects are sorted along a Morton curve and cut into clusters of
+// kClusterSize consecutive objects; a binary tree over the cluster sequence is stored in pre-order
+// ("threaded": no stack needed).  Node n = 2 float4:
+//   [0] = (box min xyz rounded down, int-bits escape)   escape = index of the next node once this
+//                                                       subtree is done (n_bp_nodes = end)
+//   [1] = (box max xyz rounded up,   int-bits cluster)  cluster >= 0: leaf for objects
+//                                                       [cluster*kClusterSize, +kClusterSize); -1: inner,
+//                                                       the first child is node n+1.
+// The fp32 boxes are conservative; every object of a touched cluster is re-tested in fp64.
 #pragma once
 
 #include <cstdint>
@@ -62,7 +72,10 @@ struct ModelPack {
 struct KernelParams {
 	ModelPack env;    // models referenced by DevObject::model
 	ModelPack agent;  // models referenced by link_model[]
-	const DevObject *objects;
+	const DevObject *objects;    // in broadphase (Morton-cluster) order
+	const double *obj_aabb;      // [n_objects][6] world AABB min xyz, max xyz (exact fp64), same order
+	const float4 *bp_nodes;      // broadphase tree, 2 float4 per node (see below)
+	uint32_t n_bp_nodes;
 	const uint32_t *link_model;  // [n_links] agent-pack model id of link j
 	uint32_t n_objects;
 	uint32_t n_links;
@@ -80,15 +93,16 @@ struct KernelParams {
 // index of the counters in KernelParams::counters
 enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_N = 5 };
 
+constexpr int kClusterSize = 32;
 constexpr int kWarpsPerCta = 8;
 constexpr int kLeafQueueCap = 64;
 constexpr int kCandQueueCap = 64;
-// per-warp shared memory: leaf queue + candidate queue + fp64 relative transform + stack
+// per-warp shared memory: leaf queue + candidate queue + fp64 relative transform + pose boxes + stack
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline constexpr unsigned warp_smem_bytes(unsigned stack_cap) {
-	return kLeafQueueCap * 8u + kCandQueueCap * 4u + 16u * 8u + stack_cap * 8u;
+	return kLeafQueueCap * 8u + kCandQueueCap * 4u + 16u * 8u + 6u * 32u * 8u + stack_cap * 8u;
 }
 
 // Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.

@@ -30,6 +30,12 @@ inline float round_up_f32(double x) {
 	return f;
 }
 
+inline float round_down_f32(double x) {
+	float f = (float)x;
+	if ((double)f > x) f = std::nextafterf(f, -INFINITY);
+	return f;
+}
+
 // [FCL-recalled] Quaternion3f::operator* / transform
 inline void qmul(const double a[4], const double b[4], double o[4]) {
 	const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -143,6 +149,84 @@ struct HostPack {
 	}
 };
 
+// Broadphase: Morton order of the objects + threaded binary tree over clusters of kClusterSize objects
+// (layout: device_layout.hpp).  Replaces FCL's DynamicAABBTreeCollisionManager for candidate
+// generation; the candidates it yields are re-tested with FCL's exact fp64 AABB::overlap, so the set
+// of (object, link) pairs that reach the narrowphase is FCL's [FCL-recalled C.6].
+uint32_t morton10(double x) {  // x in [0,1)
+	uint32_t v = (uint32_t)std::min(1023.0, std::max(0.0, x * 1024.0));
+	v = (v | (v << 16)) & 0x030000FFu;
+	v = (v | (v << 8)) & 0x0300F00Fu;
+	v = (v | (v << 4)) & 0x030C30C3u;
+	v = (v | (v << 2)) & 0x09249249u;
+	return v;
+}
+
+struct BpBuilder {
+	const std::vector<DevObject> &objs;
+	std::vector<float4> nodes;
+	explicit BpBuilder(const std::vector<DevObject> &o) : objs(o) {}
+
+	void cluster_box(size_t c0, size_t c1, double lo[3], double hi[3]) const {
+		for (int k = 0; k < 3; ++k) {
+			lo[k] = DBL_MAX;
+			hi[k] = -DBL_MAX;
+		}
+		const size_t b = c0 * kClusterSize, e = std::min(objs.size(), c1 * kClusterSize);
+		for (size_t i = b; i < e; ++i)
+			for (int k = 0; k < 3; ++k) {
+				lo[k] = std::min(lo[k], objs[i].aabb[k]);
+				hi[k] = std::max(hi[k], objs[i].aabb[3 + k]);
+			}
+	}
+
+	// pre-order emission of the subtree over clusters [c0, c1)
+	void emit(size_t c0, size_t c1) {
+		const size_t me = nodes.size() / 2;
+		double lo[3], hi[3];
+		cluster_box(c0, c1, lo, hi);
+		nodes.push_back(make_float4(round_down_f32(lo[0]), round_down_f32(lo[1]), round_down_f32(lo[2]), 0.f));
+		nodes.push_back(make_float4(round_up_f32(hi[0]), round_up_f32(hi[1]), round_up_f32(hi[2]), 0.f));
+		int32_t leaf = -1;
+		if (c1 - c0 == 1) {
+			leaf = (int32_t)c0;
+		} else {
+			const size_t mid = c0 + (c1 - c0) / 2;
+			emit(c0, mid);
+			emit(mid, c1);
+		}
+		const int32_t escape = (int32_t)(nodes.size() / 2);
+		std::memcpy(&nodes[2 * me].w, &escape, 4);
+		std::memcpy(&nodes[2 * me + 1].w, &leaf, 4);
+	}
+};
+
+void sort_objects_morton(std::vector<DevObject> &objs) {
+	if (objs.size() < 2) return;
+	double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+	for (const auto &o : objs)
+		for (int k = 0; k < 3; ++k) {
+			const double c = 0.5 * (o.aabb[k] + o.aabb[3 + k]);
+			lo[k] = std::min(lo[k], c);
+			hi[k] = std::max(hi[k], c);
+		}
+	std::vector<std::pair<uint32_t, uint32_t>> key(objs.size());
+	for (size_t i = 0; i < objs.size(); ++i) {
+		uint32_t code = 0;
+		for (int k = 0; k < 3; ++k) {
+			const double c = 0.5 * (objs[i].aabb[k] + objs[i].aabb[3 + k]);
+			const double span = hi[k] - lo[k];
+			const double u = span > 0 ? (c - lo[k]) / span : 0.0;
+			code |= morton10(u * (1023.0 / 1024.0)) << k;
+		}
+		key[i] = std::make_pair(code, (uint32_t)i);
+	}
+	std::stable_sort(key.begin(), key.end());
+	std::vector<DevObject> sorted(objs.size());
+	for (size_t i = 0; i < objs.size(); ++i) sorted[i] = objs[key[i].second];
+	objs.swap(sorted);
+}
+
 template <class T>
 struct DevBuf {
 	T *p = nullptr;
@@ -207,6 +291,8 @@ struct Device {
 	cudaEvent_t ev0[kPipe] = {nullptr, nullptr}, ev1[kPipe] = {nullptr, nullptr};
 	DevPack env, agent;
 	DevBuf<DevObject> objects;
+	DevBuf<double> obj_aabb;
+	DevBuf<float4> bp_nodes;
 	DevBuf<uint32_t> link_model;
 	DevBuf<double> poses[kPipe];
 	DevBuf<uint32_t> bits[kPipe];
@@ -222,6 +308,8 @@ struct mptcc_ctx {
 	std::vector<Device> devs;
 	HostPack env_h, agent_h;
 	std::vector<DevObject> objects_h;
+	std::vector<double> obj_aabb_h;
+	std::vector<float4> bp_nodes_h;
 	std::vector<uint32_t> link_model_h;
 	bool env_set = false, agent_set = false;
 	std::string err;
@@ -291,6 +379,8 @@ int upload_scene_part(mptcc_ctx *ctx, bool env) {
 		if (env) {
 			CU(d.env.upload(ctx->env_h, d.stream[0]));
 			CU(d.objects.upload(ctx->objects_h, d.stream[0]));
+			CU(d.obj_aabb.upload(ctx->obj_aabb_h, d.stream[0]));
+			CU(d.bp_nodes.upload(ctx->bp_nodes_h, d.stream[0]));
 		} else {
 			CU(d.agent.upload(ctx->agent_h, d.stream[0]));
 			CU(d.link_model.upload(ctx->link_model_h, d.stream[0]));
@@ -315,6 +405,9 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.env = d.env.view();
 	kp.agent = d.agent.view();
 	kp.objects = d.objects.p;
+	kp.obj_aabb = d.obj_aabb.p;
+	kp.bp_nodes = d.bp_nodes.p;
+	kp.n_bp_nodes = (uint32_t)(ctx->bp_nodes_h.size() / 2);
 	kp.link_model = d.link_model.p;
 	kp.n_objects = (uint32_t)ctx->objects_h.size();
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
@@ -395,6 +488,8 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.env.release();
 		d.agent.release();
 		d.objects.release();
+		d.obj_aabb.release();
+		d.bp_nodes.release();
 		d.link_model.release();
 		d.counters.release();
 		d.work_user.release();
@@ -419,6 +514,8 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 	if (n_objects >= (1 << 27)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
 	ctx->env_h.clear();
 	ctx->objects_h.clear();
+	ctx->obj_aabb_h.clear();
+	ctx->bp_nodes_h.clear();
 	ctx->env_set = false;
 	for (int i = 0; i < n_objects; ++i) {
 		HostBvh b;
@@ -450,6 +547,15 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 			}
 		}
 		ctx->objects_h.push_back(o);
+	}
+	sort_objects_morton(ctx->objects_h);
+	ctx->obj_aabb_h.clear();
+	for (const auto &o : ctx->objects_h) ctx->obj_aabb_h.insert(ctx->obj_aabb_h.end(), o.aabb, o.aabb + 6);
+	ctx->bp_nodes_h.clear();
+	if (!ctx->objects_h.empty()) {
+		BpBuilder bp(ctx->objects_h);
+		bp.emit(0, (ctx->objects_h.size() + kClusterSize - 1) / kClusterSize);
+		ctx->bp_nodes_h.swap(bp.nodes);
 	}
 	const int rc = upload_scene_part(ctx, true);
 	if (rc != MPTCC_OK) return rc;
