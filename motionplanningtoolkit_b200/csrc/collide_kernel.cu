@@ -302,41 +302,72 @@ __device__ __noinline__ bool exact_tri_intersect_warp(const double *__restrict__
 // Replays FCL's collisionRecurse descent from (root, root) to the leaf pair holding primitives
 // (prim1, prim2) and evaluates every OBB test on the way in fp64 [FCL-recalled C.7, C.8].
 // Returns true iff none of them reports "disjoint", i.e. iff FCL's traversal reaches that leaf pair.
-__device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const DevModel &m1, const DevModel &m2,
-                                                const double *__restrict__ rel, uint32_t prim1, uint32_t prim2,
-                                                int lane) {
-	const uint32_t pos1 = p.env.prim_pos[m1.tri_base + prim1];
+//
+// The root-to-leaf ancestor chain of each tree depends only on the primitive's position, so both
+// chains are walked at the same time (one dependent load per level, not per path step); lane l keeps
+// level l (and l+32) of both chains.  The FCL path is the merge of the two chains under the
+// firstOverSecond rule and is then formed with shuffles; its pairs are tested 32 at a time.
+__device__ __noinline__ bool exact_path_reaches(const KernelParams &p, uint32_t node_base1, uint32_t tri_base1,
+                                                const DevModel &m2, const double *__restrict__ rel, uint32_t prim1,
+                                                uint32_t prim2, int lane) {
+	const uint32_t pos1 = p.env.prim_pos[tri_base1 + prim1];
 	const uint32_t pos2 = p.agent.prim_pos[m2.tri_base + prim2];
-	const double *__restrict__ n64a = p.env.node64 + 16ull * m1.node_base;
+	const TopoRec *__restrict__ topo1 = p.env.topo + node_base1;
+	const TopoRec *__restrict__ topo2 = p.agent.topo + m2.node_base;
+	const double *__restrict__ n64a = p.env.node64 + 16ull * node_base1;
 	const double *__restrict__ n64b = p.agent.node64 + 16ull * m2.node_base;
-	uint32_t b1 = 0, b2 = 0;
+
+	uint32_t a = 0, b = 0;
+	int d1 = -1, d2 = -1;  // level of the leaf in each chain
+	uint32_t na0 = 0, na1 = 0, nb0 = 0, nb1 = 0;
+	double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
+	for (int lvl = 0; lvl < 64 && (d1 < 0 || d2 < 0); ++lvl) {
+		TopoRec r1, r2;
+		if (d1 < 0) r1 = topo1[a];
+		if (d2 < 0) r2 = topo2[b];
+		const bool mine = (lvl & 31) == lane;
+		if (d1 < 0) {
+			if (mine) {
+				if (lvl < 32) { na0 = a; sa0 = r1.size; } else { na1 = a; sa1 = r1.size; }
+			}
+			if (r1.first_child < 0) d1 = lvl;
+			else a = (uint32_t)r1.first_child + (pos1 >= (uint32_t)r1.split_pos ? 1u : 0u);
+		}
+		if (d2 < 0) {
+			if (mine) {
+				if (lvl < 32) { nb0 = b; sb0 = r2.size; } else { nb1 = b; sb1 = r2.size; }
+			}
+			if (r2.first_child < 0) d2 = lvl;
+			else b = (uint32_t)r2.first_child + (pos2 >= (uint32_t)r2.split_pos ? 1u : 0u);
+		}
+	}
+	if (d1 < 0 || d2 < 0) return true;  // deeper than 64 levels: refused at scene set-up (MPTCC_ERR_LIMIT)
+
+	int i = 0, j = 0, k = 0;
 	uint32_t my1 = 0, my2 = 0;
-	bool have = false;
-	int k = 0;
-	bool disjoint_any = false;
+	bool have = false, disjoint_any = false;
 	while (true) {
+		const uint32_t ca = (i < 32) ? __shfl_sync(FULL, na0, i) : __shfl_sync(FULL, na1, i - 32);
+		const uint32_t cb = (j < 32) ? __shfl_sync(FULL, nb0, j) : __shfl_sync(FULL, nb1, j - 32);
+		const double sz1 = (i < 32) ? __shfl_sync(FULL, sa0, i) : __shfl_sync(FULL, sa1, i - 32);
+		const double sz2 = (j < 32) ? __shfl_sync(FULL, sb0, j) : __shfl_sync(FULL, sb1, j - 32);
 		if ((k & 31) == lane) {
-			my1 = b1;
-			my2 = b2;
+			my1 = ca;
+			my2 = cb;
 			have = true;
 		}
 		++k;
-		const int2 t1 = p.env.topo[m1.node_base + b1];
-		const int2 t2 = p.agent.topo[m2.node_base + b2];
-		const bool l1 = t1.x < 0, l2 = t2.x < 0;
+		const bool l1 = i == d1, l2 = j == d2;
 		const bool last = l1 && l2;
 		if ((k & 31) == 0 || last) {
 			bool dj = false;
-			if (have)
-				dj = exact_obb_disjoint(rel, n64a + 16ull * my1, n64b + 16ull * my2);
+			if (have) dj = exact_obb_disjoint(rel, n64a + 16ull * my1, n64b + 16ull * my2);
 			have = false;
 			if (__any_sync(FULL, dj)) disjoint_any = true;
 			if (disjoint_any || last) break;
 		}
-		const double sz1 = n64a[16ull * b1 + 15];
-		const double sz2 = n64b[16ull * b2 + 15];
-		if (l2 || (!l1 && (sz1 > sz2))) b1 = (uint32_t)t1.x + (pos1 >= (uint32_t)t1.y ? 1u : 0u);
-		else b2 = (uint32_t)t2.x + (pos2 >= (uint32_t)t2.y ? 1u : 0u);
+		if (l2 || (!l1 && (sz1 > sz2))) ++i;
+		else ++j;
 	}
 	return !disjoint_any;
 }
@@ -348,8 +379,7 @@ __device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const Dev
 struct RelF {
 	float R[9];
 	float T[3];
-	float Tabs1;  // |T|_1
-	float S;      // tri filter scale (see tri_maybe)
+	float S;  // tri filter scale (see tri_maybe_f32)
 };
 
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
@@ -383,7 +413,7 @@ __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a
 	const float T1 = tx * a1.x + ty * a1.y + tz * a1.z;
 	const float T2 = tx * a2.x + ty * a2.y + tz * a2.z;
 	// margin = 128 u (|T|_1 + |c1|_1 + |c2|_1)
-	const float S1 = x.Tabs1 + (fabsf(c1x) + fabsf(c1y) + fabsf(c1z)) + (fabsf(c2x) + fabsf(c2y) + fabsf(c2z));
+	const float S1 = (fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2])) + (fabsf(c1x) + fabsf(c1y) + fabsf(c1z)) + (fabsf(c2x) + fabsf(c2y) + fabsf(c2z));
 	const float mg = (128.0f * kU) * S1;
 	float F[9];
 #pragma unroll
@@ -487,28 +517,45 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 // warp-cooperative traversal of one (environment object, agent link, pose) candidate
 // ------------------------------------------------------------------------------------------------
 struct WarpMem {
-	uint2 *leafq;     // [kLeafQueueCap]
-	uint32_t *candq;  // [kCandQueueCap]
-	double *rel;      // [12] fp64 R, T of the current candidate (+4 spare)
-	double *box;      // [6][32] world AABB of each lane's pose (min xyz, max xyz), component-major
-	uint2 *stack;     // [stack_cap]
+	uint2 *stack;        // [stack_cap]   (env node, agent node | cand << 24)
+	uint2 *leafq;        // [kLeafQueueCap] (env prim, agent prim | cand << 24)
+	float4 *cand;        // [kCandCap][4] candidate records: R(9) T(3) S src node_base1 tri_base1
+	uint32_t *cand_ids;  // [kCandCap]    pose slot << 27 | object
+	uint32_t *clq;       // [kClusterQueueCap] pose slot << 27 | cluster
+	double *rel;         // [16] fp64 R (9), T (3) of the candidate being re-decided exactly
+	double *box;         // [6][32] world AABB of each lane's pose (min xyz, max xyz), component-major
 };
 
+// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1)  [FCL-recalled C.7]; element `idx`
+// (0..8 -> R row-major, 9..11 -> T).
+__device__ __forceinline__ double rel_element(const DevObject &ob, const double *R2, const double *T2, int idx) {
+	if (idx < 9) {
+		const int r = idx / 3, cc = idx % 3;
+		return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
+	}
+	const int r = idx - 9;
+	const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
+	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
+}
+
+// Merged traversal of all `ncand` candidates of the warp's pose chunk: one stack, every entry tagged
+// with its candidate; a lane fetches its entry's transform from the candidate table.  Returns the
+// updated hit mask (bit = pose slot).
 template <bool COUNT>
-__device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevModel &m1, const DevModel &m2,
-                         const RelF &x, int lane, unsigned long long *ctr) {
-	const float4 *__restrict__ nodes1 = p.env.node32 + 4ull * m1.node_base;
+__device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const DevModel &m2, int ncand,
+                                 unsigned hitmask, unsigned validmask, const double *link_poses, unsigned rec_len,
+                                 int lane, unsigned long long *ctr) {
 	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
-	const float4 *__restrict__ tris1 = p.env.tri32 + 3ull * m1.tri_base;
 	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
 	const unsigned lt = (1u << lane) - 1u;
 	const int wide_limit = (int)p.stack_cap - (int)p.stack_guard;
 
-	int sp = 1, lq = 0;
-	if (lane == 0) wm.stack[0] = make_uint2(0u, 0u);
+	int sp = ncand, lq = 0;
+	for (int i = lane; i < ncand; i += 32) wm.stack[i] = make_uint2(0u, (unsigned)(ncand - 1 - i) << 24);
 	__syncwarp();
 
 	while (sp > 0 || lq > 0) {
+		if (hitmask == validmask) break;  // every pose-set of the chunk already collides
 		if (lq >= 32 || sp == 0) {
 			// ---- leaf phase: up to 32 triangle pairs -------------------------------------------
 			const int k = lq < 32 ? lq : 32;
@@ -517,24 +564,49 @@ __device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevMode
 			uint2 pr = make_uint2(0u, 0u);
 			if (lane < k) {
 				pr = wm.leafq[lq + lane];
-				const float4 P1 = __ldg(tris1 + 3ull * pr.x), P2 = __ldg(tris1 + 3ull * pr.x + 1),
-				             P3 = __ldg(tris1 + 3ull * pr.x + 2);
-				const float4 Q1 = __ldg(tris2 + 3ull * pr.y), Q2 = __ldg(tris2 + 3ull * pr.y + 1),
-				             Q3 = __ldg(tris2 + 3ull * pr.y + 2);
-				maybe = tri_maybe_f32(P1, P2, P3, Q1, Q2, Q3, x);
+				const float4 *rec = wm.cand + 4u * (pr.y >> 24);
+				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+				if (!((hitmask >> __float_as_uint(r3.y)) & 1u)) {
+					RelF x;
+					x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
+					x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;
+					x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
+					x.S = r3.x;
+					const float4 *t1 = p.env.tri32 + 3ull * (__float_as_uint(r3.w) + pr.x);
+					const float4 *t2 = tris2 + 3ull * (pr.y & 0xffffffu);
+					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
+					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
+					maybe = tri_maybe_f32(P1, P2, P3, Q1, Q2, Q3, x);
+				}
 			}
 			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
 			unsigned mm = __ballot_sync(FULL, maybe);
 			while (mm) {
-				const int src = __ffs(mm) - 1;
+				const int from = __ffs(mm) - 1;
 				mm &= mm - 1;
-				const uint32_t t1 = __shfl_sync(FULL, pr.x, src), t2 = __shfl_sync(FULL, pr.y, src);
+				const uint32_t t1 = __shfl_sync(FULL, pr.x, from), w2 = __shfl_sync(FULL, pr.y, from);
+				const uint32_t t2 = w2 & 0xffffffu, cand = w2 >> 24;
+				const uint32_t id = wm.cand_ids[cand];
+				const unsigned src = id >> 27, e = id & 0x7ffffffu;
+				if ((hitmask >> src) & 1u) continue;
 				if (COUNT) ctr[CTR_EXACT] += 1;
-				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
+				// fp64 relative transform of this candidate, FCL's operation order
+				const DevObject &ob = p.objects[e];
+				__syncwarp();
+				if (lane < 12) {
+					double R2[9], T2[3];
+					Quat q;
+					decode_pose(link_poses + (size_t)src * rec_len * p.n_links, p.pose_format, R2, T2, q, false);
+					wm.rel[lane] = rel_element(ob, R2, T2, lane);
+				}
+				__syncwarp();
+				const uint32_t node_base1 = __float_as_uint(wm.cand[4u * cand + 3].z);
+				const uint32_t tri_base1 = __float_as_uint(wm.cand[4u * cand + 3].w);
+				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (tri_base1 + t1),
 				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 				if (hit) {
 					if (COUNT) ctr[CTR_PATH] += 1;
-					if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) return true;
+					if (exact_path_reaches(p, node_base1, tri_base1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
 				}
 			}
 			__syncwarp();
@@ -549,26 +621,38 @@ __device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevMode
 		uint2 cA = make_uint2(0u, 0u), cB = make_uint2(0u, 0u);
 		if (lane < k) {
 			const uint2 pr = wm.stack[sp + lane];
-			const float4 *n1 = nodes1 + 4ull * pr.x;
-			const float4 *n2 = nodes2 + 4ull * pr.y;
-			const float4 a0 = __ldg(n1), a1 = __ldg(n1 + 1), a2 = __ldg(n1 + 2), a3 = __ldg(n1 + 3);
-			const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), b2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
-			if (!obb_disjoint_f32(a0, a1, a2, a3, b0, b1, b2, b3, x)) {
-				const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
-				const bool l1 = link1 < 0, l2 = link2 < 0;
-				if (l1 && l2) {
-					push_leaf = true;
-					cA = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)));
-				} else {
-					push_nodes = true;
-					const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
-					const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
-					if (l2 || (!l1 && s1 > s2)) {
-						cA = make_uint2((uint32_t)link1, pr.y);
-						cB = make_uint2((uint32_t)link1 + 1u, pr.y);
+			const unsigned tag = pr.y & 0xff000000u;
+			const float4 *rec = wm.cand + 4u * (pr.y >> 24);
+			const float4 r3 = rec[3];
+			if (!((hitmask >> __float_as_uint(r3.y)) & 1u)) {
+				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+				RelF x;
+				x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
+				x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;
+				x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
+				x.S = r3.x;
+				const uint32_t b2 = pr.y & 0xffffffu;
+				const float4 *n1 = p.env.node32 + 4ull * (__float_as_uint(r3.z) + pr.x);
+				const float4 *n2 = nodes2 + 4ull * b2;
+				const float4 a0 = __ldg(n1), a1 = __ldg(n1 + 1), a2 = __ldg(n1 + 2), a3 = __ldg(n1 + 3);
+				const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), bb2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
+				if (!obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) {
+					const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
+					const bool l1 = link1 < 0, l2 = link2 < 0;
+					if (l1 && l2) {
+						push_leaf = true;
+						cA = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
 					} else {
-						cA = make_uint2(pr.x, (uint32_t)link2);
-						cB = make_uint2(pr.x, (uint32_t)link2 + 1u);
+						push_nodes = true;
+						const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
+						const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
+						if (l2 || (!l1 && s1 > s2)) {
+							cA = make_uint2((uint32_t)link1, pr.y);
+							cB = make_uint2((uint32_t)link1 + 1u, pr.y);
+						} else {
+							cA = make_uint2(pr.x, (uint32_t)link2 | tag);
+							cB = make_uint2(pr.x, ((uint32_t)link2 + 1u) | tag);
+						}
 					}
 				}
 			}
@@ -587,7 +671,7 @@ __device__ bool traverse(const KernelParams &p, const WarpMem &wm, const DevMode
 		sp += 2 * __popc(nm);
 		__syncwarp();
 	}
-	return false;
+	return hitmask;
 }
 
 template <bool COUNT>
@@ -597,11 +681,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 	const int warp = threadIdx.x >> 5;
 	unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes(p.stack_cap);
 	WarpMem wm;
+	wm.stack = reinterpret_cast<uint2 *>(base);
+	base += (size_t)p.stack_cap * 8;
 	wm.leafq = reinterpret_cast<uint2 *>(base);
-	wm.candq = reinterpret_cast<uint32_t *>(base + kLeafQueueCap * 8);
-	wm.rel = reinterpret_cast<double *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4);
-	wm.box = reinterpret_cast<double *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8);
-	wm.stack = reinterpret_cast<uint2 *>(base + kLeafQueueCap * 8 + kCandQueueCap * 4 + 16 * 8 + 6 * 32 * 8);
+	base += kLeafQueueCap * 8;
+	wm.cand = reinterpret_cast<float4 *>(base);
+	base += kCandCap * 64;
+	wm.box = reinterpret_cast<double *>(base);
+	base += 6 * 32 * 8;
+	wm.rel = reinterpret_cast<double *>(base);
+	base += 16 * 8;
+	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
+	base += kCandCap * 4;
+	wm.clq = reinterpret_cast<uint32_t *>(base);
 
 	const unsigned ppw = 1u << p.ppw_log2;
 	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
@@ -619,16 +711,18 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 		const unsigned long long pose0 = (unsigned long long)chunk << p.ppw_log2;
 		const unsigned long long my_pose = pose0 + (unsigned)lane;
 		const bool valid = (unsigned)lane < ppw && my_pose < p.n_pose_sets;
+		const unsigned validmask = __ballot_sync(FULL, valid);
 		unsigned hitmask = 0;
 
-		for (unsigned j = 0; j < p.n_links; ++j) {
+		for (unsigned j = 0; j < p.n_links && hitmask != validmask; ++j) {
 			const DevModel &m2 = p.agent.models[p.link_model[j]];
-			// ---- phase 1: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
+			const double *link_poses = p.poses + (pose0 * p.n_links + j) * rec_len;  // pose slot s: + s*rec_len*n_links
+			// ---- phase A: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
 			float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
 			if (valid) {
 				double R[9], T[3], bmin[3], bmax[3];
 				Quat q;
-				decode_pose(p.poses + (my_pose * p.n_links + j) * rec_len, p.pose_format, R, T, q, true);
+				decode_pose(link_poses + (size_t)lane * rec_len * p.n_links, p.pose_format, R, T, q, true);
 				if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
 #pragma unroll
 					for (int k = 0; k < 3; ++k) {
@@ -647,7 +741,6 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 						bmax[k] = dadd(cw[k], m2.aabb_radius);
 					}
 				}
-				// ---- broadphase: lane-per-pose walk of the threaded cluster tree (fp32, conservative) --
 #pragma unroll
 				for (int k = 0; k < 3; ++k) {
 					wm.box[k * 32 + lane] = bmin[k];
@@ -658,10 +751,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 			}
 			__syncwarp();
 			unsigned node = valid ? 0u : p.n_bp_nodes;
-			int ncand = 0;
-			for (;;) {
-				bool more = true;
-				while (ncand <= kCandQueueCap - 32) {
+			int ncl = 0, ncand = 0, nrec = 0;
+			bool more = true;
+			while (more || ncl > 0 || ncand > 0) {
+				// ---- phase B: lane-per-pose walk of the threaded cluster tree (fp32, conservative) ------
+				while (more && ncl <= kClusterQueueCap - 32) {
 					if ((hitmask >> lane) & 1u) node = p.n_bp_nodes;
 					const bool act = node < p.n_bp_nodes;
 					if (!__any_sync(FULL, act)) {
@@ -681,77 +775,85 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 					}
 					const unsigned m = __ballot_sync(FULL, leaf_hit);
 					if (m) {
-						if (leaf_hit) wm.candq[ncand + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
-						ncand += __popc(m);
+						if (leaf_hit) wm.clq[ncl + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
+						ncl += __popc(m);
 					}
 				}
 				__syncwarp();
-				// ---- drain: (pose, cluster) entries -> exact fp64 AABB::overlap per object -> narrowphase --
-				for (int c = 0; c < ncand; ++c) {
-					const unsigned ent = wm.candq[c];
+				// ---- phase C1: (pose, cluster) -> exact fp64 AABB::overlap per object -> candidate ids ---
+				int c = 0;
+				for (; c < ncl && ncand <= kCandCap - 32; ++c) {
+					const unsigned ent = wm.clq[c];
 					const unsigned src = ent >> 27, cl = ent & 0x7ffffffu;
 					if ((hitmask >> src) & 1u) continue;
-					double sb[6];
-#pragma unroll
-					for (int k = 0; k < 6; ++k) sb[k] = wm.box[k * 32 + src];
 					const unsigned eobj = cl * kClusterSize + (unsigned)lane;
 					bool ov = false;
 					if (eobj < p.n_objects) {
 						const double *bb = p.obj_aabb + 6ull * eobj;  // AABB::overlap(env, agent), closed
-						ov = !(bb[0] > sb[3] || bb[1] > sb[4] || bb[2] > sb[5] || bb[3] < sb[0] || bb[4] < sb[1] ||
-						       bb[5] < sb[2]);
+						ov = !(bb[0] > wm.box[3 * 32 + src] || bb[1] > wm.box[4 * 32 + src] || bb[2] > wm.box[5 * 32 + src] ||
+						       bb[3] < wm.box[0 * 32 + src] || bb[4] < wm.box[1 * 32 + src] || bb[5] < wm.box[2 * 32 + src]);
 					}
-					unsigned om = __ballot_sync(FULL, ov);
-					if (COUNT) ctr[CTR_CAND] += (unsigned)__popc(om);
-					while (om) {
-						const unsigned e = cl * kClusterSize + (unsigned)(__ffs(om) - 1);
-						om &= om - 1;
+					const unsigned om = __ballot_sync(FULL, ov);
+					if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (src << 27) | eobj;
+					ncand += __popc(om);
+				}
+				// keep the unprocessed tail of the cluster queue
+				if (c < ncl) {
+					const int rest = ncl - c;
+					unsigned keep0 = 0, keep1 = 0;
+					if (lane < rest) keep0 = wm.clq[c + lane];
+					if (lane + 32 < rest) keep1 = wm.clq[c + lane + 32];
+					__syncwarp();
+					if (lane < rest) wm.clq[lane] = keep0;
+					if (lane + 32 < rest) wm.clq[lane + 32] = keep1;
+					ncl = rest;
+				} else {
+					ncl = 0;
+				}
+				__syncwarp();
+				if (COUNT) ctr[CTR_CAND] += (unsigned)(ncand - nrec);
+				// ---- phase C2: one lane per new candidate: fp64 relative transform -> fp32 record ---------
+				for (int i0 = nrec; i0 < ncand; i0 += 32) {
+					const int i = i0 + lane;
+					if (i < ncand) {
+						const uint32_t id = wm.cand_ids[i];
+						const unsigned src = id >> 27, e = id & 0x7ffffffu;
 						const DevObject &ob = p.objects[e];
 						const DevModel &m1 = p.env.models[ob.model];
-						// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1); lane r*3+c -> R(r,c),
-						// lanes 9..11 -> T.  [FCL-recalled C.7]
-						__syncwarp();
-						if (lane < 12) {
-							double R2[9], T2[3];
-							Quat q;
-							decode_pose(p.poses + ((pose0 + src) * p.n_links + j) * rec_len, p.pose_format, R2, T2, q,
-							            false);
-							if (lane < 9) {
-								const int r = lane / 3, cc = lane % 3;
-								wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
-							} else {
-								const int r = lane - 9;
-								const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
-								wm.rel[lane] = ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
-							}
-						}
-						__syncwarp();
-						RelF x;
+						double R2[9], T2[3], rl[12];
+						Quat q;
+						decode_pose(link_poses + (size_t)src * rec_len * p.n_links, p.pose_format, R2, T2, q, false);
 #pragma unroll
-						for (int k = 0; k < 9; ++k) x.R[k] = (float)wm.rel[k];
+						for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
 						// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
-						float tinf = 0.0f;
+						float tf[3], tinf = 0.f;
 #pragma unroll
 						for (int r = 0; r < 3; ++r) {
-							const double tc = wm.rel[3 * r] * m2.ctr[0] + wm.rel[3 * r + 1] * m2.ctr[1] +
-							                  wm.rel[3 * r + 2] * m2.ctr[2] + wm.rel[9 + r] - m1.ctr[r];
-							x.T[r] = (float)tc;
-							tinf = fmaxf(tinf, fabsf(x.T[r]));
+							const double tc = rl[3 * r] * m2.ctr[0] + rl[3 * r + 1] * m2.ctr[1] + rl[3 * r + 2] * m2.ctr[2] +
+							                  rl[9 + r] - m1.ctr[r];
+							tf[r] = (float)tc;
+							tinf = fmaxf(tinf, fabsf(tf[r]));
 						}
-						x.Tabs1 = fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2]);
 						// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
-						x.S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
-						if (traverse<COUNT>(p, wm, m1, m2, x, lane, ctr)) {
-							hitmask |= 1u << src;
-							break;
-						}
+						const float S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
+						float4 *rec = wm.cand + 4u * i;
+						rec[0] = make_float4((float)rl[0], (float)rl[1], (float)rl[2], (float)rl[3]);
+						rec[1] = make_float4((float)rl[4], (float)rl[5], (float)rl[6], (float)rl[7]);
+						rec[2] = make_float4((float)rl[8], tf[0], tf[1], tf[2]);
+						rec[3] = make_float4(S, __uint_as_float(src), __uint_as_float(m1.node_base), __uint_as_float(m1.tri_base));
 					}
 				}
-				ncand = 0;
+				nrec = ncand;
 				__syncwarp();
-				if (!more) break;
+				// ---- phase D: merged narrowphase once the table is full or the broadphase is done -----------
+				if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
+					if (ncand > 0)
+						hitmask = traverse_all<COUNT>(p, wm, m2, ncand, hitmask, validmask, link_poses, rec_len, lane, ctr);
+					ncand = 0;
+					nrec = 0;
+					if (hitmask == validmask) break;
+				}
 			}
-			if (__ballot_sync(FULL, valid) == hitmask) break;  // every pose-set of this warp already collides
 		}
 		// ---- verdict bits ----------------------------------------------------------------------
 		if (lane == 0) {

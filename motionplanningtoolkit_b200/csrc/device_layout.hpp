@@ -14,9 +14,9 @@
 //   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.
 //   node64 : double[16] per node: FCL's OBB verbatim -- axis (9), To (3), extent (3), size =
 //            extent.sqrLength() (1).  Only read when a positive leaf pair replays FCL's path.
-//   topo   : int2 per node: (first_child, split_pos); split_pos = first_primitive + size of the left
-//            child: a primitive at position pos in primitive_indices lies in the right child iff
-//            pos >= split_pos.
+//   topo   : TopoRec (16 B) per node: (size, first_child, split_pos); split_pos = first_primitive +
+//            size of the left child: a primitive at position pos in primitive_indices lies in the right
+//            child iff pos >= split_pos.
 //   tri64  : double[9] per triangle, model coordinates verbatim (exact pass).
 //   prim_pos : uint32 per triangle: position of the primitive in FCL's primitive_indices permutation.
 //
@@ -50,6 +50,13 @@ struct DevModel {
 	uint32_t pad[2];
 };
 
+// One node of the exact-pass topology: what FCL's descent needs to walk towards a given primitive.
+struct __attribute__((aligned(16))) TopoRec {
+	double size;          // OBB::size() = extent.sqrLength(), fp64
+	int32_t first_child;  // < 0: leaf
+	int32_t split_pos;    // first_primitive + size of the left child
+};
+
 struct DevObject {
 	double R[9];     // tf1 rotation (row-major)
 	double T[3];     // tf1 translation
@@ -63,7 +70,7 @@ struct ModelPack {
 	const float4 *node32;
 	const float4 *tri32;
 	const double *node64;
-	const int2 *topo;
+	const TopoRec *topo;
 	const double *tri64;
 	const uint32_t *prim_pos;
 	const DevModel *models;
@@ -96,13 +103,16 @@ enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_
 constexpr int kClusterSize = 32;
 constexpr int kWarpsPerCta = 8;
 constexpr int kLeafQueueCap = 64;
-constexpr int kCandQueueCap = 64;
-// per-warp shared memory: leaf queue + candidate queue + fp64 relative transform + pose boxes + stack
+constexpr int kClusterQueueCap = 64;  // (pose, cluster) entries waiting for the exact AABB test
+constexpr int kCandCap = 96;          // candidate table: (pose, object) pairs traversed together (<= 256)
+// per-warp shared memory: stack + leaf queue + candidate table + pose boxes + fp64 relative transform +
+// candidate ids + cluster queue
 #ifdef __CUDACC__
 __host__ __device__
 #endif
 inline constexpr unsigned warp_smem_bytes(unsigned stack_cap) {
-	return kLeafQueueCap * 8u + kCandQueueCap * 4u + 16u * 8u + 6u * 32u * 8u + stack_cap * 8u;
+	return stack_cap * 8u + kLeafQueueCap * 8u + kCandCap * 64u + 6u * 32u * 8u + 16u * 8u + kCandCap * 4u +
+	       kClusterQueueCap * 4u;
 }
 
 // Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.

@@ -64,7 +64,7 @@ struct HostPack {
 	std::vector<float4> node32;
 	std::vector<float4> tri32;
 	std::vector<double> node64;
-	std::vector<int2> topo;
+	std::vector<TopoRec> topo;
 	std::vector<double> tri64;
 	std::vector<uint32_t> prim_pos;
 	std::vector<DevModel> models;
@@ -79,7 +79,7 @@ struct HostPack {
 		if ((node32.size() / 4) % 2 == 0) {  // node_base must be odd: pad one node slot
 			for (int k = 0; k < 4; ++k) node32.push_back(make_float4(0, 0, 0, 0));
 			for (int k = 0; k < 16; ++k) node64.push_back(0.0);
-			topo.push_back(make_int2(0, 0));
+			topo.push_back(TopoRec{0.0, 0, 0});
 		}
 		m.node_base = (uint32_t)(node32.size() / 4);
 		m.tri_base = (uint32_t)(tri32.size() / 3);
@@ -129,7 +129,7 @@ struct HostPack {
 
 			int split = 0;
 			if (link >= 0) split = b.first_primitive[i] + b.num_primitives[link];
-			topo.push_back(make_int2(link, split));
+			topo.push_back(TopoRec{E[0] * E[0] + E[1] * E[1] + E[2] * E[2], link, split});
 		}
 		const uint32_t nt = b.num_tris();
 		const size_t pos_base = prim_pos.size();
@@ -257,7 +257,7 @@ struct DevBuf {
 struct DevPack {
 	DevBuf<float4> node32, tri32;
 	DevBuf<double> node64, tri64;
-	DevBuf<int2> topo;
+	DevBuf<TopoRec> topo;
 	DevBuf<uint32_t> prim_pos;
 	DevBuf<DevModel> models;
 	cudaError_t upload(const HostPack &h, cudaStream_t s) {
@@ -395,6 +395,8 @@ int check_ready(mptcc_ctx *ctx) {
 	if (!ctx->env_set) return fail(ctx, MPTCC_ERR_STATE, "environment not set (mptcc_set_environment)");
 	if (!ctx->agent_set) return fail(ctx, MPTCC_ERR_STATE, "agent not set (mptcc_set_agent)");
 	if (ctx->devs.empty()) return fail(ctx, MPTCC_ERR_NO_DEVICE, "context has no CUDA device");
+	if (ctx->env_h.max_depth > 64 || ctx->agent_h.max_depth > 64)
+		return fail(ctx, MPTCC_ERR_LIMIT, "BVH deeper than 64 levels is not supported by the exact path replay");
 	const unsigned guard = stack_guard_for(ctx);
 	if ((long)guard + 64 > ctx->opt_stack)
 		return fail(ctx, MPTCC_ERR_LIMIT, "BVH depth exceeds the traversal stack head-room; raise option stack_entries");
@@ -577,6 +579,7 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 			ctx->link_model_h.push_back(it->second);
 			continue;
 		}
+		if (m.nt >= (1u << 23)) return fail(ctx, MPTCC_ERR_LIMIT, "agent link meshes are limited to 2^23 triangles");
 		HostBvh b;
 		if (!build_bvh(m.xyz, m.nv, m.tri, m.nt, b))
 			return fail(ctx, MPTCC_ERR_INVALID, "agent link " + std::to_string(j) + " has an empty mesh");
