@@ -53,44 +53,50 @@ __device__ __forceinline__ Quat qmul(const Quat &a, const Quat &b) {
 	return r;
 }
 
-// [FCL-recalled] Quaternion3f::fromRotation (only what CollisionObject::computeAABB needs)
+// [FCL-recalled] Quaternion3f::fromRotation.  FCL branches on the trace and then on the largest
+// diagonal entry; every branch is "root = sqrt(s); one component = 0.5 root; the other three =
+// (sum or difference of two off-diagonal entries) * (0.5 / root)".  The operands are selected first so
+// that the warp runs ONE sqrt and ONE division (both are long fp64 routines) instead of diverging.
 __device__ __forceinline__ Quat quat_from_rotation(const double *R) {
-	Quat q;
 	const double trace = dadd(dadd(R[0], R[4]), R[8]);
-	if (trace > 0.0) {
-		double root = sqrt(dadd(trace, 1.0));
-		q.w = dmul(0.5, root);
-		root = 0.5 / root;
-		q.x = dmul(dsub(R[7], R[5]), root);
-		q.y = dmul(dsub(R[2], R[6]), root);
-		q.z = dmul(dsub(R[3], R[1]), root);
+	const bool tpos = trace > 0.0;
+	int i = 0;
+	if (R[4] > R[0]) i = 1;
+	if (R[8] > (i == 1 ? R[4] : R[0])) i = 2;
+	// else-branch: s = ((Rii - Rjj) - Rkk) + 1 with (j,k) = (i+1, i+2) mod 3
+	const double dii = i == 0 ? R[0] : (i == 1 ? R[4] : R[8]);
+	const double djj = i == 0 ? R[4] : (i == 1 ? R[8] : R[0]);
+	const double dkk = i == 0 ? R[8] : (i == 1 ? R[0] : R[4]);
+	const double s = tpos ? dadd(trace, 1.0) : dadd(dsub(dsub(dii, djj), dkk), 1.0);
+	double root = sqrt(s);
+	const double half = dmul(0.5, root);
+	root = 0.5 / root;
+	// trace > 0 : x=(R21-R12) y=(R02-R20) z=(R10-R01)          (w = half)
+	// i == 0    : w=(R21-R12) y=(R10+R01) z=(R20+R02)          (x = half)
+	// i == 1    : w=(R02-R20) z=(R21+R12) x=(R01+R10)          (y = half)
+	// i == 2    : w=(R10-R01) x=(R02+R20) y=(R12+R21)          (z = half)
+	const double d21 = dsub(R[7], R[5]), d02 = dsub(R[2], R[6]), d10 = dsub(R[3], R[1]);
+	Quat q;
+	if (tpos) {
+		q.w = half;
+		q.x = dmul(d21, root);
+		q.y = dmul(d02, root);
+		q.z = dmul(d10, root);
+	} else if (i == 0) {
+		q.x = half;
+		q.w = dmul(d21, root);
+		q.y = dmul(dadd(R[3], R[1]), root);
+		q.z = dmul(dadd(R[6], R[2]), root);
+	} else if (i == 1) {
+		q.y = half;
+		q.w = dmul(d02, root);
+		q.z = dmul(dadd(R[7], R[5]), root);
+		q.x = dmul(dadd(R[1], R[3]), root);
 	} else {
-		// i = argmax of the diagonal (FCL's "next[]" walk), spelled out so that R stays in registers
-		int i = 0;
-		if (R[4] > R[0]) i = 1;
-		if (R[8] > (i == 1 ? R[4] : R[0])) i = 2;
-		if (i == 0) {  // j = 1, k = 2
-			double root = sqrt(dadd(dsub(dsub(R[0], R[4]), R[8]), 1.0));
-			q.x = dmul(0.5, root);
-			root = 0.5 / root;
-			q.w = dmul(dsub(R[7], R[5]), root);
-			q.y = dmul(dadd(R[3], R[1]), root);
-			q.z = dmul(dadd(R[6], R[2]), root);
-		} else if (i == 1) {  // j = 2, k = 0
-			double root = sqrt(dadd(dsub(dsub(R[4], R[8]), R[0]), 1.0));
-			q.y = dmul(0.5, root);
-			root = 0.5 / root;
-			q.w = dmul(dsub(R[2], R[6]), root);
-			q.z = dmul(dadd(R[7], R[5]), root);
-			q.x = dmul(dadd(R[1], R[3]), root);
-		} else {  // j = 0, k = 1
-			double root = sqrt(dadd(dsub(dsub(R[8], R[0]), R[4]), 1.0));
-			q.z = dmul(0.5, root);
-			root = 0.5 / root;
-			q.w = dmul(dsub(R[3], R[1]), root);
-			q.x = dmul(dadd(R[2], R[6]), root);
-			q.y = dmul(dadd(R[5], R[7]), root);
-		}
+		q.z = half;
+		q.w = dmul(d10, root);
+		q.x = dmul(dadd(R[2], R[6]), root);
+		q.y = dmul(dadd(R[5], R[7]), root);
 	}
 	return q;
 }
@@ -303,45 +309,29 @@ __device__ __noinline__ bool exact_tri_intersect_warp(const double *__restrict__
 // (prim1, prim2) and evaluates every OBB test on the way in fp64 [FCL-recalled C.7, C.8].
 // Returns true iff none of them reports "disjoint", i.e. iff FCL's traversal reaches that leaf pair.
 //
-// The root-to-leaf ancestor chain of each tree depends only on the primitive's position, so both
-// chains are walked at the same time (one dependent load per level, not per path step); lane l keeps
-// level l (and l+32) of both chains.  The FCL path is the merge of the two chains under the
-// firstOverSecond rule and is then formed with shuffles; its pairs are tested 32 at a time.
-__device__ __noinline__ bool exact_path_reaches(const KernelParams &p, uint32_t node_base1, uint32_t tri_base1,
-                                                const DevModel &m2, const double *__restrict__ rel, uint32_t prim1,
-                                                uint32_t prim2, int lane) {
-	const uint32_t pos1 = p.env.prim_pos[tri_base1 + prim1];
-	const uint32_t pos2 = p.agent.prim_pos[m2.tri_base + prim2];
-	const TopoRec *__restrict__ topo1 = p.env.topo + node_base1;
-	const TopoRec *__restrict__ topo2 = p.agent.topo + m2.node_base;
-	const double *__restrict__ n64a = p.env.node64 + 16ull * node_base1;
+// The root-to-leaf chain of each tree depends only on the primitive and is precomputed (ModelPack::anc):
+// lane l fetches level l (and l+32) of both chains and the fp64 size of those nodes -- two dependent
+// loads in total.  The FCL path is the merge of the two chains under the firstOverSecond rule; it is
+// formed with shuffles and its pairs are tested 32 at a time.
+__device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const DevModel &m1, const DevModel &m2,
+                                                const double *__restrict__ rel, uint32_t prim1, uint32_t prim2,
+                                                int lane) {
+	const uint32_t *__restrict__ anc1 = p.env.anc + m1.anc_base + (unsigned long long)prim1 * m1.depth;
+	const uint32_t *__restrict__ anc2 = p.agent.anc + m2.anc_base + (unsigned long long)prim2 * m2.depth;
+	const double *__restrict__ n64a = p.env.node64 + 16ull * m1.node_base;
 	const double *__restrict__ n64b = p.agent.node64 + 16ull * m2.node_base;
-
-	uint32_t a = 0, b = 0;
-	int d1 = -1, d2 = -1;  // level of the leaf in each chain
-	uint32_t na0 = 0, na1 = 0, nb0 = 0, nb1 = 0;
-	double sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0;
-	for (int lvl = 0; lvl < 64 && (d1 < 0 || d2 < 0); ++lvl) {
-		TopoRec r1, r2;
-		if (d1 < 0) r1 = topo1[a];
-		if (d2 < 0) r2 = topo2[b];
-		const bool mine = (lvl & 31) == lane;
-		if (d1 < 0) {
-			if (mine) {
-				if (lvl < 32) { na0 = a; sa0 = r1.size; } else { na1 = a; sa1 = r1.size; }
-			}
-			if (r1.first_child < 0) d1 = lvl;
-			else a = (uint32_t)r1.first_child + (pos1 >= (uint32_t)r1.split_pos ? 1u : 0u);
-		}
-		if (d2 < 0) {
-			if (mine) {
-				if (lvl < 32) { nb0 = b; sb0 = r2.size; } else { nb1 = b; sb1 = r2.size; }
-			}
-			if (r2.first_child < 0) d2 = lvl;
-			else b = (uint32_t)r2.first_child + (pos2 >= (uint32_t)r2.split_pos ? 1u : 0u);
-		}
-	}
-	if (d1 < 0 || d2 < 0) return true;  // deeper than 64 levels: refused at scene set-up (MPTCC_ERR_LIMIT)
+	const uint32_t NONE = 0xffffffffu;
+	const uint32_t na0 = (uint32_t)lane < m1.depth ? anc1[lane] : NONE;
+	const uint32_t na1 = (uint32_t)lane + 32u < m1.depth ? anc1[lane + 32] : NONE;
+	const uint32_t nb0 = (uint32_t)lane < m2.depth ? anc2[lane] : NONE;
+	const uint32_t nb1 = (uint32_t)lane + 32u < m2.depth ? anc2[lane + 32] : NONE;
+	const double sa0 = na0 != NONE ? n64a[16ull * na0 + 15] : 0.0;
+	const double sa1 = na1 != NONE ? n64a[16ull * na1 + 15] : 0.0;
+	const double sb0 = nb0 != NONE ? n64b[16ull * nb0 + 15] : 0.0;
+	const double sb1 = nb1 != NONE ? n64b[16ull * nb1 + 15] : 0.0;
+	// level of the leaf in each chain
+	const int d1 = __popc(__ballot_sync(FULL, na0 != NONE)) + __popc(__ballot_sync(FULL, na1 != NONE)) - 1;
+	const int d2 = __popc(__ballot_sync(FULL, nb0 != NONE)) + __popc(__ballot_sync(FULL, nb1 != NONE)) - 1;
 
 	int i = 0, j = 0, k = 0;
 	uint32_t my1 = 0, my2 = 0;
@@ -517,7 +507,6 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 // warp-cooperative traversal of one (environment object, agent link, pose) candidate
 // ------------------------------------------------------------------------------------------------
 struct WarpMem {
-	uint2 *stack;        // [stack_cap]   (env node, agent node | cand << 24)
 	uint2 *leafq;        // [kLeafQueueCap] (env prim, agent prim | cand << 24)
 	float4 *cand;        // [kCandCap][4] candidate records: R(9) T(3) S src node_base1 tri_base1
 	uint32_t *cand_ids;  // [kCandCap]    pose slot << 27 | object
@@ -538,9 +527,13 @@ __device__ __forceinline__ double rel_element(const DevObject &ob, const double 
 	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
 }
 
-// Merged traversal of all `ncand` candidates of the warp's pose chunk: one stack, every entry tagged
-// with its candidate; a lane fetches its entry's transform from the candidate table.  Returns the
-// updated hit mask (bit = pose slot).
+// Narrowphase of all `ncand` candidates of the warp's pose chunk.  Every lane runs FCL's depth-first
+// descent for one candidate at a time on a private stack (local memory, ring buffer); a lane whose
+// stack runs empty takes the next unstarted candidate, and once those are gone it steals the bottom
+// (= largest pending subtree) entry of a lane that has at least two -- all warp-synchronously, with
+// ballots and shuffles only.  Leaf pairs go to a shared queue and are tested 32 at a time.  Depth-first
+// order per candidate is what lets a colliding pose stop after about as many tests as FCL needs.
+// Returns the updated hit mask (bit = pose slot).
 template <bool COUNT>
 __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const DevModel &m2, int ncand,
                                  unsigned hitmask, unsigned validmask, const double *link_poses, unsigned rec_len,
@@ -548,16 +541,55 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
 	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
 	const unsigned lt = (1u << lane) - 1u;
-	const int wide_limit = (int)p.stack_cap - (int)p.stack_guard;
+	constexpr unsigned M = kLaneStackCap - 1;
 
-	int sp = ncand, lq = 0;
-	for (int i = lane; i < ncand; i += 32) wm.stack[i] = make_uint2(0u, (unsigned)(ncand - 1 - i) << 24);
-	__syncwarp();
+	uint2 stk[kLaneStackCap];
+	unsigned top = 0, bot = 0;  // ring buffer: entries [bot, top) = pending right siblings
+	uint2 cur = make_uint2(0u, 0u);
+	bool has = false;           // `cur` is the pair this lane tests next (top of its logical stack)
+	int qhead = 0, lq = 0;
 
-	while (sp > 0 || lq > 0) {
-		if (hitmask == validmask) break;  // every pose-set of the chunk already collides
-		if (lq >= 32 || sp == 0) {
-			// ---- leaf phase: up to 32 triangle pairs -------------------------------------------
+	while (hitmask != validmask) {
+		if (!has && top != bot) {
+			cur = stk[--top & M];
+			has = true;
+		}
+		// ---- 1. idle lanes start the next unstarted candidates --------------------------------------
+		unsigned im = __ballot_sync(FULL, !has);
+		if (im && qhead < ncand) {
+			const int c = qhead + __popc(im & lt);
+			if (!has && c < ncand) {
+				cur = make_uint2(0u, (unsigned)c << 24);
+				has = true;
+			}
+			qhead += __popc(im);
+			im = __ballot_sync(FULL, !has);
+		}
+		// ---- 2. ... or steal the bottom entry (largest pending subtree) of a busy lane ------------------
+		if (im && qhead >= ncand) {
+			const unsigned dm = __ballot_sync(FULL, has && top != bot);
+			if (dm) {
+				const int n_thieves = __popc(im), n_donors = __popc(dm);
+				const int r = __popc(im & lt);
+				const bool thief = !has && r < n_donors;
+				const int from = thief ? (int)__fns(dm, 0, r + 1) : lane;
+				const bool robbed = ((dm >> lane) & 1u) && __popc(dm & lt) < n_thieves;
+				uint2 e = make_uint2(0u, 0u);
+				if (robbed) e = stk[bot++ & M];
+				e.x = __shfl_sync(FULL, e.x, from);
+				e.y = __shfl_sync(FULL, e.y, from);
+				if (thief) {
+					cur = e;
+					has = true;
+				}
+			}
+		}
+		const bool idle = !has;
+		const unsigned am = __ballot_sync(FULL, !idle);
+		if (am == 0u && lq == 0) break;
+
+		if (lq >= 32 || am == 0u) {
+			// ---- 3. leaf phase: up to 32 triangle pairs -------------------------------------------------
 			const int k = lq < 32 ? lq : 32;
 			lq -= k;
 			bool maybe = false;
@@ -600,31 +632,30 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 					wm.rel[lane] = rel_element(ob, R2, T2, lane);
 				}
 				__syncwarp();
-				const uint32_t node_base1 = __float_as_uint(wm.cand[4u * cand + 3].z);
-				const uint32_t tri_base1 = __float_as_uint(wm.cand[4u * cand + 3].w);
-				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (tri_base1 + t1),
+				const DevModel &m1 = p.env.models[ob.model];
+				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
 				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 				if (hit) {
 					if (COUNT) ctr[CTR_PATH] += 1;
-					if (exact_path_reaches(p, node_base1, tri_base1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
+					if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
 				}
 			}
 			__syncwarp();
 			continue;
 		}
-		// ---- node phase: pop up to 32 pairs, test, push children of the survivors ---------------
-		int k = sp < 32 ? sp : 32;
-		const int room = wide_limit - sp;  // wide mode keeps sp <= wide_limit; else depth-first
-		if (k > room) k = room < 1 ? 1 : room;
-		sp -= k;
-		bool push_leaf = false, push_nodes = false;
-		uint2 cA = make_uint2(0u, 0u), cB = make_uint2(0u, 0u);
-		if (lane < k) {
-			const uint2 pr = wm.stack[sp + lane];
+		// ---- 4. node step: every busy lane tests its current pair; on overlap it keeps the left child
+		//         as the next current pair and stacks the right one (FCL visits left first) -------------
+		bool push_leaf = false;
+		uint2 leaf = make_uint2(0u, 0u);
+		if (has) {
+			const uint2 pr = cur;
+			has = false;
 			const unsigned tag = pr.y & 0xff000000u;
 			const float4 *rec = wm.cand + 4u * (pr.y >> 24);
 			const float4 r3 = rec[3];
-			if (!((hitmask >> __float_as_uint(r3.y)) & 1u)) {
+			if ((hitmask >> __float_as_uint(r3.y)) & 1u) {
+				top = bot;  // this lane's stack holds one candidate only, and its pose-set already collides
+			} else {
 				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
 				RelF x;
 				x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
@@ -632,43 +663,44 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 				x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
 				x.S = r3.x;
 				const uint32_t b2 = pr.y & 0xffffffu;
-				const float4 *n1 = p.env.node32 + 4ull * (__float_as_uint(r3.z) + pr.x);
+				const float4 *nodes1 = p.env.node32 + 4ull * __float_as_uint(r3.z);
+				const float4 *n1 = nodes1 + 4ull * pr.x;
 				const float4 *n2 = nodes2 + 4ull * b2;
 				const float4 a0 = __ldg(n1), a1 = __ldg(n1 + 1), a2 = __ldg(n1 + 2), a3 = __ldg(n1 + 3);
 				const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), bb2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
+				const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
+				const bool l1 = link1 < 0, l2 = link2 < 0;
+				const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
+				const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
+				const bool first = l2 || (!l1 && s1 > s2);  // descend the environment tree
+				if (!(l1 && l2)) {
+					// the children (one 128-byte line) are needed next if the boxes overlap: start the fetch now
+					const float4 *ch = first ? nodes1 + 4ull * (uint32_t)link1 : nodes2 + 4ull * (uint32_t)link2;
+					asm volatile("prefetch.global.L1 [%0];" ::"l"(ch));
+				}
 				if (!obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) {
-					const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
-					const bool l1 = link1 < 0, l2 = link2 < 0;
 					if (l1 && l2) {
 						push_leaf = true;
-						cA = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
+						leaf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
 					} else {
-						push_nodes = true;
-						const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
-						const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
-						if (l2 || (!l1 && s1 > s2)) {
-							cA = make_uint2((uint32_t)link1, pr.y);
-							cB = make_uint2((uint32_t)link1 + 1u, pr.y);
+						uint2 right;
+						if (first) {
+							cur = make_uint2((uint32_t)link1, pr.y);
+							right = make_uint2((uint32_t)link1 + 1u, pr.y);
 						} else {
-							cA = make_uint2(pr.x, (uint32_t)link2 | tag);
-							cB = make_uint2(pr.x, ((uint32_t)link2 + 1u) | tag);
+							cur = make_uint2(pr.x, (uint32_t)link2 | tag);
+							right = make_uint2(pr.x, ((uint32_t)link2 + 1u) | tag);
 						}
+						has = true;
+						stk[top++ & M] = right;
 					}
 				}
 			}
 		}
-		if (COUNT) ctr[CTR_BV] += (unsigned)k;
-		__syncwarp();
+		if (COUNT) ctr[CTR_BV] += (unsigned)__popc(am);
 		const unsigned lm = __ballot_sync(FULL, push_leaf);
-		const unsigned nm = __ballot_sync(FULL, push_nodes);
-		if (push_leaf) wm.leafq[lq + __popc(lm & lt)] = cA;
-		if (push_nodes) {
-			const int at = sp + 2 * __popc(nm & lt);
-			wm.stack[at] = cB;      // right child below ...
-			wm.stack[at + 1] = cA;  // ... left child on top (visited first, like FCL)
-		}
+		if (push_leaf) wm.leafq[lq + __popc(lm & lt)] = leaf;
 		lq += __popc(lm);
-		sp += 2 * __popc(nm);
 		__syncwarp();
 	}
 	return hitmask;
@@ -679,10 +711,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
-	unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes(p.stack_cap);
+	unsigned char *base = smem_raw + (size_t)warp * warp_smem_bytes();
 	WarpMem wm;
-	wm.stack = reinterpret_cast<uint2 *>(base);
-	base += (size_t)p.stack_cap * 8;
 	wm.leafq = reinterpret_cast<uint2 *>(base);
 	base += kLeafQueueCap * 8;
 	wm.cand = reinterpret_cast<float4 *>(base);
@@ -781,22 +811,30 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 				}
 				__syncwarp();
 				// ---- phase C1: (pose, cluster) -> exact fp64 AABB::overlap per object -> candidate ids ---
+				// 32 / kClusterSize queue entries per iteration: lane -> (entry, object of the cluster)
+				constexpr int kPer = 32 / kClusterSize;
 				int c = 0;
-				for (; c < ncl && ncand <= kCandCap - 32; ++c) {
-					const unsigned ent = wm.clq[c];
-					const unsigned src = ent >> 27, cl = ent & 0x7ffffffu;
-					if ((hitmask >> src) & 1u) continue;
-					const unsigned eobj = cl * kClusterSize + (unsigned)lane;
+				for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
+					const int idx = c + lane / kClusterSize;
 					bool ov = false;
-					if (eobj < p.n_objects) {
-						const double *bb = p.obj_aabb + 6ull * eobj;  // AABB::overlap(env, agent), closed
-						ov = !(bb[0] > wm.box[3 * 32 + src] || bb[1] > wm.box[4 * 32 + src] || bb[2] > wm.box[5 * 32 + src] ||
-						       bb[3] < wm.box[0 * 32 + src] || bb[4] < wm.box[1 * 32 + src] || bb[5] < wm.box[2 * 32 + src]);
+					unsigned src = 0, eobj = 0;
+					if (idx < ncl) {
+						const unsigned ent = wm.clq[idx];
+						src = ent >> 27;
+						eobj = (ent & 0x7ffffffu) * kClusterSize + (unsigned)(lane % kClusterSize);
+						if (!((hitmask >> src) & 1u)) {
+							const double *bb = p.obj_aabb + eobj;  // AABB::overlap(env, agent), closed intervals
+							const unsigned st = p.n_objects_pad;
+							ov = !(bb[0] > wm.box[3 * 32 + src] || bb[st] > wm.box[4 * 32 + src] ||
+							       bb[2 * st] > wm.box[5 * 32 + src] || bb[3 * st] < wm.box[0 * 32 + src] ||
+							       bb[4 * st] < wm.box[1 * 32 + src] || bb[5 * st] < wm.box[2 * 32 + src]);
+						}
 					}
 					const unsigned om = __ballot_sync(FULL, ov);
 					if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (src << 27) | eobj;
 					ncand += __popc(om);
 				}
+				if (c > ncl) c = ncl;
 				// keep the unprocessed tail of the cluster queue
 				if (c < ncl) {
 					const int rest = ncl - c;
@@ -871,9 +909,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 
 }  // namespace
 
-int collide_max_ctas_per_sm(unsigned stack_cap, bool count) {
+int collide_max_ctas_per_sm(bool count) {
 	int n = 0;
-	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes(stack_cap);
+	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes();
 	cudaError_t e;
 	if (count) {
 		cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -890,7 +928,7 @@ int collide_max_ctas_per_sm(unsigned stack_cap, bool count) {
 }
 
 int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream) {
-	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes(p.stack_cap);
+	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes();
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
 	cudaError_t e;
 	if (count) {

@@ -14,11 +14,10 @@
 //   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.
 //   node64 : double[16] per node: FCL's OBB verbatim -- axis (9), To (3), extent (3), size =
 //            extent.sqrLength() (1).  Only read when a positive leaf pair replays FCL's path.
-//   topo   : TopoRec (16 B) per node: (size, first_child, split_pos); split_pos = first_primitive +
-//            size of the left child: a primitive at position pos in primitive_indices lies in the right
-//            child iff pos >= split_pos.
+//   anc    : uint32[depth] per triangle: the root-to-leaf chain of node ids that ends at the leaf holding
+//            that primitive (unused levels = 0xffffffff); depth = DevModel::depth.  Lets the exact pass
+//            fetch a whole ancestor chain with one coalesced load instead of walking the tree.
 //   tri64  : double[9] per triangle, model coordinates verbatim (exact pass).
-//   prim_pos : uint32 per triangle: position of the primitive in FCL's primitive_indices permutation.
 //
 // Broadphase tree (bp_nodes): the objects are sorted along a Morton curve and cut into clusters of
 // kClusterSize consecutive objects; a binary tree over the cluster sequence is stored in pre-order
@@ -47,14 +46,7 @@ struct DevModel {
 	double aabb_radius;
 	float r2;              // max |v - ctr|_2 over the vertices, rounded up
 	float rinf;            // max |v - ctr|_inf over the vertices, rounded up
-	uint32_t pad[2];
-};
-
-// One node of the exact-pass topology: what FCL's descent needs to walk towards a given primitive.
-struct __attribute__((aligned(16))) TopoRec {
-	double size;          // OBB::size() = extent.sqrLength(), fp64
-	int32_t first_child;  // < 0: leaf
-	int32_t split_pos;    // first_primitive + size of the left child
+	unsigned long long anc_base;  // first word of this model's ancestor chains in ModelPack::anc
 };
 
 struct DevObject {
@@ -70,9 +62,8 @@ struct ModelPack {
 	const float4 *node32;
 	const float4 *tri32;
 	const double *node64;
-	const TopoRec *topo;
 	const double *tri64;
-	const uint32_t *prim_pos;
+	const uint32_t *anc;
 	const DevModel *models;
 };
 
@@ -80,7 +71,9 @@ struct KernelParams {
 	ModelPack env;    // models referenced by DevObject::model
 	ModelPack agent;  // models referenced by link_model[]
 	const DevObject *objects;    // in broadphase (Morton-cluster) order
-	const double *obj_aabb;      // [n_objects][6] world AABB min xyz, max xyz (exact fp64), same order
+	const double *obj_aabb;      // [6][n_objects_pad] world AABB min xyz, max xyz (exact fp64), component-major,
+	                             // same order, padded with empty boxes to a multiple of kClusterSize
+	uint32_t n_objects_pad;
 	const float4 *bp_nodes;      // broadphase tree, 2 float4 per node (see below)
 	uint32_t n_bp_nodes;
 	const uint32_t *link_model;  // [n_links] agent-pack model id of link j
@@ -92,31 +85,30 @@ struct KernelParams {
 	unsigned long long n_pose_sets;
 	uint32_t *verdict_bits;
 	uint32_t *work_counter;
-	uint32_t stack_cap;    // entries per warp
-	uint32_t stack_guard;  // head-room kept for the depth-first fall-back (>= depth1 + depth2 + 2)
 	unsigned long long *counters;  // [6] or nullptr
 };
 
 // index of the counters in KernelParams::counters
 enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_N = 5 };
 
-constexpr int kClusterSize = 32;
+constexpr int kClusterSize = 8;
 constexpr int kWarpsPerCta = 8;
 constexpr int kLeafQueueCap = 64;
 constexpr int kClusterQueueCap = 64;  // (pose, cluster) entries waiting for the exact AABB test
+constexpr int kLaneStackCap = 64;     // per-lane depth-first stack (local memory); needs depth1 + depth2 + 2 <= 64
 constexpr int kCandCap = 96;          // candidate table: (pose, object) pairs traversed together (<= 256)
-// per-warp shared memory: stack + leaf queue + candidate table + pose boxes + fp64 relative transform +
+// per-warp shared memory: leaf queue + candidate table + pose boxes + fp64 relative transform +
 // candidate ids + cluster queue
 #ifdef __CUDACC__
 __host__ __device__
 #endif
-inline constexpr unsigned warp_smem_bytes(unsigned stack_cap) {
-	return stack_cap * 8u + kLeafQueueCap * 8u + kCandCap * 64u + 6u * 32u * 8u + 16u * 8u + kCandCap * 4u +
+inline constexpr unsigned warp_smem_bytes() {
+	return kLeafQueueCap * 8u + kCandCap * 64u + 6u * 32u * 8u + 16u * 8u + kCandCap * 4u +
 	       kClusterQueueCap * 4u;
 }
 
 // Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.
 int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
-int collide_max_ctas_per_sm(unsigned stack_cap, bool count);
+int collide_max_ctas_per_sm(bool count);
 
 }  // namespace mptcc

@@ -64,9 +64,8 @@ struct HostPack {
 	std::vector<float4> node32;
 	std::vector<float4> tri32;
 	std::vector<double> node64;
-	std::vector<TopoRec> topo;
 	std::vector<double> tri64;
-	std::vector<uint32_t> prim_pos;
+	std::vector<uint32_t> anc;
 	std::vector<DevModel> models;
 	uint32_t max_depth = 0;
 
@@ -79,7 +78,6 @@ struct HostPack {
 		if ((node32.size() / 4) % 2 == 0) {  // node_base must be odd: pad one node slot
 			for (int k = 0; k < 4; ++k) node32.push_back(make_float4(0, 0, 0, 0));
 			for (int k = 0; k < 16; ++k) node64.push_back(0.0);
-			topo.push_back(TopoRec{0.0, 0, 0});
 		}
 		m.node_base = (uint32_t)(node32.size() / 4);
 		m.tri_base = (uint32_t)(tri32.size() / 3);
@@ -127,14 +125,28 @@ struct HostPack {
 			for (int k = 0; k < 3; ++k) node64.push_back(E[k]);
 			node64.push_back(E[0] * E[0] + E[1] * E[1] + E[2] * E[2]);  // Vec3f::sqrLength, OBB::size()
 
-			int split = 0;
-			if (link >= 0) split = b.first_primitive[i] + b.num_primitives[link];
-			topo.push_back(TopoRec{E[0] * E[0] + E[1] * E[1] + E[2] * E[2], link, split});
 		}
 		const uint32_t nt = b.num_tris();
-		const size_t pos_base = prim_pos.size();
-		prim_pos.resize(pos_base + nt);
-		for (uint32_t i = 0; i < nt; ++i) prim_pos[pos_base + b.primitive_indices[i]] = i;
+		// ancestor chains: anc[anc_base + prim * depth + level] = node id at that level of the path to prim
+		m.anc_base = anc.size();
+		{
+			std::vector<int32_t> parent(nn, -1);
+			for (uint32_t i = 0; i < nn; ++i)
+				if (b.first_child[i] >= 0) {
+					parent[b.first_child[i]] = (int32_t)i;
+					parent[b.first_child[i] + 1] = (int32_t)i;
+				}
+			anc.resize(anc.size() + (size_t)nt * b.depth, 0xffffffffu);
+			std::vector<uint32_t> chain;
+			for (uint32_t i = 0; i < nn; ++i) {
+				if (b.first_child[i] >= 0) continue;
+				const uint32_t prim = (uint32_t)(-(b.first_child[i] + 1));
+				chain.clear();
+				for (int32_t v = (int32_t)i; v >= 0; v = parent[v]) chain.push_back((uint32_t)v);
+				uint32_t *dst = &anc[m.anc_base + (size_t)prim * b.depth];
+				for (size_t l = 0; l < chain.size(); ++l) dst[l] = chain[chain.size() - 1 - l];
+			}
+		}
 		for (uint32_t t = 0; t < nt; ++t) {
 			for (int c = 0; c < 3; ++c) {
 				const double *v = &b.xyz[3 * (size_t)b.tri[3 * (size_t)t + c]];
@@ -257,8 +269,7 @@ struct DevBuf {
 struct DevPack {
 	DevBuf<float4> node32, tri32;
 	DevBuf<double> node64, tri64;
-	DevBuf<TopoRec> topo;
-	DevBuf<uint32_t> prim_pos;
+	DevBuf<uint32_t> anc;
 	DevBuf<DevModel> models;
 	cudaError_t upload(const HostPack &h, cudaStream_t s) {
 		cudaError_t e;
@@ -266,18 +277,16 @@ struct DevPack {
 		if ((e = tri32.upload(h.tri32, s)) != cudaSuccess) return e;
 		if ((e = node64.upload(h.node64, s)) != cudaSuccess) return e;
 		if ((e = tri64.upload(h.tri64, s)) != cudaSuccess) return e;
-		if ((e = topo.upload(h.topo, s)) != cudaSuccess) return e;
-		if ((e = prim_pos.upload(h.prim_pos, s)) != cudaSuccess) return e;
+		if ((e = anc.upload(h.anc, s)) != cudaSuccess) return e;
 		return models.upload(h.models, s);
 	}
-	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, topo.p, tri64.p, prim_pos.p, models.p}; }
+	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, tri64.p, anc.p, models.p}; }
 	void release() {
 		node32.release();
 		tri32.release();
 		node64.release();
 		tri64.release();
-		topo.release();
-		prim_pos.release();
+		anc.release();
 		models.release();
 	}
 };
@@ -315,12 +324,10 @@ struct mptcc_ctx {
 	std::string err;
 	bool count = false;
 	long opt_ppw = 0;           // 0 = auto
-	long opt_stack = 512;       // stack entries per warp
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
 	long opt_sub_batch = 1 << 18;
 	mptcc_counters ctr{};
 	int ctas_per_sm_cached = -1;
-	long ctas_cached_stack = -1;
 	bool ctas_cached_count = false;
 };
 
@@ -349,9 +356,8 @@ int cuda_fail(mptcc_ctx *c, cudaError_t e, const char *what) {
 unsigned stack_guard_for(const mptcc_ctx *c) { return c->env_h.max_depth + c->agent_h.max_depth + 2; }
 
 int grid_for(mptcc_ctx *ctx, const Device &d) {
-	if (ctx->ctas_per_sm_cached < 0 || ctx->ctas_cached_stack != ctx->opt_stack || ctx->ctas_cached_count != ctx->count) {
-		ctx->ctas_per_sm_cached = collide_max_ctas_per_sm((unsigned)ctx->opt_stack, ctx->count);
-		ctx->ctas_cached_stack = ctx->opt_stack;
+	if (ctx->ctas_per_sm_cached < 0 || ctx->ctas_cached_count != ctx->count) {
+		ctx->ctas_per_sm_cached = collide_max_ctas_per_sm(ctx->count);
 		ctx->ctas_cached_count = ctx->count;
 	}
 	int per_sm = ctx->ctas_per_sm_cached;
@@ -397,9 +403,8 @@ int check_ready(mptcc_ctx *ctx) {
 	if (ctx->devs.empty()) return fail(ctx, MPTCC_ERR_NO_DEVICE, "context has no CUDA device");
 	if (ctx->env_h.max_depth > 64 || ctx->agent_h.max_depth > 64)
 		return fail(ctx, MPTCC_ERR_LIMIT, "BVH deeper than 64 levels is not supported by the exact path replay");
-	const unsigned guard = stack_guard_for(ctx);
-	if ((long)guard + 64 > ctx->opt_stack)
-		return fail(ctx, MPTCC_ERR_LIMIT, "BVH depth exceeds the traversal stack head-room; raise option stack_entries");
+	if (stack_guard_for(ctx) > (unsigned)kLaneStackCap)
+		return fail(ctx, MPTCC_ERR_LIMIT, "BVH depths exceed the per-lane traversal stack (depth1 + depth2 + 2 <= 64)");
 	return MPTCC_OK;
 }
 
@@ -408,13 +413,12 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.agent = d.agent.view();
 	kp.objects = d.objects.p;
 	kp.obj_aabb = d.obj_aabb.p;
+	kp.n_objects_pad = (uint32_t)(ctx->obj_aabb_h.size() / 6);
 	kp.bp_nodes = d.bp_nodes.p;
 	kp.n_bp_nodes = (uint32_t)(ctx->bp_nodes_h.size() / 2);
 	kp.link_model = d.link_model.p;
 	kp.n_objects = (uint32_t)ctx->objects_h.size();
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
-	kp.stack_cap = (uint32_t)ctx->opt_stack;
-	kp.stack_guard = stack_guard_for(ctx);
 	kp.counters = ctx->count ? d.counters.p : nullptr;
 }
 
@@ -551,8 +555,13 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 		ctx->objects_h.push_back(o);
 	}
 	sort_objects_morton(ctx->objects_h);
-	ctx->obj_aabb_h.clear();
-	for (const auto &o : ctx->objects_h) ctx->obj_aabb_h.insert(ctx->obj_aabb_h.end(), o.aabb, o.aabb + 6);
+	{
+		const size_t n = ctx->objects_h.size(), np = (n + kClusterSize - 1) / kClusterSize * kClusterSize;
+		ctx->obj_aabb_h.assign(6 * np, 0.0);
+		for (size_t i = 0; i < np; ++i)
+			for (int k = 0; k < 6; ++k)  // padding: empty boxes (min = +max, max = -max) never overlap
+				ctx->obj_aabb_h[k * np + i] = i < n ? ctx->objects_h[i].aabb[k] : (k < 3 ? DBL_MAX : -DBL_MAX);
+	}
 	ctx->bp_nodes_h.clear();
 	if (!ctx->objects_h.empty()) {
 		BpBuilder bp(ctx->objects_h);
@@ -771,9 +780,6 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	if (k == "poses_per_warp") {
 		if (value < 0 || value > 32 || (value & (value - 1))) return fail(ctx, MPTCC_ERR_INVALID, "poses_per_warp: 0 or a power of two <= 32");
 		ctx->opt_ppw = value;
-	} else if (k == "stack_entries") {
-		if (value < 128 || value > 4096) return fail(ctx, MPTCC_ERR_INVALID, "stack_entries: 128..4096");
-		ctx->opt_stack = value;
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
