@@ -76,28 +76,19 @@ __device__ __forceinline__ Quat quat_from_rotation(const double *R) {
 	// i == 1    : w=(R02-R20) z=(R21+R12) x=(R01+R10)          (y = half)
 	// i == 2    : w=(R10-R01) x=(R02+R20) y=(R12+R21)          (z = half)
 	const double d21 = dsub(R[7], R[5]), d02 = dsub(R[2], R[6]), d10 = dsub(R[3], R[1]);
+	const double s01 = dadd(R[3], R[1]), s02 = dadd(R[6], R[2]), s12 = dadd(R[7], R[5]);
+	// a*b is commutative and R(j,i)+R(i,j) is symmetric in IEEE arithmetic, so the operand order of FCL's
+	// additions does not matter; only which entries are combined does.
+	const int sel = tpos ? 3 : i;
+	const double A = sel == 3 || sel == 0 ? d21 : (sel == 1 ? d02 : d10);
+	const double B = sel == 3 ? d02 : (sel == 0 ? s01 : (sel == 1 ? s12 : s02));
+	const double C = sel == 3 ? d10 : (sel == 0 ? s02 : (sel == 1 ? s01 : s12));
+	const double pa = dmul(A, root), pb = dmul(B, root), pc = dmul(C, root);
 	Quat q;
-	if (tpos) {
-		q.w = half;
-		q.x = dmul(d21, root);
-		q.y = dmul(d02, root);
-		q.z = dmul(d10, root);
-	} else if (i == 0) {
-		q.x = half;
-		q.w = dmul(d21, root);
-		q.y = dmul(dadd(R[3], R[1]), root);
-		q.z = dmul(dadd(R[6], R[2]), root);
-	} else if (i == 1) {
-		q.y = half;
-		q.w = dmul(d02, root);
-		q.z = dmul(dadd(R[7], R[5]), root);
-		q.x = dmul(dadd(R[1], R[3]), root);
-	} else {
-		q.z = half;
-		q.w = dmul(d10, root);
-		q.x = dmul(dadd(R[2], R[6]), root);
-		q.y = dmul(dadd(R[5], R[7]), root);
-	}
+	q.w = sel == 3 ? half : pa;
+	q.x = sel == 3 ? pa : (sel == 0 ? half : (sel == 1 ? pc : pb));
+	q.y = sel == 3 ? pb : (sel == 0 ? pb : (sel == 1 ? half : pc));
+	q.z = sel == 3 ? pc : (sel == 0 ? pc : (sel == 1 ? pb : half));
 	return q;
 }
 
@@ -636,8 +627,24 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
 				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 				if (hit) {
-					if (COUNT) ctr[CTR_PATH] += 1;
-					if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
+					// Path certificate.  FCL reports this contact only if every OBB pair on its descent to
+					// the two leaves passed obbDisjoint.  Each of those boxes contains its triangle, the two
+					// triangles were just found to meet, and obbDisjoint pads every radius by 1e-6 times (at
+					// least) the two smallest extents of one box; when that pad (>= 1e-6 mu) exceeds the
+					// magnitudes entering the test by a factor >= 1e5 above fp64 round-off (2^-53 ~ 1e-16),
+					// no test on the path can report "disjoint" and the replay is provably redundant
+					// (DESIGN.md "Path certificate").  mu = min over the two root-to-leaf chains, precomputed per
+					// triangle; it is 0 for degenerate boxes, which forces the replay.
+					const double mag = fabs(wm.rel[9]) + fabs(wm.rel[10]) + fabs(wm.rel[11]) + m1.cmax1 + m2.cmax1 +
+					                   m1.esum + m2.esum;
+					const double mu = fmin((double)p.env.mu_chain[m1.tri_base + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
+					const bool certified = !p.always_replay && mu >= 1e-5 * mag;
+					if (certified) {
+						hitmask |= 1u << src;
+					} else {
+						if (COUNT) ctr[CTR_PATH] += 1;
+						if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
+					}
 				}
 			}
 			__syncwarp();
@@ -825,9 +832,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 						if (!((hitmask >> src) & 1u)) {
 							const double *bb = p.obj_aabb + eobj;  // AABB::overlap(env, agent), closed intervals
 							const unsigned st = p.n_objects_pad;
-							ov = !(bb[0] > wm.box[3 * 32 + src] || bb[st] > wm.box[4 * 32 + src] ||
-							       bb[2 * st] > wm.box[5 * 32 + src] || bb[3 * st] < wm.box[0 * 32 + src] ||
-							       bb[4 * st] < wm.box[1 * 32 + src] || bb[5 * st] < wm.box[2 * 32 + src]);
+							const double e0 = bb[0], e1 = bb[st], e2 = bb[2 * st], e3 = bb[3 * st], e4 = bb[4 * st],
+							             e5 = bb[5 * st];
+							const bool out = (e0 > wm.box[3 * 32 + src]) | (e1 > wm.box[4 * 32 + src]) |
+							                 (e2 > wm.box[5 * 32 + src]) | (e3 < wm.box[0 * 32 + src]) |
+							                 (e4 < wm.box[1 * 32 + src]) | (e5 < wm.box[2 * 32 + src]);
+							ov = !out;
 						}
 					}
 					const unsigned om = __ballot_sync(FULL, ov);

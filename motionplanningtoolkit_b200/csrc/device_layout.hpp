@@ -47,6 +47,9 @@ struct DevModel {
 	float r2;              // max |v - ctr|_2 over the vertices, rounded up
 	float rinf;            // max |v - ctr|_inf over the vertices, rounded up
 	unsigned long long anc_base;  // first word of this model's ancestor chains in ModelPack::anc
+	// replay certificate (collide_kernel.cu, "path certificate"):
+	double cmax1;  // max over nodes of |To|_1
+	double esum;   // max over nodes of extent[0] + extent[1] + extent[2]
 };
 
 struct DevObject {
@@ -64,6 +67,8 @@ struct ModelPack {
 	const double *node64;
 	const double *tri64;
 	const uint32_t *anc;
+	const float *mu_chain;  // per triangle: min over its ancestor chain (leaf included) of the sum of the two
+	                        // smallest OBB extents of the node, rounded down (path certificate)
 	const DevModel *models;
 };
 
@@ -85,7 +90,8 @@ struct KernelParams {
 	unsigned long long n_pose_sets;
 	uint32_t *verdict_bits;
 	uint32_t *work_counter;
-	unsigned long long *counters;  // [6] or nullptr
+	unsigned long long *counters;  // [CTR_N] or nullptr
+	uint32_t always_replay;        // 1: replay FCL's path for every positive pair (ignore the certificate)
 };
 
 // index of the counters in KernelParams::counters

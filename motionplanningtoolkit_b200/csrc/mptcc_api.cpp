@@ -66,6 +66,7 @@ struct HostPack {
 	std::vector<double> node64;
 	std::vector<double> tri64;
 	std::vector<uint32_t> anc;
+	std::vector<float> mu_chain;
 	std::vector<DevModel> models;
 	uint32_t max_depth = 0;
 
@@ -106,6 +107,18 @@ struct HostPack {
 		m.rinf = round_up_f32(rinf * (1.0 + 1e-6));
 
 		const uint32_t nn = b.num_nodes();
+		std::vector<double> node_mu(nn);
+		for (uint32_t i = 0; i < nn; ++i) {
+			const double *C = &b.center[3 * (size_t)i];
+			const double *E = &b.extent[3 * (size_t)i];
+			const double emin = std::min(E[0], std::min(E[1], E[2]));
+			const double emax = std::max(E[0], std::max(E[1], E[2]));
+			const double emid = std::max(std::min(E[0], E[1]), std::min(std::max(E[0], E[1]), E[2]));
+			(void)emax;
+			node_mu[i] = emin + emid;
+			m.cmax1 = std::max(m.cmax1, std::fabs(C[0]) + std::fabs(C[1]) + std::fabs(C[2]));
+			m.esum = std::max(m.esum, E[0] + E[1] + E[2]);
+		}
 		for (uint32_t i = 0; i < nn; ++i) {
 			const double *A = &b.axis[9 * (size_t)i];
 			const double *C = &b.center[3 * (size_t)i];
@@ -137,6 +150,8 @@ struct HostPack {
 					parent[b.first_child[i] + 1] = (int32_t)i;
 				}
 			anc.resize(anc.size() + (size_t)nt * b.depth, 0xffffffffu);
+			const size_t mu_base = mu_chain.size();
+			mu_chain.resize(mu_base + nt, 0.f);
 			std::vector<uint32_t> chain;
 			for (uint32_t i = 0; i < nn; ++i) {
 				if (b.first_child[i] >= 0) continue;
@@ -145,6 +160,9 @@ struct HostPack {
 				for (int32_t v = (int32_t)i; v >= 0; v = parent[v]) chain.push_back((uint32_t)v);
 				uint32_t *dst = &anc[m.anc_base + (size_t)prim * b.depth];
 				for (size_t l = 0; l < chain.size(); ++l) dst[l] = chain[chain.size() - 1 - l];
+				double mu = DBL_MAX;
+				for (uint32_t v : chain) mu = std::min(mu, node_mu[v]);
+				mu_chain[mu_base + prim] = round_down_f32(mu);
 			}
 		}
 		for (uint32_t t = 0; t < nt; ++t) {
@@ -270,6 +288,7 @@ struct DevPack {
 	DevBuf<float4> node32, tri32;
 	DevBuf<double> node64, tri64;
 	DevBuf<uint32_t> anc;
+	DevBuf<float> mu_chain;
 	DevBuf<DevModel> models;
 	cudaError_t upload(const HostPack &h, cudaStream_t s) {
 		cudaError_t e;
@@ -278,15 +297,17 @@ struct DevPack {
 		if ((e = node64.upload(h.node64, s)) != cudaSuccess) return e;
 		if ((e = tri64.upload(h.tri64, s)) != cudaSuccess) return e;
 		if ((e = anc.upload(h.anc, s)) != cudaSuccess) return e;
+		if ((e = mu_chain.upload(h.mu_chain, s)) != cudaSuccess) return e;
 		return models.upload(h.models, s);
 	}
-	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, tri64.p, anc.p, models.p}; }
+	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, tri64.p, anc.p, mu_chain.p, models.p}; }
 	void release() {
 		node32.release();
 		tri32.release();
 		node64.release();
 		tri64.release();
 		anc.release();
+		mu_chain.release();
 		models.release();
 	}
 };
@@ -326,6 +347,7 @@ struct mptcc_ctx {
 	long opt_ppw = 0;           // 0 = auto
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
 	long opt_sub_batch = 1 << 18;
+	long opt_always_replay = 0;
 	mptcc_counters ctr{};
 	int ctas_per_sm_cached = -1;
 	bool ctas_cached_count = false;
@@ -420,6 +442,7 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.n_objects = (uint32_t)ctx->objects_h.size();
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
 	kp.counters = ctx->count ? d.counters.p : nullptr;
+	kp.always_replay = ctx->opt_always_replay ? 1u : 0u;
 }
 
 // Enqueue (memsets +) kernel for n pose-sets already on the device.
@@ -783,6 +806,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
+	} else if (k == "always_replay") {
+		ctx->opt_always_replay = value != 0;
 	} else if (k == "sub_batch") {
 		if (value < 32) return fail(ctx, MPTCC_ERR_INVALID, "sub_batch: >= 32");
 		ctx->opt_sub_batch = value;

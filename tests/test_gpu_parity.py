@@ -159,10 +159,30 @@ def test_segments_match_safe_edge_semantics(box_scene):
 def test_counters_and_exact_path(box_scene):
     rng = scenes.SplitMix64(3)
     poses = scenes.random_poses_rt12(rng, 4096, (-1.2, -1.2, -1.2), (1.2, 1.2, 1.2))
-    chk = box_scene.checker()
+    chk = box_scene.checker(always_replay=1)
     chk.enable_counters(True)
     bits = chk.check_poses(poses)
     c = chk.counters()
     assert_bits_equal(bits, box_scene.oracle_bits(poses), len(poses), "counting kernel")
     assert c["n_pose_sets"] == 4096 and c["n_bv_tests"] > 0 and c["n_leaf_tests"] > 0
+    assert c["n_exact_tri"] >= int(O.unpack_bits(bits, len(poses)).sum())
+    # with always_replay every positive triangle pair replays FCL's root-to-leaf OBB tests in fp64
     assert c["n_path_checks"] >= int(O.unpack_bits(bits, len(poses)).sum())
+
+
+def test_path_certificate_equals_full_replay(built):
+    """The certificate that skips the fp64 path replay must never change a verdict."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(77)
+    poses = scenes.random_poses_near_objects(rng, 20000, env, 2.0)
+    a = sc.checker(always_replay=1)
+    b = sc.checker(always_replay=0)
+    a.enable_counters(True)
+    b.enable_counters(True)
+    ba, bb = a.check_poses(poses), b.check_poses(poses)
+    assert np.array_equal(ba, bb)
+    assert_bits_equal(bb, sc.oracle_bits(poses), len(poses), "certificate")
+    assert a.counters()["n_path_checks"] > 0
+    assert b.counters()["n_path_checks"] <= a.counters()["n_path_checks"]
