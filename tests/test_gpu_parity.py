@@ -186,3 +186,22 @@ def test_path_certificate_equals_full_replay(built):
     assert_bits_equal(bb, sc.oracle_bits(poses), len(poses), "certificate")
     assert a.counters()["n_path_checks"] > 0
     assert b.counters()["n_path_checks"] <= a.counters()["n_path_checks"]
+
+
+import glob  # noqa: E402
+import os  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(GOLDEN, "*.npz"))), ids=os.path.basename)
+def test_gpu_matches_golden_vectors(built, path):
+    """Committed fixtures (tools/make_golden.py): seeded poses + the oracle's verdict words."""
+    from test_oracle_kat import _golden_scene
+    g = np.load(path)
+    env, links = _golden_scene(os.path.basename(path))
+    chk = capi.Checker(1)
+    chk.set_environment(env, g["pose7"])
+    chk.set_agent(links)
+    got = chk.check_poses(g["poses"], int(g["fmt"]))
+    assert_bits_equal(got, g["bits"], g["poses"].shape[0], os.path.basename(path))

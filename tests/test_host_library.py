@@ -1,0 +1,132 @@
+"""CPU tests of libmptcc's host side: the C ABI surface, the host BVH builder (must be bit-identical to
+the oracle's restatement of FCL's builder), failure modes without a GPU, and the sharding helpers."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from motionplanningtoolkit_b200 import capi, meshio, scenes, sharding
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    header = open(os.path.join(ROOT, "include", "mptcc.h")).read()
+    declared = set(re.findall(r"\b(mptcc_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", capi.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (mptcc_[a-z0-9_]+)", nm))
+    assert declared <= exported
+
+
+def test_no_cpu_fallback(built):
+    """Without a usable sm_100 device the context cannot be created: there is no CPU path."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(capi.MptccError) as e:
+        capi.Checker(1)
+    assert e.value.code == capi.ERR_NO_DEVICE
+
+
+def test_host_bvh_is_bit_identical_to_oracle(built):
+    for name in ("unit_box", "blimp", "model", "divider"):
+        for k, (v, t) in enumerate(meshio.environment_submeshes(meshio.load_mptm(name))):
+            a, b = capi.HostBvh(v, t), O.Model(v, t)
+            na, nb = a.nodes(), b.nodes()
+            for key in na:
+                assert np.array_equal(na[key], nb[key]), (name, k, key)
+            assert np.array_equal(a.primitive_indices(), b.primitive_indices())
+            (ba, ca, ra), (bb, cb, rb) = a.local_aabb(), b.local_aabb()
+            assert np.array_equal(ba, bb) and np.array_equal(ca, cb) and ra == rb
+
+
+def test_host_bvh_on_procedural_meshes(built):
+    env = scenes.synthetic_environment(12)
+    for v, t in env:
+        a, b = capi.HostBvh(v, t), O.Model(v, t)
+        na, nb = a.nodes(), b.nodes()
+        for key in na:
+            assert np.array_equal(na[key], nb[key]), key
+        assert a.num_nodes == 2 * len(t) - 1 and a.depth >= int(np.ceil(np.log2(len(t)))) + 1
+
+
+def test_empty_mesh_is_rejected(built):
+    with pytest.raises(capi.MptccError):
+        capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
+
+
+def test_agent_submesh_rules():
+    subs = meshio.load_mptm("blimp")
+    assert [len(t) for _, t in subs] == [8, 121, 1194, 32]
+    v, t = meshio.agent_submesh(subs, "last")            # the reference keeps only the last sub-mesh (Q2)
+    assert len(t) == 32
+    v, t = meshio.agent_submesh(subs, "merge")
+    assert len(t) == 1355 and t.max() == len(v) - 1
+    assert len(meshio.environment_submeshes(meshio.load_mptm("divider"))) == 110
+
+
+def test_omnidirectional_edge_interpolation():
+    """Omnidirectional::getPoses: iterations = (unsigned)(dist/dt); end point added iff iterations*dt < dist."""
+    # dist/dt = 10 exactly: ten poses 0 .. 0.9 and NO end pose, because 10*0.1 < 1.0 is false (reference quirk)
+    p = scenes.omnidirectional_edge_poses([0, 0, 0], [1, 0, 0], 0.1)
+    assert len(p) == 10 and np.allclose(p[0], 0) and np.allclose(p[-1], [0.9, 0, 0])
+    p = scenes.omnidirectional_edge_poses([0, 0, 0], [0.05, 0, 0], 0.1)      # shorter than dt: start and end
+    assert len(p) == 2
+    p = scenes.omnidirectional_edge_poses([0, 0, 0], [0, 0.35, 0], 0.1)
+    assert len(p) == 4 and np.allclose(p[:, 1], [0, 0.1, 0.2, 0.35])
+
+
+def test_splitmix64_reference_values():
+    r = scenes.SplitMix64(0)
+    assert [int(x) for x in r.next_u64(3)] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4, 0x06C45D188009454F]
+    a = scenes.SplitMix64(5).next_u64(10)
+    r = scenes.SplitMix64(5)
+    b = np.concatenate([r.next_u64(4), r.next_u64(6)])
+    assert np.array_equal(a, b)
+
+
+def test_shard_ranges_are_word_aligned_and_cover():
+    for n in (0, 1, 31, 32, 33, 1000, 4097, 1 << 20):
+        for w in (1, 2, 3, 4, 8):
+            prev = 0
+            for r in range(w):
+                b, e = sharding.shard_range(n, w, r)
+                assert b == prev and b % 32 == 0 or b == n
+                assert e >= b
+                prev = e
+            assert prev == n
+
+
+def _gloo_worker(rank, world, port, n, out_dir):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    box = meshio.load_mptm("unit_box")[0]
+    om = O.Model(*box)
+    env = O.Environment([om])
+    rng = scenes.SplitMix64(1234)
+    poses = scenes.random_poses_rt12(rng, n, (-1.6,) * 3, (1.6,) * 3)            # same batch on every rank
+    local = sharding.check_sharded(lambda p: O.verdicts(env, [om], p), poses, world, rank)
+    words = sharding.all_gather_verdicts(local, n, world, rank, dist)
+    whole = O.verdicts(env, [om], poses)
+    np.save(os.path.join(out_dir, "ok_%d.npy" % rank), np.array([np.array_equal(words, whole)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [1000, 4097])
+def test_two_rank_sharding_matches_unsplit_run(built, tmp_path, n):
+    """N > 1 path on CPU (gloo, world_size 2): per-rank slices concatenate to the unsplit verdict words."""
+    import torch.multiprocessing as mp
+    port = 29500 + (os.getpid() + n) % 2000
+    mp.spawn(_gloo_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r))[0]
