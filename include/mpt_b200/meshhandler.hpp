@@ -1,0 +1,239 @@
+// meshhandler.hpp -- drop-in for /root/reference/utilities/meshhandler.hpp on top of libmptcc.
+//
+// Same class and method names, argument meaning and error behaviour as the reference:
+//   StaticEnvironmentMeshHandler(file, pose)   meshhandler.hpp:18-55   (exit(0) when the mesh cannot be loaded)
+//   SimpleAgentMeshHandler(file)               meshhandler.hpp:114-135 (keeps the LAST non-empty sub-mesh)
+//   MeshHandler::isInCollision(env, agent, poses, checkSelfCollision, debug)   meshhandler.hpp:187-243
+// plus the batched form the call sites switch to:
+//   MeshHandler::collidingPoseSets(env, agent, poses) -> one bool per pose-set (one isInCollision each).
+//
+// Mesh files: Assimp is replaced by the flat .mptm format (tools/convert_meshes.py converts .dae/.3ds with
+// the sub-mesh semantics of AssimpMeshLoader::get, /root/reference/utilities/assimp_mesh_loader.hpp:20-60).
+#pragma once
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../mptcc.h"
+#include "fcl_types.hpp"
+
+namespace fcl_helpers {
+// fcl_helpers::parseTransform (/root/reference/utilities/fcl_helpers.hpp:16-25): "x y z qw qx qy qz", read
+// left to right (the reference's unsequenced *++token arguments only work that way).
+inline fcl::Transform3f parseTransform(const std::string &transform) {
+	std::istringstream in(transform);
+	double v[7] = {0, 0, 0, 1, 0, 0, 0};
+	for (int i = 0; i < 7; ++i) in >> v[i];
+	return fcl::Transform3f(fcl::Quaternion3f(v[3], v[4], v[5], v[6]), fcl::Vec3f(v[0], v[1], v[2]));
+}
+}  // namespace fcl_helpers
+
+namespace mpt_b200 {
+
+struct SubMesh {
+	std::vector<double> xyz;     // [nv*3]
+	std::vector<uint32_t> tri;   // [nt*3]
+};
+
+// Stand-in for AssimpMeshLoader: one SubMesh per aiMesh, in order.
+class MptmMeshLoader {
+public:
+	explicit MptmMeshLoader(const std::string &file) : error(false) {
+		std::ifstream f(file.c_str(), std::ios::binary);
+		char magic[4];
+		uint32_t ver = 0, nsub = 0;
+		if (!f.is_open() || !f.read(magic, 4) || std::memcmp(magic, "MPTM", 4) != 0 ||
+		    !f.read(reinterpret_cast<char *>(&ver), 4) || ver != 1 || !f.read(reinterpret_cast<char *>(&nsub), 4)) {
+			fprintf(stderr, "%s: not a readable .mptm mesh (convert .dae/.3ds with tools/convert_meshes.py)\n", file.c_str());
+			error = true;
+			return;
+		}
+		meshes.resize(nsub);
+		for (auto &m : meshes) {
+			uint32_t nv = 0, nt = 0;
+			f.read(reinterpret_cast<char *>(&nv), 4);
+			f.read(reinterpret_cast<char *>(&nt), 4);
+			m.xyz.resize(3 * (size_t)nv);
+			m.tri.resize(3 * (size_t)nt);
+			f.read(reinterpret_cast<char *>(m.xyz.data()), sizeof(double) * m.xyz.size());
+			f.read(reinterpret_cast<char *>(m.tri.data()), sizeof(uint32_t) * m.tri.size());
+			if (!f) {
+				fprintf(stderr, "%s: truncated mesh file\n", file.c_str());
+				error = true;
+				return;
+			}
+		}
+	}
+	std::vector<SubMesh> meshes;
+	bool error;
+};
+
+inline mptcc_mesh as_c_mesh(const SubMesh &m) {
+	mptcc_mesh c;
+	c.xyz = m.xyz.data();
+	c.nv = (uint32_t)(m.xyz.size() / 3);
+	c.tri = m.tri.data();
+	c.nt = (uint32_t)(m.tri.size() / 3);
+	return c;
+}
+
+}  // namespace mpt_b200
+
+class SimpleAgentMeshHandler {
+public:
+	// mergeSubMeshes = false reproduces the reference: agentModel is overwritten for every non-empty
+	// sub-mesh, so only the last one collides (meshhandler.hpp:124-134).
+	explicit SimpleAgentMeshHandler(const std::string &filename, bool mergeSubMeshes = false) {
+		mpt_b200::MptmMeshLoader loader(filename);
+		if (loader.error) exit(0);
+		for (const auto &m : loader.meshes) {
+			if (m.xyz.empty() || m.tri.empty()) continue;
+			if (!mergeSubMeshes) {
+				model = m;
+			} else {
+				const uint32_t base = (uint32_t)(model.xyz.size() / 3);
+				model.xyz.insert(model.xyz.end(), m.xyz.begin(), m.xyz.end());
+				for (uint32_t i : m.tri) model.tri.push_back(i + base);
+			}
+		}
+	}
+	const mpt_b200::SubMesh &getModel() const { return model; }
+
+private:
+	mpt_b200::SubMesh model;
+};
+
+class StaticEnvironmentMeshHandler {
+public:
+	StaticEnvironmentMeshHandler(const std::string &filename, const std::string &pose, int nDevices = 1)
+	    : ctx(nullptr), agentKey() {
+		mpt_b200::MptmMeshLoader loader(filename);
+		if (loader.error) exit(0);
+		const fcl::Transform3f tf = fcl_helpers::parseTransform(pose);
+		for (const auto &m : loader.meshes)
+			if (!m.xyz.empty() && !m.tri.empty()) objects.push_back(m);  // one CollisionObject per non-empty sub-mesh
+		const int rc = mptcc_create(&ctx, nDevices, nullptr);
+		if (rc != MPTCC_OK) {
+			fprintf(stderr, "mptcc_create failed (%d): no usable B200 -- there is no CPU fallback\n", rc);
+			exit(1);
+		}
+		std::vector<mptcc_mesh> cm;
+		std::vector<double> pose7;
+		for (const auto &m : objects) {
+			cm.push_back(mpt_b200::as_c_mesh(m));
+			const double p[7] = {tf.getTranslation()[0], tf.getTranslation()[1], tf.getTranslation()[2],
+			                     tf.getQuatRotation().getW(), tf.getQuatRotation().getX(), tf.getQuatRotation().getY(),
+			                     tf.getQuatRotation().getZ()};
+			pose7.insert(pose7.end(), p, p + 7);
+		}
+		check(mptcc_set_environment(ctx, (int)cm.size(), cm.data(), pose7.data()), "mptcc_set_environment");
+	}
+	~StaticEnvironmentMeshHandler() { mptcc_destroy(ctx); }
+	StaticEnvironmentMeshHandler(const StaticEnvironmentMeshHandler &) = delete;
+	StaticEnvironmentMeshHandler &operator=(const StaticEnvironmentMeshHandler &) = delete;
+
+	// The context bound to this environment, with `agent` installed as the current link models.
+	mptcc_ctx *getCollisionChecker(const std::vector<const SimpleAgentMeshHandler *> &agent) const {
+		if (agent != agentKey) {
+			std::vector<mptcc_mesh> cm;
+			for (const auto *a : agent) cm.push_back(mpt_b200::as_c_mesh(a->getModel()));
+			check(mptcc_set_agent(ctx, (int)cm.size(), cm.data()), "mptcc_set_agent");
+			agentKey = agent;
+		}
+		return ctx;
+	}
+	void check(int rc, const char *what) const {
+		if (rc != MPTCC_OK) {
+			fprintf(stderr, "%s failed (%d): %s\n", what, rc, mptcc_last_error(ctx));
+			exit(1);
+		}
+	}
+
+private:
+	std::vector<mpt_b200::SubMesh> objects;
+	mptcc_ctx *ctx;
+	mutable std::vector<const SimpleAgentMeshHandler *> agentKey;
+};
+
+class MeshHandler {
+public:
+	// [P][L] transforms -> pose records.  All transforms of a batch built from matrices / translations use
+	// RT12; all built from quaternions use TQ7; a mixed batch is split by the callers below.
+	static int packPoses(const std::vector<std::vector<fcl::Transform3f> > &poses, size_t links, bool quat,
+	                     std::vector<double> &out) {
+		out.clear();
+		for (const auto &set : poses) {
+			if (set.size() != links) return -1;
+			for (const auto &tf : set) {
+				if (quat) {
+					const double r[7] = {tf.getTranslation()[0], tf.getTranslation()[1], tf.getTranslation()[2],
+					                     tf.getQuatRotation().getW(), tf.getQuatRotation().getX(),
+					                     tf.getQuatRotation().getY(), tf.getQuatRotation().getZ()};
+					out.insert(out.end(), r, r + 7);
+				} else {
+					out.insert(out.end(), tf.getRotation().data(), tf.getRotation().data() + 9);
+					const double t[3] = {tf.getTranslation()[0], tf.getTranslation()[1], tf.getTranslation()[2]};
+					out.insert(out.end(), t, t + 3);
+				}
+			}
+		}
+		return 0;
+	}
+
+	// One verdict per pose-set (true = in collision): what one MeshHandler::isInCollision call per pose-set
+	// would return.  This is the call the batched planners use.
+	static std::vector<bool> collidingPoseSets(const StaticEnvironmentMeshHandler &environment,
+	                                           const std::vector<const SimpleAgentMeshHandler *> &agent,
+	                                           const std::vector<std::vector<fcl::Transform3f> > &poses) {
+		std::vector<bool> verdict(poses.size(), false);
+		if (poses.empty() || agent.empty()) return verdict;
+		mptcc_ctx *ctx = environment.getCollisionChecker(agent);
+		// split by constructor kind (pose-sets whose links mix kinds are not produced by any agent)
+		for (int quat = 0; quat < 2; ++quat) {
+			std::vector<std::vector<fcl::Transform3f> > part;
+			std::vector<size_t> index;
+			for (size_t i = 0; i < poses.size(); ++i) {
+				if (poses[i].empty()) continue;  // no agent objects: never in collision (Blimp::getPoses stub)
+				if ((int)poses[i][0].builtFromQuaternion() == quat) {
+					part.push_back(poses[i]);
+					index.push_back(i);
+				}
+			}
+			if (part.empty()) continue;
+			std::vector<double> rec;
+			if (packPoses(part, agent.size(), quat != 0, rec) != 0) {
+				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
+				exit(1);
+			}
+			std::vector<uint32_t> bits((part.size() + 31) / 32, 0u);
+			environment.check(mptcc_check_poses(ctx, part.size(), rec.data(), quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
+			                                    bits.data()),
+			                  "mptcc_check_poses");
+			for (size_t k = 0; k < part.size(); ++k) verdict[index[k]] = (bits[k >> 5] >> (k & 31)) & 1u;
+		}
+		return verdict;
+	}
+
+	// The reference's signature and meaning: one bool for the whole batch of pose-sets.
+	static bool isInCollision(const StaticEnvironmentMeshHandler &environment,
+	                          const std::vector<const SimpleAgentMeshHandler *> &agent,
+	                          const std::vector<std::vector<fcl::Transform3f> > &poses, bool checkSelfCollision = false,
+	                          bool debug = false) {
+		if (checkSelfCollision) {
+			// no caller in the reference enables it (map3d.hpp:33,36 default false); SURVEY 8f N4
+			fprintf(stderr, "MeshHandler::isInCollision: checkSelfCollision is not implemented on the GPU path\n");
+			exit(1);
+		}
+		(void)debug;  // contact points are not computed (enable_contact = false in the reference as well)
+		const std::vector<bool> v = collidingPoseSets(environment, agent, poses);
+		for (bool b : v)
+			if (b) return true;
+		return false;
+	}
+};
