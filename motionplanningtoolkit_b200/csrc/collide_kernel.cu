@@ -25,6 +25,7 @@ namespace mptcc {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+typedef unsigned long long u64;
 constexpr float kU = 5.9604645e-8f;  // 2^-24, fp32 unit round-off
 
 // ------------------------------------------------------------------------------------------------
@@ -500,10 +501,11 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 struct WarpMem {
 	uint2 *leafq;        // [kLeafQueueCap] (env prim, agent prim | cand << 24)
 	float4 *cand;        // [kCandCap][4] candidate records: R(9) T(3) S src node_base1 tri_base1
-	uint32_t *cand_ids;  // [kCandCap]    pose slot << 27 | object
+	uint32_t *cand_ids;  // [kCandCap]    pose slot (0..63) << 26 | object
 	uint32_t *clq;       // [kClusterQueueCap] pose slot << 27 | cluster
 	double *rel;         // [16] fp64 R (9), T (3) of the candidate being re-decided exactly
 	double *box;         // [6][32] world AABB of each lane's pose (min xyz, max xyz), component-major
+	unsigned char *donor;  // [32] work stealing: donor rank -> lane
 };
 
 // relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1)  [FCL-recalled C.7]; element `idx`
@@ -526,8 +528,8 @@ __device__ __forceinline__ double rel_element(const DevObject &ob, const double 
 // order per candidate is what lets a colliding pose stop after about as many tests as FCL needs.
 // Returns the updated hit mask (bit = pose slot).
 template <bool COUNT>
-__device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const DevModel &m2, int ncand,
-                                 unsigned hitmask, unsigned validmask, const double *link_poses, unsigned rec_len,
+__device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevModel &m2, int ncand,
+                                 u64 hitmask, u64 validmask, const double *link_poses, unsigned rec_len,
                                  int lane, unsigned long long *ctr) {
 	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
 	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
@@ -557,16 +559,20 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 			im = __ballot_sync(FULL, !has);
 		}
 		// ---- 2. ... or steal the bottom entry (largest pending subtree) of a busy lane ------------------
-		if (im && qhead >= ncand) {
+		if (im && qhead >= ncand && !p.no_steal) {
 			const unsigned dm = __ballot_sync(FULL, has && top != bot);
 			if (dm) {
 				const int n_thieves = __popc(im), n_donors = __popc(dm);
+				const int drank = __popc(dm & lt);
+				const bool donor = (dm >> lane) & 1u;
+				if (donor) wm.donor[drank] = (unsigned char)lane;  // rank -> lane table: the r-th thief robs the r-th donor
+				__syncwarp();
 				const int r = __popc(im & lt);
 				const bool thief = !has && r < n_donors;
-				const int from = thief ? (int)__fns(dm, 0, r + 1) : lane;
-				const bool robbed = ((dm >> lane) & 1u) && __popc(dm & lt) < n_thieves;
+				const int from = thief ? (int)wm.donor[r] : lane;
+				const bool robbed = donor && drank < n_thieves;
 				uint2 e = make_uint2(0u, 0u);
-				if (robbed) e = stk[bot++ & M];
+				if (robbed) e = p.steal_bottom ? stk[bot++ & M] : stk[--top & M];
 				e.x = __shfl_sync(FULL, e.x, from);
 				e.y = __shfl_sync(FULL, e.y, from);
 				if (thief) {
@@ -589,7 +595,7 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 				pr = wm.leafq[lq + lane];
 				const float4 *rec = wm.cand + 4u * (pr.y >> 24);
 				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
-				if (!((hitmask >> __float_as_uint(r3.y)) & 1u)) {
+				if (!((hitmask >> __float_as_uint(r3.y)) & 1ull)) {
 					RelF x;
 					x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
 					x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;
@@ -610,8 +616,8 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 				const uint32_t t1 = __shfl_sync(FULL, pr.x, from), w2 = __shfl_sync(FULL, pr.y, from);
 				const uint32_t t2 = w2 & 0xffffffu, cand = w2 >> 24;
 				const uint32_t id = wm.cand_ids[cand];
-				const unsigned src = id >> 27, e = id & 0x7ffffffu;
-				if ((hitmask >> src) & 1u) continue;
+				const unsigned src = id >> 26, e = id & 0x3ffffffu;
+				if ((hitmask >> src) & 1ull) continue;
 				if (COUNT) ctr[CTR_EXACT] += 1;
 				// fp64 relative transform of this candidate, FCL's operation order
 				const DevObject &ob = p.objects[e];
@@ -640,10 +646,10 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 					const double mu = fmin((double)p.env.mu_chain[m1.tri_base + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
 					const bool certified = !p.always_replay && mu >= 1e-5 * mag;
 					if (certified) {
-						hitmask |= 1u << src;
+						hitmask |= 1ull << src;
 					} else {
 						if (COUNT) ctr[CTR_PATH] += 1;
-						if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) hitmask |= 1u << src;
+						if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) hitmask |= 1ull << src;
 					}
 				}
 			}
@@ -660,7 +666,7 @@ __device__ unsigned traverse_all(const KernelParams &p, const WarpMem &wm, const
 			const unsigned tag = pr.y & 0xff000000u;
 			const float4 *rec = wm.cand + 4u * (pr.y >> 24);
 			const float4 r3 = rec[3];
-			if ((hitmask >> __float_as_uint(r3.y)) & 1u) {
+			if ((hitmask >> __float_as_uint(r3.y)) & 1ull) {
 				top = bot;  // this lane's stack holds one candidate only, and its pose-set already collides
 			} else {
 				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
@@ -731,6 +737,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
 	base += kCandCap * 4;
 	wm.clq = reinterpret_cast<uint32_t *>(base);
+	base += kClusterQueueCap * 4;
+	wm.donor = base;
 
 	const unsigned ppw = 1u << p.ppw_log2;
 	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
@@ -746,168 +754,182 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 		chunk = __shfl_sync(FULL, chunk, 0);
 		if (chunk >= n_chunks) break;
 		const unsigned long long pose0 = (unsigned long long)chunk << p.ppw_log2;
-		const unsigned long long my_pose = pose0 + (unsigned)lane;
-		const bool valid = (unsigned)lane < ppw && my_pose < p.n_pose_sets;
-		const unsigned validmask = __ballot_sync(FULL, valid);
-		unsigned hitmask = 0;
+		const unsigned long long left = p.n_pose_sets - pose0;
+		const unsigned nvalid = left < ppw ? (unsigned)left : ppw;
+		const u64 validmask = nvalid >= 64u ? ~0ull : ((1ull << nvalid) - 1ull);
+		const unsigned rounds = (nvalid + 31u) >> 5;  // 32 pose slots per round, up to 64 slots per chunk
+		u64 hitmask = 0;
 
 		for (unsigned j = 0; j < p.n_links && hitmask != validmask; ++j) {
 			const DevModel &m2 = p.agent.models[p.link_model[j]];
 			const double *link_poses = p.poses + (pose0 * p.n_links + j) * rec_len;  // pose slot s: + s*rec_len*n_links
-			// ---- phase A: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
-			float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
-			if (valid) {
-				double R[9], T[3], bmin[3], bmax[3];
-				Quat q;
-				decode_pose(link_poses + (size_t)lane * rec_len * p.n_links, p.pose_format, R, T, q, true);
-				if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
+			int ncand = 0, nrec = 0;  // the candidate table is shared by the rounds of this link
+			for (unsigned round = 0; round < rounds && hitmask != validmask; ++round) {
+				const unsigned slot = round * 32u + (unsigned)lane;
+				const bool valid = slot < nvalid;
+				// ---- phase A: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
+				float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
+				if (valid) {
+					double R[9], T[3], bmin[3], bmax[3];
+					Quat q;
+					decode_pose(link_poses + (size_t)slot * rec_len * p.n_links, p.pose_format, R, T, q, true);
+					if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
+#pragma unroll
+						for (int k = 0; k < 3; ++k) {
+							bmin[k] = dadd(m2.aabb_min[k], T[k]);
+							bmax[k] = dadd(m2.aabb_max[k], T[k]);
+						}
+					} else {
+						// Transform3f::transform(c) = q.transform(c) + T, q.transform(c) = (q (0,c) q*).xyz
+						const Quat c{0.0, m2.aabb_center[0], m2.aabb_center[1], m2.aabb_center[2]};
+						const Quat qc{q.w, -q.x, -q.y, -q.z};
+						const Quat r = qmul(qmul(q, c), qc);
+						const double cw[3] = {dadd(r.x, T[0]), dadd(r.y, T[1]), dadd(r.z, T[2])};
+#pragma unroll
+						for (int k = 0; k < 3; ++k) {
+							bmin[k] = dsub(cw[k], m2.aabb_radius);
+							bmax[k] = dadd(cw[k], m2.aabb_radius);
+						}
+					}
 #pragma unroll
 					for (int k = 0; k < 3; ++k) {
-						bmin[k] = dadd(m2.aabb_min[k], T[k]);
-						bmax[k] = dadd(m2.aabb_max[k], T[k]);
-					}
-				} else {
-					// Transform3f::transform(c) = q.transform(c) + T, q.transform(c) = (q (0,c) q*).xyz
-					const Quat c{0.0, m2.aabb_center[0], m2.aabb_center[1], m2.aabb_center[2]};
-					const Quat qc{q.w, -q.x, -q.y, -q.z};
-					const Quat r = qmul(qmul(q, c), qc);
-					const double cw[3] = {dadd(r.x, T[0]), dadd(r.y, T[1]), dadd(r.z, T[2])};
-#pragma unroll
-					for (int k = 0; k < 3; ++k) {
-						bmin[k] = dsub(cw[k], m2.aabb_radius);
-						bmax[k] = dadd(cw[k], m2.aabb_radius);
-					}
-				}
-#pragma unroll
-				for (int k = 0; k < 3; ++k) {
-					wm.box[k * 32 + lane] = bmin[k];
-					wm.box[(3 + k) * 32 + lane] = bmax[k];
-					amin[k] = __double2float_rd(bmin[k]);
-					amax[k] = __double2float_ru(bmax[k]);
-				}
-			}
-			__syncwarp();
-			unsigned node = valid ? 0u : p.n_bp_nodes;
-			int ncl = 0, ncand = 0, nrec = 0;
-			bool more = true;
-			while (more || ncl > 0 || ncand > 0) {
-				// ---- phase B: lane-per-pose walk of the threaded cluster tree (fp32, conservative) ------
-				while (more && ncl <= kClusterQueueCap - 32) {
-					if ((hitmask >> lane) & 1u) node = p.n_bp_nodes;
-					const bool act = node < p.n_bp_nodes;
-					if (!__any_sync(FULL, act)) {
-						more = false;
-						break;
-					}
-					bool leaf_hit = false;
-					unsigned cl = 0;
-					if (act) {
-						const float4 lo = __ldg(p.bp_nodes + 2ull * node), hi = __ldg(p.bp_nodes + 2ull * node + 1);
-						const bool ov = !(lo.x > amax[0] || lo.y > amax[1] || lo.z > amax[2] || hi.x < amin[0] ||
-						                  hi.y < amin[1] || hi.z < amin[2]);
-						const int esc = __float_as_int(lo.w), leaf = __float_as_int(hi.w);
-						leaf_hit = ov && leaf >= 0;
-						cl = (unsigned)leaf;
-						node = (ov && leaf < 0) ? node + 1u : (unsigned)esc;
-					}
-					const unsigned m = __ballot_sync(FULL, leaf_hit);
-					if (m) {
-						if (leaf_hit) wm.clq[ncl + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
-						ncl += __popc(m);
+						wm.box[k * 32 + lane] = bmin[k];
+						wm.box[(3 + k) * 32 + lane] = bmax[k];
+						amin[k] = __double2float_rd(bmin[k]);
+						amax[k] = __double2float_ru(bmax[k]);
 					}
 				}
 				__syncwarp();
-				// ---- phase C1: (pose, cluster) -> exact fp64 AABB::overlap per object -> candidate ids ---
-				// 32 / kClusterSize queue entries per iteration: lane -> (entry, object of the cluster)
-				constexpr int kPer = 32 / kClusterSize;
-				int c = 0;
-				for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
-					const int idx = c + lane / kClusterSize;
-					bool ov = false;
-					unsigned src = 0, eobj = 0;
-					if (idx < ncl) {
-						const unsigned ent = wm.clq[idx];
-						src = ent >> 27;
-						eobj = (ent & 0x7ffffffu) * kClusterSize + (unsigned)(lane % kClusterSize);
-						if (!((hitmask >> src) & 1u)) {
-							const double *bb = p.obj_aabb + eobj;  // AABB::overlap(env, agent), closed intervals
-							const unsigned st = p.n_objects_pad;
-							const double e0 = bb[0], e1 = bb[st], e2 = bb[2 * st], e3 = bb[3 * st], e4 = bb[4 * st],
-							             e5 = bb[5 * st];
-							const bool out = (e0 > wm.box[3 * 32 + src]) | (e1 > wm.box[4 * 32 + src]) |
-							                 (e2 > wm.box[5 * 32 + src]) | (e3 < wm.box[0 * 32 + src]) |
-							                 (e4 < wm.box[1 * 32 + src]) | (e5 < wm.box[2 * 32 + src]);
-							ov = !out;
+				unsigned node = valid ? 0u : p.n_bp_nodes;
+				int ncl = 0;
+				bool more = true;
+				while (more || ncl > 0) {
+					// ---- phase B: lane-per-pose walk of the threaded cluster tree (fp32, conservative) ----
+					while (more && ncl <= kClusterQueueCap - 32) {
+						if ((hitmask >> slot) & 1ull) node = p.n_bp_nodes;
+						const bool act = node < p.n_bp_nodes;
+						if (!__any_sync(FULL, act)) {
+							more = false;
+							break;
+						}
+						bool leaf_hit = false;
+						unsigned cl = 0;
+						if (act) {
+							const float4 lo = __ldg(p.bp_nodes + 2ull * node), hi = __ldg(p.bp_nodes + 2ull * node + 1);
+							const bool ov = !(lo.x > amax[0] || lo.y > amax[1] || lo.z > amax[2] || hi.x < amin[0] ||
+							                  hi.y < amin[1] || hi.z < amin[2]);
+							const int esc = __float_as_int(lo.w), leaf = __float_as_int(hi.w);
+							leaf_hit = ov && leaf >= 0;
+							cl = (unsigned)leaf;
+							node = (ov && leaf < 0) ? node + 1u : (unsigned)esc;
+						}
+						const unsigned m = __ballot_sync(FULL, leaf_hit);
+						if (m) {
+							if (leaf_hit) wm.clq[ncl + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
+							ncl += __popc(m);
 						}
 					}
-					const unsigned om = __ballot_sync(FULL, ov);
-					if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (src << 27) | eobj;
-					ncand += __popc(om);
-				}
-				if (c > ncl) c = ncl;
-				// keep the unprocessed tail of the cluster queue
-				if (c < ncl) {
-					const int rest = ncl - c;
-					unsigned keep0 = 0, keep1 = 0;
-					if (lane < rest) keep0 = wm.clq[c + lane];
-					if (lane + 32 < rest) keep1 = wm.clq[c + lane + 32];
 					__syncwarp();
-					if (lane < rest) wm.clq[lane] = keep0;
-					if (lane + 32 < rest) wm.clq[lane + 32] = keep1;
-					ncl = rest;
-				} else {
-					ncl = 0;
-				}
-				__syncwarp();
-				if (COUNT) ctr[CTR_CAND] += (unsigned)(ncand - nrec);
-				// ---- phase C2: one lane per new candidate: fp64 relative transform -> fp32 record ---------
-				for (int i0 = nrec; i0 < ncand; i0 += 32) {
-					const int i = i0 + lane;
-					if (i < ncand) {
-						const uint32_t id = wm.cand_ids[i];
-						const unsigned src = id >> 27, e = id & 0x7ffffffu;
-						const DevObject &ob = p.objects[e];
-						const DevModel &m1 = p.env.models[ob.model];
-						double R2[9], T2[3], rl[12];
-						Quat q;
-						decode_pose(link_poses + (size_t)src * rec_len * p.n_links, p.pose_format, R2, T2, q, false);
-#pragma unroll
-						for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
-						// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
-						float tf[3], tinf = 0.f;
-#pragma unroll
-						for (int r = 0; r < 3; ++r) {
-							const double tc = rl[3 * r] * m2.ctr[0] + rl[3 * r + 1] * m2.ctr[1] + rl[3 * r + 2] * m2.ctr[2] +
-							                  rl[9 + r] - m1.ctr[r];
-							tf[r] = (float)tc;
-							tinf = fmaxf(tinf, fabsf(tf[r]));
+					// ---- phase C1: (pose, cluster) -> exact fp64 AABB::overlap per object -> candidate ids -
+					// 32 / kClusterSize queue entries per iteration: lane -> (entry, object of the cluster)
+					constexpr int kPer = 32 / kClusterSize;
+					int c = 0;
+					for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
+						const int idx = c + lane / kClusterSize;
+						bool ov = false;
+						unsigned src = 0, eobj = 0;
+						if (idx < ncl) {
+							const unsigned ent = wm.clq[idx];
+							const unsigned sl = ent >> 27;  // lane slot of this round
+							src = round * 32u + sl;
+							eobj = (ent & 0x7ffffffu) * kClusterSize + (unsigned)(lane % kClusterSize);
+							if (!((hitmask >> src) & 1ull)) {
+								const double *bb = p.obj_aabb + eobj;  // AABB::overlap(env, agent), closed intervals
+								const unsigned st = p.n_objects_pad;
+								const double e0 = bb[0], e1 = bb[st], e2 = bb[2 * st], e3 = bb[3 * st], e4 = bb[4 * st],
+								             e5 = bb[5 * st];
+								const bool out = (e0 > wm.box[3 * 32 + sl]) | (e1 > wm.box[4 * 32 + sl]) |
+								                 (e2 > wm.box[5 * 32 + sl]) | (e3 < wm.box[0 * 32 + sl]) |
+								                 (e4 < wm.box[1 * 32 + sl]) | (e5 < wm.box[2 * 32 + sl]);
+								ov = !out;
+							}
 						}
-						// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
-						const float S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
-						float4 *rec = wm.cand + 4u * i;
-						rec[0] = make_float4((float)rl[0], (float)rl[1], (float)rl[2], (float)rl[3]);
-						rec[1] = make_float4((float)rl[4], (float)rl[5], (float)rl[6], (float)rl[7]);
-						rec[2] = make_float4((float)rl[8], tf[0], tf[1], tf[2]);
-						rec[3] = make_float4(S, __uint_as_float(src), __uint_as_float(m1.node_base), __uint_as_float(m1.tri_base));
+						const unsigned om = __ballot_sync(FULL, ov);
+						if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (src << 26) | eobj;
+						ncand += __popc(om);
+					}
+					if (c > ncl) c = ncl;
+					// keep the unprocessed tail of the cluster queue
+					if (c < ncl) {
+						const int rest = ncl - c;
+						unsigned keep0 = 0, keep1 = 0;
+						if (lane < rest) keep0 = wm.clq[c + lane];
+						if (lane + 32 < rest) keep1 = wm.clq[c + lane + 32];
+						__syncwarp();
+						if (lane < rest) wm.clq[lane] = keep0;
+						if (lane + 32 < rest) wm.clq[lane + 32] = keep1;
+						ncl = rest;
+					} else {
+						ncl = 0;
+					}
+					__syncwarp();
+					if (COUNT) ctr[CTR_CAND] += (unsigned)(ncand - nrec);
+					// ---- phase C2: one lane per new candidate: fp64 relative transform -> fp32 record -------
+					for (int i0 = nrec; i0 < ncand; i0 += 32) {
+						const int i = i0 + lane;
+						if (i < ncand) {
+							const uint32_t id = wm.cand_ids[i];
+							const unsigned src = id >> 26, e = id & 0x3ffffffu;
+							const DevObject &ob = p.objects[e];
+							const DevModel &m1 = p.env.models[ob.model];
+							double R2[9], T2[3], rl[12];
+							Quat q;
+							decode_pose(link_poses + (size_t)src * rec_len * p.n_links, p.pose_format, R2, T2, q, false);
+#pragma unroll
+							for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
+							// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
+							float tf[3], tinf = 0.f;
+#pragma unroll
+							for (int r = 0; r < 3; ++r) {
+								const double tc = rl[3 * r] * m2.ctr[0] + rl[3 * r + 1] * m2.ctr[1] +
+								                  rl[3 * r + 2] * m2.ctr[2] + rl[9 + r] - m1.ctr[r];
+								tf[r] = (float)tc;
+								tinf = fmaxf(tinf, fabsf(tf[r]));
+							}
+							// S = max(S_q, S_p) + S_p, S_q = 5.01 r2(agent) + 4 |Tc|_inf, S_p = rinf(env)
+							const float S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
+							float4 *rec = wm.cand + 4u * i;
+							rec[0] = make_float4((float)rl[0], (float)rl[1], (float)rl[2], (float)rl[3]);
+							rec[1] = make_float4((float)rl[4], (float)rl[5], (float)rl[6], (float)rl[7]);
+							rec[2] = make_float4((float)rl[8], tf[0], tf[1], tf[2]);
+							rec[3] = make_float4(S, __uint_as_float(src), __uint_as_float(m1.node_base),
+							                     __uint_as_float(m1.tri_base));
+						}
+					}
+					nrec = ncand;
+					__syncwarp();
+					// ---- phase D (table full): merged narrowphase ---------------------------------------------
+					if (ncand > kCandCap - 32) {
+						hitmask = traverse_all<COUNT>(p, wm, m2, ncand, hitmask, validmask, link_poses, rec_len, lane, ctr);
+						ncand = 0;
+						nrec = 0;
+						if (hitmask == validmask) break;
 					}
 				}
-				nrec = ncand;
-				__syncwarp();
-				// ---- phase D: merged narrowphase once the table is full or the broadphase is done -----------
-				if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
-					if (ncand > 0)
-						hitmask = traverse_all<COUNT>(p, wm, m2, ncand, hitmask, validmask, link_poses, rec_len, lane, ctr);
-					ncand = 0;
-					nrec = 0;
-					if (hitmask == validmask) break;
-				}
 			}
+			// ---- phase D: the candidates left after the last round of this link ---------------------------
+			if (ncand > 0 && hitmask != validmask)
+				hitmask = traverse_all<COUNT>(p, wm, m2, ncand, hitmask, validmask, link_poses, rec_len, lane, ctr);
 		}
 		// ---- verdict bits ----------------------------------------------------------------------
 		if (lane == 0) {
 			const unsigned long long word = pose0 >> 5;
-			if (ppw == 32u) p.verdict_bits[word] = hitmask;
-			else if (hitmask) atomicOr(p.verdict_bits + word, hitmask << (unsigned)(pose0 & 31ull));
+			if (ppw >= 32u) {
+				p.verdict_bits[word] = (uint32_t)hitmask;
+				if (nvalid > 32u) p.verdict_bits[word + 1] = (uint32_t)(hitmask >> 32);
+			} else if (hitmask) {
+				atomicOr(p.verdict_bits + word, (uint32_t)hitmask << (unsigned)(pose0 & 31ull));
+			}
 		}
 	}
 	if (COUNT && lane == 0) {

@@ -91,6 +91,8 @@ struct KernelParams {
 	uint32_t *verdict_bits;
 	uint32_t *work_counter;
 	unsigned long long *counters;  // [CTR_N] or nullptr
+	uint32_t steal_bottom;         // 1: thieves take the bottom (largest, most speculative) pending pair
+	uint32_t no_steal;             // 1: lanes never steal pending subtrees (experiment knob)
 	uint32_t always_replay;        // 1: replay FCL's path for every positive pair (ignore the certificate)
 };
 
@@ -110,7 +112,7 @@ __host__ __device__
 #endif
 inline constexpr unsigned warp_smem_bytes() {
 	return kLeafQueueCap * 8u + kCandCap * 64u + 6u * 32u * 8u + 16u * 8u + kCandCap * 4u +
-	       kClusterQueueCap * 4u;
+	       kClusterQueueCap * 4u + 32u;
 }
 
 // Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.

@@ -348,6 +348,8 @@ struct mptcc_ctx {
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
 	long opt_sub_batch = 1 << 18;
 	long opt_always_replay = 0;
+	long opt_no_steal = 0;
+	long opt_steal_bottom = 0;
 	mptcc_counters ctr{};
 	int ctas_per_sm_cached = -1;
 	bool ctas_cached_count = false;
@@ -391,12 +393,12 @@ int grid_for(mptcc_ctx *ctx, const Device &d) {
 unsigned pick_ppw_log2(const mptcc_ctx *ctx, uint64_t n, int grid) {
 	if (ctx->opt_ppw > 0) {
 		unsigned l = 0;
-		while ((1l << (l + 1)) <= ctx->opt_ppw && l < 5) ++l;
+		while ((1l << (l + 1)) <= ctx->opt_ppw && l < 6) ++l;
 		return l;
 	}
 	// enough chunks for ~2 per resident warp, else fewer poses per warp
 	const uint64_t warps = (uint64_t)grid * kWarpsPerCta;
-	unsigned l = 5;
+	unsigned l = 5;  // 64 pose slots per warp are supported (option poses_per_warp) but measured slower
 	while (l > 0 && (n >> l) < 2 * warps) --l;
 	return l;
 }
@@ -443,6 +445,8 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
 	kp.counters = ctx->count ? d.counters.p : nullptr;
 	kp.always_replay = ctx->opt_always_replay ? 1u : 0u;
+	kp.no_steal = ctx->opt_no_steal ? 1u : 0u;
+	kp.steal_bottom = ctx->opt_steal_bottom ? 1u : 0u;
 }
 
 // Enqueue (memsets +) kernel for n pose-sets already on the device.
@@ -458,7 +462,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	kp.work_counter = d_work;
 	kp.ppw_log2 = pick_ppw_log2(ctx, n, grid);
 	CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
-	if (kp.ppw_log2 != 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
+	if (kp.ppw_log2 < 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
 	const uint64_t chunks = (n + (1ull << kp.ppw_log2) - 1) >> kp.ppw_log2;
 	int g = grid;
 	const uint64_t need = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
@@ -540,7 +544,7 @@ int mptcc_num_devices(const mptcc_ctx *ctx) { return ctx ? (int)ctx->devs.size()
 
 int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshes, const double *obj_pose7) {
 	if (!ctx || n_objects < 0 || (n_objects > 0 && (!meshes || !obj_pose7))) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
-	if (n_objects >= (1 << 27)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
+	if (n_objects >= (1 << 26)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
 	ctx->env_h.clear();
 	ctx->objects_h.clear();
 	ctx->obj_aabb_h.clear();
@@ -801,11 +805,15 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	if (!ctx || !name) return MPTCC_ERR_INVALID;
 	const std::string k(name);
 	if (k == "poses_per_warp") {
-		if (value < 0 || value > 32 || (value & (value - 1))) return fail(ctx, MPTCC_ERR_INVALID, "poses_per_warp: 0 or a power of two <= 32");
+		if (value < 0 || value > 64 || (value & (value - 1))) return fail(ctx, MPTCC_ERR_INVALID, "poses_per_warp: 0 or a power of two <= 64");
 		ctx->opt_ppw = value;
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
+	} else if (k == "steal_bottom") {
+		ctx->opt_steal_bottom = value != 0;
+	} else if (k == "no_steal") {
+		ctx->opt_no_steal = value != 0;
 	} else if (k == "always_replay") {
 		ctx->opt_always_replay = value != 0;
 	} else if (k == "sub_batch") {
