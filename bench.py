@@ -185,6 +185,9 @@ def run_ours(args):
     per_gpu = args.poses_per_gpu
     env, agent = make_scene()
     chk = capi.Checker(device_ids=[local])
+    for kv in filter(None, os.environ.get("MPTCC_OPTS", "").split(",")):   # tuning experiments only
+        k, v = kv.split("=")
+        chk.set_option(k, int(v))
     chk.set_environment(env)
     chk.set_agent([agent])
 

@@ -21,11 +21,17 @@
 
 #include "device_layout.hpp"
 
+#ifndef MPTCC_ENV_NO_L1
+#define MPTCC_ENV_NO_L1 0
+#endif
+
 namespace mptcc {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
+// plan word y: [31:24] candidate, [23] children are environment nodes, [22] single (root) test, [21:0] agent node
+constexpr unsigned kPlanEnv = 1u << 23, kPlanSingle = 1u << 22, kPlanIdxMask = (1u << 22) - 1u;
 constexpr float kU = 5.9604645e-8f;  // 2^-24, fp32 unit round-off
 
 // ------------------------------------------------------------------------------------------------
@@ -498,6 +504,18 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 // ------------------------------------------------------------------------------------------------
 // warp-cooperative traversal of one (environment object, agent link, pose) candidate
 // ------------------------------------------------------------------------------------------------
+// Environment node gathers: optionally keep them out of L1 so that they do not evict the small hot sets
+// (agent tree, broadphase tree, lane stacks).
+__device__ __forceinline__ float4 ld_env(const float4 *p) {
+#if MPTCC_ENV_NO_L1
+	float4 v;
+	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+#else
+	return __ldg(p);
+#endif
+}
+
 struct WarpMem {
 	uint2 *leafq;        // [kLeafQueueCap] (env prim, agent prim | cand << 24)
 	float4 *cand;        // [kCandCap][4] candidate records: R(9) T(3) S src node_base1 tri_base1
@@ -552,7 +570,7 @@ __device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevM
 		if (im && qhead < ncand) {
 			const int c = qhead + __popc(im & lt);
 			if (!has && c < ncand) {
-				cur = make_uint2(0u, (unsigned)c << 24);
+				cur = make_uint2(0u, kPlanSingle | ((unsigned)c << 24));  // root pair
 				has = true;
 			}
 			qhead += __popc(im);
@@ -585,7 +603,7 @@ __device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevM
 		const unsigned am = __ballot_sync(FULL, !idle);
 		if (am == 0u && lq == 0) break;
 
-		if (lq >= 32 || am == 0u) {
+		if (lq >= 32 || am == 0u) {  // (a node step adds at most 64 entries: capacity 32 + 64)
 			// ---- 3. leaf phase: up to 32 triangle pairs -------------------------------------------------
 			const int k = lq < 32 ? lq : 32;
 			lq -= k;
@@ -656,10 +674,14 @@ __device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevM
 			__syncwarp();
 			continue;
 		}
-		// ---- 4. node step: every busy lane tests its current pair; on overlap it keeps the left child
-		//         as the next current pair and stacks the right one (FCL visits left first) -------------
-		bool push_leaf = false;
-		uint2 leaf = make_uint2(0u, 0u);
+		// ---- 4. node step.  `cur` is a PLAN: a pair already known to overlap, stored as "the two children
+		//         of the tree FCL descends next, against the other node".  One step fetches the sibling
+		//         line (both children share 128 bytes) plus the other node and runs both tests: one memory
+		//         round trip per two OBB tests.  Survivors become plans themselves; the first child's plan
+		//         stays current and the second is stacked (FCL visits the first child first). -----------------
+		bool leaf0 = false, leaf1 = false;
+		uint2 lf0 = make_uint2(0u, 0u), lf1 = make_uint2(0u, 0u);
+		unsigned n_tests = 0;
 		if (has) {
 			const uint2 pr = cur;
 			has = false;
@@ -675,42 +697,61 @@ __device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevM
 				x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;
 				x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
 				x.S = r3.x;
-				const uint32_t b2 = pr.y & 0xffffffu;
 				const float4 *nodes1 = p.env.node32 + 4ull * __float_as_uint(r3.z);
-				const float4 *n1 = nodes1 + 4ull * pr.x;
-				const float4 *n2 = nodes2 + 4ull * b2;
-				const float4 a0 = __ldg(n1), a1 = __ldg(n1 + 1), a2 = __ldg(n1 + 2), a3 = __ldg(n1 + 3);
-				const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), bb2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
-				const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
-				const bool l1 = link1 < 0, l2 = link2 < 0;
-				const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
-				const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
-				const bool first = l2 || (!l1 && s1 > s2);  // descend the environment tree
-				if (!(l1 && l2)) {
-					// the children (one 128-byte line) are needed next if the boxes overlap: start the fetch now
-					const float4 *ch = first ? nodes1 + 4ull * (uint32_t)link1 : nodes2 + 4ull * (uint32_t)link2;
-					asm volatile("prefetch.global.L1 [%0];" ::"l"(ch));
-				}
-				if (!obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) {
+				const bool env_side = (pr.y & kPlanEnv) != 0u;  // the children are environment nodes
+				const bool single = (pr.y & kPlanSingle) != 0u; // root pair: one test
+				const uint32_t i2base = pr.y & kPlanIdxMask;
+				uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
+				bool ok0 = false, ok1 = false;
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					if (k == 1 && single) break;
+					const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
+					const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
+					const float4 *n1 = nodes1 + 4ull * i1;
+					const float4 *n2 = nodes2 + 4ull * i2;
+					const float4 a0 = ld_env(n1), a1 = ld_env(n1 + 1), a2 = ld_env(n1 + 2), a3 = ld_env(n1 + 3);
+					const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), bb2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
+					++n_tests;
+					if (obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) continue;
+					const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
+					const bool l1 = link1 < 0, l2 = link2 < 0;
 					if (l1 && l2) {
-						push_leaf = true;
-						leaf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
-					} else {
-						uint2 right;
-						if (first) {
-							cur = make_uint2((uint32_t)link1, pr.y);
-							right = make_uint2((uint32_t)link1 + 1u, pr.y);
-						} else {
-							cur = make_uint2(pr.x, (uint32_t)link2 | tag);
-							right = make_uint2(pr.x, ((uint32_t)link2 + 1u) | tag);
-						}
-						has = true;
-						stk[top++ & M] = right;
+						const uint2 lf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
+						if (k == 0) { leaf0 = true; lf0 = lf; } else { leaf1 = true; lf1 = lf; }
+						continue;
 					}
+					// firstOverSecond(i1, i2): descend the environment tree iff l2 || (!l1 && size1 > size2)
+					const float s1 = a3.x * a3.x + a3.y * a3.y + a3.z * a3.z;
+					const float s2 = b3.x * b3.x + b3.y * b3.y + b3.z * b3.z;
+					const bool first = l2 || (!l1 && s1 > s2);
+					const uint2 pl = first ? make_uint2((uint32_t)link1, i2 | kPlanEnv | tag)
+					                       : make_uint2(i1, (uint32_t)link2 | tag);
+					if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
+				}
+				if (ok0) {
+					cur = plan0;
+					has = true;
+					if (ok1) stk[top++ & M] = plan1;
+				} else if (ok1) {
+					cur = plan1;
+					has = true;
 				}
 			}
 		}
-		if (COUNT) ctr[CTR_BV] += (unsigned)__popc(am);
+		if (COUNT) {
+			unsigned t = n_tests;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+			ctr[CTR_BV] += t;
+		}
+		{
+			const unsigned lm0 = __ballot_sync(FULL, leaf0);
+			if (leaf0) wm.leafq[lq + __popc(lm0 & lt)] = lf0;
+			lq += __popc(lm0);
+		}
+		const bool push_leaf = leaf1;
+		const uint2 leaf = lf1;
 		const unsigned lm = __ballot_sync(FULL, push_leaf);
 		if (push_leaf) wm.leafq[lq + __popc(lm & lt)] = leaf;
 		lq += __popc(lm);

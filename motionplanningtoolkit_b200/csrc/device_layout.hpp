@@ -101,10 +101,13 @@ enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_
 
 constexpr int kClusterSize = 8;
 constexpr int kWarpsPerCta = 8;
-constexpr int kLeafQueueCap = 64;
+constexpr int kLeafQueueCap = 96;   // a node step appends <= 64 pairs; the leaf phase runs at >= 32
 constexpr int kClusterQueueCap = 64;  // (pose, cluster) entries waiting for the exact AABB test
 constexpr int kLaneStackCap = 64;     // per-lane depth-first stack (local memory); needs depth1 + depth2 + 2 <= 64
-constexpr int kCandCap = 96;          // candidate table: (pose, object) pairs traversed together (<= 256)
+#ifndef MPTCC_CAND_CAP
+#define MPTCC_CAND_CAP 96
+#endif
+constexpr int kCandCap = MPTCC_CAND_CAP;          // candidate table: (pose, object) pairs traversed together (<= 256)
 // per-warp shared memory: leaf queue + candidate table + pose boxes + fp64 relative transform +
 // candidate ids + cluster queue
 #ifdef __CUDACC__

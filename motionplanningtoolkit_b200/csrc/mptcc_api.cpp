@@ -615,7 +615,7 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 			ctx->link_model_h.push_back(it->second);
 			continue;
 		}
-		if (m.nt >= (1u << 23)) return fail(ctx, MPTCC_ERR_LIMIT, "agent link meshes are limited to 2^23 triangles");
+		if (m.nt >= (1u << 21)) return fail(ctx, MPTCC_ERR_LIMIT, "agent link meshes are limited to 2^21 triangles");
 		HostBvh b;
 		if (!build_bvh(m.xyz, m.nv, m.tri, m.nt, b))
 			return fail(ctx, MPTCC_ERR_INVALID, "agent link " + std::to_string(j) + " has an empty mesh");
