@@ -21,10 +21,6 @@
 
 #include "device_layout.hpp"
 
-#ifndef MPTCC_ENV_NO_L1
-#define MPTCC_ENV_NO_L1 0
-#endif
-
 namespace mptcc {
 namespace {
 
@@ -504,18 +500,6 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 // ------------------------------------------------------------------------------------------------
 // warp-cooperative traversal of one (environment object, agent link, pose) candidate
 // ------------------------------------------------------------------------------------------------
-// Environment node gathers: optionally keep them out of L1 so that they do not evict the small hot sets
-// (agent tree, broadphase tree, lane stacks).
-__device__ __forceinline__ float4 ld_env(const float4 *p) {
-#if MPTCC_ENV_NO_L1
-	float4 v;
-	asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-	return v;
-#else
-	return __ldg(p);
-#endif
-}
-
 struct WarpMem {
 	uint2 *leafq;        // [kLeafQueueCap] (env prim, agent prim | cand << 24)
 	float4 *cand;        // [kCandCap][4] candidate records: R(9) T(3) S src node_base1 tri_base1
@@ -698,20 +682,26 @@ __device__ u64 traverse_all(const KernelParams &p, const WarpMem &wm, const DevM
 				x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
 				x.S = r3.x;
 				const float4 *nodes1 = p.env.node32 + 4ull * __float_as_uint(r3.z);
-				const bool env_side = (pr.y & kPlanEnv) != 0u;  // the children are environment nodes
-				const bool single = (pr.y & kPlanSingle) != 0u; // root pair: one test
+				const bool single = (pr.y & kPlanSingle) != 0u;           // root pair: one test
+				const bool env_side = single || (pr.y & kPlanEnv) != 0u;  // the children are environment nodes
 				const uint32_t i2base = pr.y & kPlanIdxMask;
 				uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
 				bool ok0 = false, ok1 = false;
+				// the node that stays (fetched once) and the sibling line of the tree that is descended
+				const float4 *op = env_side ? nodes2 + 4ull * i2base : nodes1 + 4ull * pr.x;
+				const float4 *cp = env_side ? nodes1 + 4ull * pr.x : nodes2 + 4ull * i2base;
+				const float4 o0 = __ldg(op), o1 = __ldg(op + 1), o2 = __ldg(op + 2), o3 = __ldg(op + 3);
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
 					if (k == 1 && single) break;
 					const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
 					const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
-					const float4 *n1 = nodes1 + 4ull * i1;
-					const float4 *n2 = nodes2 + 4ull * i2;
-					const float4 a0 = ld_env(n1), a1 = ld_env(n1 + 1), a2 = ld_env(n1 + 2), a3 = ld_env(n1 + 3);
-					const float4 b0 = __ldg(n2), b1 = __ldg(n2 + 1), bb2 = __ldg(n2 + 2), b3 = __ldg(n2 + 3);
+					const float4 c0 = __ldg(cp + 4 * k), c1 = __ldg(cp + 4 * k + 1), c2 = __ldg(cp + 4 * k + 2),
+					             c3 = __ldg(cp + 4 * k + 3);
+					const float4 a0 = env_side ? c0 : o0, a1 = env_side ? c1 : o1, a2 = env_side ? c2 : o2,
+					             a3 = env_side ? c3 : o3;
+					const float4 b0 = env_side ? o0 : c0, b1 = env_side ? o1 : c1, bb2 = env_side ? o2 : c2,
+					             b3 = env_side ? o3 : c3;
 					++n_tests;
 					if (obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) continue;
 					const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
