@@ -212,3 +212,116 @@ def terrain(nx=708, ny=708, extent=200.0, height=6.0, seed=SEED_ENV):
 
 def fixture(name):
     return meshio.load_mptm(name)
+
+
+# ---------------------------------------------------------------------------------------------------
+# pose producers of the reference's agents (inputs of the hot path; restated verbatim incl. quirks)
+# ---------------------------------------------------------------------------------------------------
+
+def _normalize_theta(t):
+    """Blimp/SnakeTrailers::normalizeTheta (/root/reference/agents/blimp.hpp:358-360)."""
+    return t - 2 * np.pi * np.floor((t + np.pi) / (2 * np.pi))
+
+
+def _rz_convention(theta, T):
+    """R(0,0)=c, R(1,0)=-s, R(0,1)=s, R(1,1)=c (blimp.hpp:350-353, snake_trailers.hpp:427-430)."""
+    n = len(theta)
+    R = np.tile(np.eye(3), (n, 1, 1))
+    c, s = np.cos(theta), np.sin(theta)
+    R[:, 0, 0] = c
+    R[:, 1, 0] = -s
+    R[:, 0, 1] = s
+    R[:, 1, 1] = c
+    return poses_rt12(R, T)
+
+
+BLIMP_INST = dict(length=10.0, vmin=-1.0, vmax=5.0, psi_min=-0.785398, psi_max=0.785398, vz_min=-5.0, vz_max=5.0)
+
+
+def blimp_do_step(s, a, w, z, dt, P=BLIMP_INST):
+    """Blimp::doStep (/root/reference/agents/blimp.hpp:293-317); state columns x y z theta v psi vz.
+    (theta advances by v*tan(psi)/length WITHOUT dt, as in the reference.)"""
+    x, y, zz, th, v, psi, vz = s.T
+    n = np.empty_like(s)
+    n[:, 0] = x + np.cos(th) * v * dt
+    n[:, 1] = y + np.sin(th) * v * dt
+    n[:, 3] = _normalize_theta(th + v * np.tan(psi) / P["length"])
+    n[:, 2] = zz + vz * dt
+    n[:, 4] = np.clip(v + a * dt, P["vmin"], P["vmax"])
+    n[:, 5] = np.clip(psi + w * dt, P["psi_min"], P["psi_max"])
+    n[:, 6] = np.clip(vz + z * dt, P["vz_min"], P["vz_max"])
+    return n
+
+
+def blimp_edge_poses(rng, n_edges, lo, hi, steps=10, dt=0.1):
+    """uniform start states inside [lo,hi], uniform controls (a in [-1,1], w in
+    [-0.1745,0.1745], z in [-1,1], blimp.hpp:123), `steps` poses per edge via stateToFCLTransform
+    (blimp.hpp:339-356; Blimp::getPoses itself is a stub, SURVEY Q3).  Returns (poses [n*steps,12],
+    seg_begin [n+1])."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    s = np.zeros((n_edges, 7))
+    for k in range(3):
+        s[:, k] = rng.uniform(n_edges, lo[k], hi[k])
+    s[:, 3] = rng.uniform(n_edges, -np.pi, np.pi)
+    s[:, 4] = rng.uniform(n_edges, BLIMP_INST["vmin"], BLIMP_INST["vmax"])
+    s[:, 5] = rng.uniform(n_edges, BLIMP_INST["psi_min"], BLIMP_INST["psi_max"])
+    s[:, 6] = rng.uniform(n_edges, BLIMP_INST["vz_min"], BLIMP_INST["vz_max"])
+    a, w, z = rng.uniform(n_edges, -1, 1), rng.uniform(n_edges, -0.1745, 0.1745), rng.uniform(n_edges, -1, 1)
+    out = np.empty((n_edges, steps, 12))
+    for i in range(steps):
+        out[:, i] = _rz_convention(s[:, 3], s[:, :3])
+        s = blimp_do_step(s, a, w, z, dt)
+    return out.reshape(-1, 12), np.arange(n_edges + 1, dtype=np.uint64) * steps
+
+
+SNAKE_INST = dict(trailers=10, length=1.0, hitch=0.25, vmin=-1.0, vmax=5.0, psi_min=-0.785398, psi_max=0.785398)
+
+
+def snake_state_poses(states, P=SNAKE_INST):
+    """SnakeTrailers::stateToFCLTransforms (/root/reference/agents/snake_trailers.hpp:411-459), verbatim
+    including Q4: every trailer sits at (-(L+h), y0, 0) and carries the RELATIVE hitch rotation.
+    states: [n, 5 + trailers] = x y theta v psi theta_1..theta_k.  Returns [n, trailers+1, 12]."""
+    n, k = len(states), P["trailers"]
+    out = np.empty((n, k + 1, 12))
+    T = np.zeros((n, 3))
+    T[:, 0], T[:, 1] = states[:, 0], states[:, 1]
+    out[:, 0] = _rz_convention(states[:, 2], T)
+    T = T.copy()
+    T[:, 0] = -(P["length"] + P["hitch"])
+    th = np.concatenate([states[:, 2:3], states[:, 5:5 + k]], axis=1)   # THETA, THETA+1, ...
+    for i in range(1, k + 1):
+        out[:, i] = _rz_convention(th[:, i] - th[:, i - 1], T)
+    return out
+
+
+def snake_random_states(rng, n, lo, hi, P=SNAKE_INST):
+    k = P["trailers"]
+    s = np.zeros((n, 5 + k))
+    s[:, 0], s[:, 1] = rng.uniform(n, lo[0], hi[0]), rng.uniform(n, lo[1], hi[1])
+    s[:, 2] = rng.uniform(n, -np.pi, np.pi)
+    s[:, 3] = rng.uniform(n, P["vmin"], P["vmax"])
+    s[:, 4] = rng.uniform(n, P["psi_min"], P["psi_max"])
+    for i in range(k):
+        s[:, 5 + i] = _normalize_theta(s[:, 2] + rng.uniform(n, -0.6, 0.6))
+    return s
+
+
+def prm_slice_edges(rng, n_milestones, lo, hi, k=10, dt=0.1, existing=None):
+    """BASELINE.md C2 / PRM::addMilestone (/root/reference/planners/prm/prm.hpp:334-387): every new
+    milestone is connected by a full straight edge (Omnidirectional::steer with fraction clamped to 1) to
+    its k nearest EARLIER milestones; each edge is interpolated at dt.  Returns (poses, seg_begin, points)."""
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    pts = np.stack([rng.uniform(n_milestones, lo[a], hi[a]) for a in range(3)], axis=1)
+    allp = pts if existing is None else np.concatenate([existing, pts])
+    first = 0 if existing is None else len(existing)
+    segs, chunks = [0], []
+    for i in range(first, len(allp)):
+        if i == 0:
+            continue
+        d = np.linalg.norm(allp[:i] - allp[i], axis=1)
+        for j in np.argsort(d, kind="stable")[:k]:
+            e = omnidirectional_edge_poses(allp[i], allp[j], dt)
+            chunks.append(e)
+            segs.append(segs[-1] + len(e))
+    T = np.concatenate(chunks) if chunks else np.zeros((0, 3))
+    return translation_poses(T), np.asarray(segs, dtype=np.uint64), allp
