@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 								const bool out = (e0 > wm.box[3 * 32 + sl]) | (e1 > wm.box[4 * 32 + sl]) |
 								                 (e2 > wm.box[5 * 32 + sl]) | (e3 < wm.box[0 * 32 + sl]) |
 								                 (e4 < wm.box[1 * 32 + sl]) | (e5 < wm.box[2 * 32 + sl]);
-								ov = !out;
+								ov = !out && eobj < p.n_objects;  // (a NaN box "overlaps" the padding boxes too)
 							}
 						}
 						const unsigned om = __ballot_sync(FULL, ov);
