@@ -102,6 +102,13 @@ int main(int argc, char **argv) {
 		edges.push_back(e);
 	}
 	const std::vector<bool> batched = workspace.safeEdges(agent, edges, ccDT);
+	// the same edges with the interpolation done on the device
+	std::vector<double> startEnd;
+	for (const auto &e : edges) {
+		startEnd.insert(startEnd.end(), e.start.v, e.start.v + 3);
+		startEnd.insert(startEnd.end(), e.end.v, e.end.v + 3);
+	}
+	const std::vector<bool> onDevice = workspace.safeStraightEdges(agent, startEnd, ccDT);
 	FILE *f = fopen(argv[4], "wb");
 	const uint64_t n64 = n;
 	fwrite(&n64, 8, 1, f);
@@ -111,6 +118,7 @@ int main(int argc, char **argv) {
 		const uint8_t b = batched[i], s = single;
 		n_safe += b;
 		n_diff += b != s;
+		n_diff += onDevice[i] != batched[i];
 		fwrite(edges[i].start.v, 8, 3, f);
 		fwrite(edges[i].end.v, 8, 3, f);
 		fwrite(&b, 1, 1, f);

@@ -73,6 +73,11 @@ public:
 				}
 		return safe;
 	}
+	// Edges of translation-only agents (Omnidirectional): only (start, end) cross the PCIe bus, the poses
+	// are interpolated on the device.  result[i] == safeEdge(agent, Edge(start_i, end_i), dt).
+	std::vector<bool> safeStraightEdges(const Agent &agent, const std::vector<double> &startEnd, double dt) const {
+		return MeshHandler::safeStraightEdges(mesh, agent.getMeshes(), startEnd, dt);
+	}
 	// result[i] == safePoses(agent, {poseSets[i]})
 	std::vector<bool> safePosesBatch(const Agent &agent, const std::vector<std::vector<fcl::Transform3f> > &poseSets) const {
 		auto agentMeshes = agent.getMeshes();

@@ -220,6 +220,21 @@ public:
 		return verdict;
 	}
 
+	// straight, translation-only edges (start xyz, end xyz) interpolated ON THE DEVICE with the
+	// rule of Omnidirectional::getPoses (agents/omnidirectional.hpp:202-247); result[i] = edge i is safe.
+	static std::vector<bool> safeStraightEdges(const StaticEnvironmentMeshHandler &environment,
+	                                           const std::vector<const SimpleAgentMeshHandler *> &agent,
+	                                           const std::vector<double> &startEnd /* 6 per edge */, double dt) {
+		const size_t n = startEnd.size() / 6;
+		std::vector<bool> safe(n, true);
+		if (n == 0) return safe;
+		mptcc_ctx *ctx = environment.getCollisionChecker(agent);
+		std::vector<uint8_t> out(n, 0);
+		environment.check(mptcc_check_omni_edges(ctx, n, startEnd.data(), dt, out.data()), "mptcc_check_omni_edges");
+		for (size_t i = 0; i < n; ++i) safe[i] = out[i] != 0;
+		return safe;
+	}
+
 	// The reference's signature and meaning: one bool for the whole batch of pose-sets.
 	static bool isInCollision(const StaticEnvironmentMeshHandler &environment,
 	                          const std::vector<const SimpleAgentMeshHandler *> &agent,

@@ -103,6 +103,13 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n_pose_sets, const double *poses,
 int mptcc_check_segments(mptcc_ctx *ctx, uint64_t n_segments, const uint64_t *seg_begin, const double *poses,
                          int pose_format, uint8_t *segment_safe);
 
+/* Omnidirectional::getPoses on the device (/root/reference/agents/omnidirectional.hpp:202-247):
+ * edge e = start xyz, end xyz (6 doubles); its pose-sets are the reference's translation-only interpolation
+ * at spacing dt (iterations = (unsigned)(dist/dt); {start,end} if 0; the end pose is appended iff
+ * iterations*dt < dist), generated on the GPU with the reference's fp64 arithmetic.
+ * edge_safe[e] = 1 iff none collides (Map3D::safeEdge).  Needs a single-link agent. */
+int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start_end, double dt, uint8_t *edge_safe);
+
 /* ---- queries: device buffers (inputs already resident in HBM) -------------------------------- */
 /* d_poses / d_verdict_bits are device pointers on device slot `slot` (0..n_devices-1); the launch is
  * enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's stream) and NOT synchronised. */

@@ -20,7 +20,7 @@ _ERR_NAMES = {1: "INVALID", 2: "STATE", 3: "NO_DEVICE", 4: "CUDA", 5: "NOMEM", 6
 # every symbol include/mptcc.h declares (tests check that the library exports exactly these)
 EXPORTS = [
     "mptcc_create", "mptcc_destroy", "mptcc_last_error", "mptcc_num_devices", "mptcc_set_environment",
-    "mptcc_set_agent", "mptcc_check_poses", "mptcc_check_segments", "mptcc_check_poses_device",
+    "mptcc_set_agent", "mptcc_check_poses", "mptcc_check_segments", "mptcc_check_omni_edges", "mptcc_check_poses_device",
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_set_option",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
@@ -74,6 +74,8 @@ def load():
     L.mptcc_check_poses.argtypes = [vp, C.c_uint64, vp, C.c_int, vp]
     L.mptcc_check_segments.restype = C.c_int
     L.mptcc_check_segments.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_int, C.POINTER(C.c_uint8)]
+    L.mptcc_check_omni_edges.restype = C.c_int
+    L.mptcc_check_omni_edges.argtypes = [vp, C.c_uint64, vp, C.c_double, vp]
     L.mptcc_check_poses_device.restype = C.c_int
     L.mptcc_check_poses_device.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, vp]
     L.mptcc_synchronize.restype = C.c_int
@@ -224,6 +226,13 @@ class Checker:
         safe = np.zeros(len(sb) - 1, np.uint8)
         self._check(self.lib.mptcc_check_segments(self.h, len(sb) - 1, sb.ctypes.data_as(C.POINTER(C.c_uint64)),
                                                   p.ctypes.data, fmt, safe.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return safe.astype(bool)
+
+    def check_omni_edges(self, start_end, dt):
+        """start_end: float64 [n, 6]; poses are interpolated on the device (Omnidirectional::getPoses)."""
+        e = np.ascontiguousarray(start_end, dtype=np.float64).reshape(-1, 6)
+        safe = np.zeros(len(e), np.uint8)
+        self._check(self.lib.mptcc_check_omni_edges(self.h, len(e), e.ctypes.data, float(dt), safe.ctypes.data))
         return safe.astype(bool)
 
     def check_poses_device(self, n, d_poses_ptr, d_bits_ptr, fmt=POSE_RT12, slot=0, stream=None):

@@ -122,4 +122,10 @@ inline constexpr unsigned warp_smem_bytes() {
 int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
 int collide_max_ctas_per_sm(bool count);
 
+// edge_kernels.cu
+int launch_expand_omni_edges(const double *d_edges, const unsigned long long *d_offsets, unsigned long long n_edges,
+                             unsigned long long total_poses, double dt, double *d_poses, void *stream);
+int launch_reduce_segments(const uint32_t *d_bits, const unsigned long long *d_offsets, unsigned long long n_segments,
+                           unsigned char *d_safe, void *stream);
+
 }  // namespace mptcc

@@ -329,6 +329,13 @@ struct Device {
 	DevBuf<uint32_t> work[kPipe];
 	DevBuf<unsigned long long> counters;
 	DevBuf<uint32_t> work_user;  // work counter of the device-buffer entry point
+	// on-device edge interpolation (mptcc_check_omni_edges)
+	DevBuf<double> edge_in;
+	DevBuf<unsigned long long> edge_off;
+	DevBuf<double> edge_poses;
+	DevBuf<uint32_t> edge_bits;
+	DevBuf<unsigned char> edge_safe;
+	DevBuf<uint32_t> edge_work;
 	float last_ms = 0.f;
 };
 
@@ -526,6 +533,12 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.link_model.release();
 		d.counters.release();
 		d.work_user.release();
+		d.edge_in.release();
+		d.edge_off.release();
+		d.edge_poses.release();
+		d.edge_bits.release();
+		d.edge_safe.release();
+		d.edge_work.release();
 		for (int k = 0; k < kPipe; ++k) {
 			d.poses[k].release();
 			d.bits[k].release();
@@ -719,6 +732,63 @@ int mptcc_check_segments(mptcc_ctx *ctx, uint64_t n_segments, const uint64_t *se
 				break;
 			}
 		segment_safe[s] = safe;
+	}
+	return MPTCC_OK;
+}
+
+// Number of pose-sets Omnidirectional::getPoses produces for one edge (omnidirectional.hpp:216-244).
+static uint64_t omni_pose_count(const double *e, double dt) {
+	const double dx = e[3] - e[0], dy = e[4] - e[1], dz = e[5] - e[2];
+	const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+	const double ratio = dist / dt;
+	const unsigned int iterations = ratio >= 1.0 ? (ratio < 4294967295.0 ? (unsigned int)ratio : 4294967295u) : 0u;
+	if (iterations < 1) return 2;
+	return (uint64_t)iterations + (((double)iterations * dt < dist) ? 1u : 0u);
+}
+
+int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start_end, double dt, uint8_t *edge_safe) {
+	int rc = check_ready(ctx);
+	if (rc != MPTCC_OK) return rc;
+	if (ctx->link_model_h.size() != 1) return fail(ctx, MPTCC_ERR_STATE, "mptcc_check_omni_edges needs a single-link agent");
+	if (!(dt > 0.0)) return fail(ctx, MPTCC_ERR_INVALID, "dt must be positive");
+	if (n_edges == 0) return MPTCC_OK;
+	if (!start_end || !edge_safe) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
+	// sub-batches of edges whose poses fit the device-side pose buffer, round-robin over the devices
+	const uint64_t max_poses = 1ull << 21;
+	const size_t nd = ctx->devs.size();
+	std::vector<unsigned long long> off;
+	uint64_t e0 = 0;
+	size_t turn = 0;
+	while (e0 < n_edges) {
+		off.assign(1, 0ull);
+		uint64_t e1 = e0;
+		while (e1 < n_edges && (off.back() < max_poses || e1 == e0)) {
+			off.push_back(off.back() + omni_pose_count(start_end + 6 * e1, dt));
+			++e1;
+		}
+		const uint64_t ne = e1 - e0, np = off.back();
+		Device &d = ctx->devs[turn % nd];
+		++turn;
+		CU(cudaSetDevice(d.id));
+		cudaStream_t s = d.stream[0];
+		CU(cudaStreamSynchronize(s));  // the host vector `off` and the device buffers are reused
+		CU(d.edge_in.reserve(6 * ne));
+		CU(d.edge_off.reserve(ne + 1));
+		CU(d.edge_poses.reserve(12 * np));
+		CU(d.edge_bits.reserve((np + 31) / 32));
+		CU(d.edge_safe.reserve(ne));
+		CU(d.edge_work.reserve(1));
+		CU(cudaMemcpyAsync(d.edge_in.p, start_end + 6 * e0, sizeof(double) * 6 * ne, cudaMemcpyHostToDevice, s));
+		CU(cudaMemcpyAsync(d.edge_off.p, off.data(), sizeof(unsigned long long) * (ne + 1), cudaMemcpyHostToDevice, s));
+		int e = launch_expand_omni_edges(d.edge_in.p, d.edge_off.p, ne, np, dt, d.edge_poses.p, s);
+		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "expand_omni_edges launch");
+		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_RT12, d.edge_bits.p, d.edge_work.p, s);
+		if (rc != MPTCC_OK) return rc;
+		e = launch_reduce_segments(d.edge_bits.p, d.edge_off.p, ne, d.edge_safe.p, s);
+		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "reduce_segments launch");
+		CU(cudaMemcpyAsync(edge_safe + e0, d.edge_safe.p, ne, cudaMemcpyDeviceToHost, s));
+		CU(cudaStreamSynchronize(s));  // `off` goes out of scope / is rewritten next round
+		e0 = e1;
 	}
 	return MPTCC_OK;
 }

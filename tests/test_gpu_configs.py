@@ -93,3 +93,30 @@ def test_non_finite_poses_match_oracle(built):
     poses[130, 4] = -np.inf
     chk = sc.checker()
     assert_bits_equal(chk.check_poses(poses), sc.oracle_bits(poses), len(poses), "non-finite poses")
+
+
+def test_on_device_edge_interpolation(built):
+    """N2: mptcc_check_omni_edges == check_segments over host-interpolated poses == the oracle."""
+    b = unit_box()
+    sc = Scene([b], [b])
+    rng = scenes.SplitMix64(31)
+    n = 5000
+    start = np.stack([rng.uniform(n, -3, 3) for _ in range(3)], 1)
+    length = rng.uniform(n, 0.0, 4.0)
+    d = np.stack([rng.uniform(n, -1, 1) for _ in range(3)], 1)
+    end = start + d / np.linalg.norm(d, axis=1, keepdims=True) * length[:, None]
+    end[:5] = start[:5]                                   # zero-length edges: {start, end}
+    end[5:10] = start[5:10] + [[1.0, 0, 0]] * 5           # dist/dt exactly 10: no end pose (reference quirk)
+    edges = np.concatenate([start, end], axis=1)
+    chk = sc.checker()
+    got = chk.check_omni_edges(edges, 0.1)
+    segs, allp = [0], []
+    for i in range(n):
+        pts = scenes.omnidirectional_edge_poses(start[i], end[i], 0.1)
+        allp.append(pts)
+        segs.append(segs[-1] + len(pts))
+    poses = scenes.translation_poses(np.concatenate(allp))
+    assert np.array_equal(got, chk.check_segments(segs, poses))
+    hit = O.unpack_bits(sc.oracle_bits(poses), len(poses))
+    want = np.array([not hit[segs[i]:segs[i + 1]].any() for i in range(n)])
+    assert np.array_equal(got, want) and 0 < want.sum() < n
