@@ -129,7 +129,7 @@ int mptcc_reset_counters(mptcc_ctx *ctx);
 /* Milliseconds of the kernels of the last host-buffer check call on device slot `slot`
  * (CUDA events on the launching stream). */
 int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
-/* Tuning knobs: "poses_per_warp" (0 = auto, 1..32 power of two), "ctas_per_sm", "sub_batch". */
+/* Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1), "split_min", "split_cap", "always_replay". */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */

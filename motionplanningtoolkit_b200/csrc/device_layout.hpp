@@ -90,6 +90,15 @@ struct KernelParams {
 	unsigned long long n_pose_sets;
 	uint32_t *verdict_bits;
 	uint32_t *work_counter;
+	// split pipeline (split_kernels.cu): candidate list written by the broadphase kernel
+	float4 *cand_rec;               // [cand_cap][4] fp32 candidate records
+	uint32_t *cand_obj;             // [cand_cap] environment object of the candidate
+	uint32_t *cand_pose;            // [cand_cap] pose-set index of the candidate
+	unsigned int *cand_total;       // [1] candidates appended (can exceed cand_cap: then *overflow = 1)
+	unsigned int *overflow;         // [1]
+	unsigned int cand_cap;
+	const unsigned int *run_if;     // fused kernel: return at once unless *run_if != 0 (nullptr: always run)
+	uint32_t *work_counter2;        // batch counter of the narrowphase kernel
 	unsigned long long *counters;  // [CTR_N] or nullptr
 	uint32_t steal_bottom;         // 1: thieves take the bottom (largest, most speculative) pending pair
 	uint32_t no_steal;             // 1: lanes never steal pending subtrees (experiment knob)
@@ -121,6 +130,11 @@ inline constexpr unsigned warp_smem_bytes() {
 // Launch wrapper implemented in collide_kernel.cu.  Returns a cudaError_t as int.
 int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
 int collide_max_ctas_per_sm(bool count);
+
+// split_kernels.cu: broadphase kernel (poses -> candidate list) and narrowphase kernel (candidate list ->
+// verdict bits); single-link agents.
+int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *stream);
+int launch_narrowphase(const KernelParams &p, int sm_count, bool count, void *stream);
 
 // edge_kernels.cu
 int launch_expand_omni_edges(const double *d_edges, const unsigned long long *d_offsets, unsigned long long n_edges,

@@ -314,6 +314,19 @@ struct DevPack {
 
 constexpr int kPipe = 2;  // ping-pong staging sets per device
 
+// Buffers of the split pipeline (split_kernels.cu) for one launch slot; grow-only.
+struct SplitBufs {
+	DevBuf<float4> rec;
+	DevBuf<uint32_t> obj, pose;
+	DevBuf<unsigned int> ctl;  // [0] cand_total, [1] overflow, [2] narrowphase batch counter
+	void release() {
+		rec.release();
+		obj.release();
+		pose.release();
+		ctl.release();
+	}
+};
+
 struct Device {
 	int id = 0;
 	int sm_count = 0;
@@ -329,6 +342,7 @@ struct Device {
 	DevBuf<uint32_t> work[kPipe];
 	DevBuf<unsigned long long> counters;
 	DevBuf<uint32_t> work_user;  // work counter of the device-buffer entry point
+	SplitBufs split[kPipe + 2];  // staging sets, device-buffer entry point, edge entry point
 	// on-device edge interpolation (mptcc_check_omni_edges)
 	DevBuf<double> edge_in;
 	DevBuf<unsigned long long> edge_off;
@@ -355,6 +369,9 @@ struct mptcc_ctx {
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
 	long opt_sub_batch = 1 << 18;
 	long opt_always_replay = 0;
+	long opt_split = 1;              // two-kernel pipeline for large single-link batches
+	long opt_split_min = 1 << 15;    // ... from this many pose-sets per launch
+	long opt_split_cap = 3;          // candidate list capacity, per pose-set
 	long opt_no_steal = 0;
 	long opt_steal_bottom = 0;
 	mptcc_counters ctr{};
@@ -452,13 +469,23 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
 	kp.counters = ctx->count ? d.counters.p : nullptr;
 	kp.always_replay = ctx->opt_always_replay ? 1u : 0u;
+	kp.cand_rec = nullptr;
+	kp.cand_obj = nullptr;
+	kp.cand_pose = nullptr;
+	kp.cand_total = nullptr;
+	kp.overflow = nullptr;
+	kp.cand_cap = 0;
+	kp.run_if = nullptr;
+	kp.work_counter2 = nullptr;
 	kp.no_steal = ctx->opt_no_steal ? 1u : 0u;
 	kp.steal_bottom = ctx->opt_steal_bottom ? 1u : 0u;
 }
 
-// Enqueue (memsets +) kernel for n pose-sets already on the device.
+// Enqueue (memsets +) kernels for n pose-sets already on the device.  Large single-link batches take the
+// split pipeline (broadphase kernel -> candidate list -> narrowphase kernel, then the fused kernel as a
+// conditional overflow fall-back); everything else the fused kernel.
 int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
-                   uint32_t *d_work, cudaStream_t s) {
+                   uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr) {
 	KernelParams kp;
 	fill_params(ctx, d, kp);
 	const int grid = grid_for(ctx, d);
@@ -468,6 +495,38 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	kp.verdict_bits = d_bits;
 	kp.work_counter = d_work;
 	kp.ppw_log2 = pick_ppw_log2(ctx, n, grid);
+	const bool split = sb != nullptr && ctx->opt_split && ctx->link_model_h.size() == 1 && n >= (uint64_t)ctx->opt_split_min &&
+	                   n < (1ull << 32) && !ctx->objects_h.empty();
+	if (split) {
+		const uint64_t cap64 = std::min<uint64_t>(n * (uint64_t)ctx->opt_split_cap, 0xfffffff0ull);
+		CU(sb->rec.reserve(4 * cap64));
+		CU(sb->obj.reserve(cap64));
+		CU(sb->pose.reserve(cap64));
+		CU(sb->ctl.reserve(4));
+		kp.cand_rec = sb->rec.p;
+		kp.cand_obj = sb->obj.p;
+		kp.cand_pose = sb->pose.p;
+		kp.cand_total = sb->ctl.p;
+		kp.overflow = sb->ctl.p + 1;
+		kp.work_counter2 = sb->ctl.p + 2;
+		kp.cand_cap = (unsigned int)cap64;
+		CU(cudaMemsetAsync(sb->ctl.p, 0, 4 * sizeof(unsigned int), s));
+		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
+		CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
+		int e = launch_broadphase(kp, d.sm_count, ctx->count, s);
+		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "broadphase_kernel launch");
+		e = launch_narrowphase(kp, d.sm_count, ctx->count, s);
+		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase_kernel launch");
+		// overflow fall-back: the fused kernel returns at once unless the candidate list overflowed
+		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
+		kp.run_if = kp.overflow;
+		kp.ppw_log2 = 4;  // atomicOr into the words the split kernels already wrote
+		e = launch_collide(kp, grid, ctx->count, s);
+		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel (fall-back) launch");
+		ctx->ctr.n_kernel_launches += 3;
+		ctx->ctr.n_pose_sets += n;
+		return MPTCC_OK;
+	}
 	CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 	if (kp.ppw_log2 < 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
 	const uint64_t chunks = (n + (1ull << kp.ppw_log2) - 1) >> kp.ppw_log2;
@@ -533,6 +592,7 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.link_model.release();
 		d.counters.release();
 		d.work_user.release();
+		for (auto &sb : d.split) sb.release();
 		d.edge_in.release();
 		d.edge_off.release();
 		d.edge_poses.release();
@@ -691,7 +751,7 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 			CU(d.bits[k].reserve(jb.w1 - jb.w0));
 			CU(cudaMemcpyAsync(d.poses[k].p, poses + p0 * rec, sizeof(double) * cnt * rec, cudaMemcpyHostToDevice, d.stream[k]));
 			CU(cudaEventRecord(d.ev0[k], d.stream[k]));
-			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k]);
+			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k], &d.split[k]);
 			if (rc != MPTCC_OK) return rc;
 			CU(cudaEventRecord(d.ev1[k], d.stream[k]));
 			CU(cudaMemcpyAsync(verdict_bits + jb.w0, d.bits[k].p, sizeof(uint32_t) * (jb.w1 - jb.w0), cudaMemcpyDeviceToHost,
@@ -782,7 +842,7 @@ int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start
 		CU(cudaMemcpyAsync(d.edge_off.p, off.data(), sizeof(unsigned long long) * (ne + 1), cudaMemcpyHostToDevice, s));
 		int e = launch_expand_omni_edges(d.edge_in.p, d.edge_off.p, ne, np, dt, d.edge_poses.p, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "expand_omni_edges launch");
-		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_RT12, d.edge_bits.p, d.edge_work.p, s);
+		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_RT12, d.edge_bits.p, d.edge_work.p, s, &d.split[kPipe + 1]);
 		if (rc != MPTCC_OK) return rc;
 		e = launch_reduce_segments(d.edge_bits.p, d.edge_off.p, ne, d.edge_safe.p, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "reduce_segments launch");
@@ -804,7 +864,7 @@ int mptcc_check_poses_device(mptcc_ctx *ctx, int slot, uint64_t n, const double 
 	Device &d = ctx->devs[slot];
 	CU(cudaSetDevice(d.id));
 	cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : d.stream[0];
-	return enqueue_kernel(ctx, d, n, d_poses, fmt, d_bits, d.work_user.p, s);
+	return enqueue_kernel(ctx, d, n, d_poses, fmt, d_bits, d.work_user.p, s, &d.split[kPipe]);
 }
 
 int mptcc_synchronize(mptcc_ctx *ctx) {
@@ -884,6 +944,14 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 		ctx->opt_steal_bottom = value != 0;
 	} else if (k == "no_steal") {
 		ctx->opt_no_steal = value != 0;
+	} else if (k == "split") {
+		ctx->opt_split = value != 0;
+	} else if (k == "split_min") {
+		if (value < 32) return fail(ctx, MPTCC_ERR_INVALID, "split_min: >= 32");
+		ctx->opt_split_min = value;
+	} else if (k == "split_cap") {
+		if (value < 1 || value > 64) return fail(ctx, MPTCC_ERR_INVALID, "split_cap: 1..64 candidates per pose-set");
+		ctx->opt_split_cap = value;
 	} else if (k == "always_replay") {
 		ctx->opt_always_replay = value != 0;
 	} else if (k == "sub_batch") {

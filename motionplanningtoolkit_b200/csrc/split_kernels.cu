@@ -1,0 +1,267 @@
+// split_kernels.cu -- the two-kernel pipeline of libmptcc for large batches of single-link pose-sets.
+//
+//   broadphase_kernel  : phases A-C2 of collide_device.cuh for chunks of 32 pose-sets.  It has no traversal
+//                        state, so it runs at a much higher occupancy than the fused kernel and hides the
+//                        latency of its dependent loads (pose records, tree walk, object boxes) with warps.
+//                        Output: a global list of candidates (pose-set, environment object, fp32 record),
+//                        the candidates of one pose-set adjacent.
+//   narrowphase_kernel : persistent warps take batches of kCandCap candidates from that list, whatever
+//                        pose-sets they belong to, and run the depth-first lane traversal (traverse_all) on
+//                        them: no chunk boundaries, always a full table, perfect load balance.  Hits are
+//                        published with atomicOr into the (zeroed) verdict words.
+//
+// If the list overflows its capacity the broadphase sets *overflow and the host-enqueued fused kernel, which
+// is launched right after with run_if = overflow, recomputes the launch (verdict bits only ever get set for
+// colliding pose-sets, so OR-ing both results is exact).
+#include "collide_device.cuh"
+
+namespace mptcc {
+namespace {
+
+constexpr int kBpWarpsPerCta = 8;
+
+// per-warp shared memory of the broadphase kernel: pose boxes + cluster queue + candidate ids
+__host__ __device__ constexpr unsigned bp_warp_smem_bytes() { return 6u * 32u * 8u + kClusterQueueCap * 4u + kCandCap * 4u + 32u * 4u; }
+
+// per-warp shared memory of the narrowphase kernel
+__host__ __device__ constexpr unsigned np_warp_smem_bytes() {
+	return kLeafQueueCap * 8u + kCandCap * 64u + 16u * 8u + kCandCap * 4u + kCandCap * 4u + kCandCap + 32u;
+}
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	unsigned char *base = smem_raw + (size_t)warp * bp_warp_smem_bytes();
+	WarpMem wm{};
+	wm.box = reinterpret_cast<double *>(base);
+	base += 6 * 32 * 8;
+	wm.clq = reinterpret_cast<uint32_t *>(base);
+	base += kClusterQueueCap * 4;
+	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
+	base += kCandCap * 4;
+	unsigned *pfx = reinterpret_cast<unsigned *>(base);  // [32] first list position of each pose slot's run
+
+	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
+	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const unsigned lt = (1u << lane) - 1u;
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+	unsigned long long n_cand_total = 0;
+
+	while (true) {
+		unsigned chunk = 0;
+		if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
+		chunk = __shfl_sync(FULL, chunk, 0);
+		if (chunk >= n_chunks) break;
+		const unsigned long long pose0 = (unsigned long long)chunk << 5;
+		const unsigned long long left = p.n_pose_sets - pose0;
+		const unsigned nvalid = left < 32ull ? (unsigned)left : 32u;
+		const bool valid = (unsigned)lane < nvalid;
+		const double *chunk_poses = p.poses + pose0 * rec_len;
+
+		// ---- phase A ------------------------------------------------------------------------------------
+		float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
+		if (valid) pose_world_box(chunk_poses + (size_t)lane * rec_len, p.pose_format, m2, wm.box + lane, amin, amax);
+		__syncwarp();
+		unsigned node = valid ? 0u : p.n_bp_nodes;
+		int ncl = 0, ncand = 0;
+		bool more = true;
+		while (more || ncl > 0 || ncand > 0) {
+			// ---- phase B ----------------------------------------------------------------------------------
+			while (more && ncl <= kClusterQueueCap - 32) {
+				const bool act = node < p.n_bp_nodes;
+				if (!__any_sync(FULL, act)) {
+					more = false;
+					break;
+				}
+				unsigned cl = 0;
+				const bool leaf_hit = act && bp_tree_step(p, node, amin, amax, cl);
+				const unsigned m = __ballot_sync(FULL, leaf_hit);
+				if (m) {
+					if (leaf_hit) wm.clq[ncl + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
+					ncl += __popc(m);
+				}
+			}
+			__syncwarp();
+			// ---- phase C1 ---------------------------------------------------------------------------------
+			constexpr int kPer = 32 / kClusterSize;
+			int c = 0;
+			for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
+				const int idx = c + lane / kClusterSize;
+				bool ov = false;
+				unsigned sl = 0, eobj = 0;
+				if (idx < ncl) {
+					const unsigned ent = wm.clq[idx];
+					sl = ent >> 27;
+					eobj = (ent & 0x7ffffffu) * kClusterSize + (unsigned)(lane % kClusterSize);
+					ov = exact_aabb_overlap(p, wm, eobj, sl);
+				}
+				const unsigned om = __ballot_sync(FULL, ov);
+				if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (sl << 26) | eobj;
+				ncand += __popc(om);
+			}
+			if (c > ncl) c = ncl;
+			if (c < ncl) {  // keep the unprocessed tail of the cluster queue
+				const int rest = ncl - c;
+				unsigned keep0 = 0, keep1 = 0;
+				if (lane < rest) keep0 = wm.clq[c + lane];
+				if (lane + 32 < rest) keep1 = wm.clq[c + lane + 32];
+				__syncwarp();
+				if (lane < rest) wm.clq[lane] = keep0;
+				if (lane + 32 < rest) wm.clq[lane + 32] = keep1;
+				ncl = rest;
+			} else {
+				ncl = 0;
+			}
+			__syncwarp();
+			// ---- flush: group by pose slot, phase C2, append to the global candidate list --------------------
+			if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
+				if (ncand > 0) {
+					// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
+					int mine = 0;
+					for (int i = 0; i < ncand; ++i) mine += (wm.cand_ids[i] >> 26) == (unsigned)lane;
+					int pre = mine;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						const int v = __shfl_up_sync(FULL, pre, o);
+						if (lane >= o) pre += v;
+					}
+					pfx[lane] = (unsigned)(pre - mine);
+					unsigned gbase = 0;
+					if (lane == 0) gbase = atomicAdd(p.cand_total, (unsigned)ncand);
+					gbase = __shfl_sync(FULL, gbase, 0);
+					__syncwarp();
+					if ((unsigned long long)gbase + (unsigned)ncand > (unsigned long long)p.cand_cap) {
+						if (lane == 0) atomicExch(p.overflow, 1u);  // the fused fall-back recomputes this launch
+					} else {
+						for (int i = lane; i < ncand; i += 32) {
+							const uint32_t id = wm.cand_ids[i];
+							const unsigned sl = id >> 26, e = id & 0x3ffffffu;
+							int rank = 0;  // candidates of the same pose slot that precede i
+							for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
+							const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
+							float4 rec[4];
+							make_candidate_record(p, chunk_poses + (size_t)sl * rec_len, p.objects[e], m2, 0u, rec);
+							float4 *out = p.cand_rec + 4ull * dst;
+							out[0] = rec[0];
+							out[1] = rec[1];
+							out[2] = rec[2];
+							out[3] = rec[3];
+							p.cand_obj[dst] = e;
+							p.cand_pose[dst] = (uint32_t)(pose0 + sl);
+						}
+					}
+					n_cand_total += (unsigned)ncand;
+				}
+				ncand = 0;
+				__syncwarp();
+			}
+		}
+	}
+	if (COUNT && lane == 0 && n_cand_total) atomicAdd(p.counters + CTR_CAND, n_cand_total);
+}
+
+
+template <bool COUNT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	unsigned char *base = smem_raw + (size_t)warp * np_warp_smem_bytes();
+	WarpMem wm{};
+	wm.leafq = reinterpret_cast<uint2 *>(base);
+	base += kLeafQueueCap * 8;
+	wm.cand = reinterpret_cast<float4 *>(base);
+	base += kCandCap * 64;
+	wm.rel = reinterpret_cast<double *>(base);
+	base += 16 * 8;
+	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
+	base += kCandCap * 4;
+	wm.cand_pose = reinterpret_cast<uint32_t *>(base);
+	base += kCandCap * 4;
+	wm.dead = base;
+	base += kCandCap;
+	wm.donor = base;
+
+	// An overflowed list has holes (a flush that did not fit wrote nothing): leave the whole launch to the
+	// fused fall-back kernel.
+	if (*p.overflow != 0u) return;
+	const unsigned total = *p.cand_total;
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+	SplitTrav tv;
+	tv.poses = p.poses;
+	tv.rec_len = p.pose_format == 1u ? 7u : 12u;
+	tv.verdict_bits = p.verdict_bits;
+	unsigned long long ctr[CTR_N];
+#pragma unroll
+	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
+
+	while (true) {
+		unsigned first = 0;
+		if (lane == 0) first = atomicAdd(p.work_counter2, (unsigned)kCandCap);
+		first = __shfl_sync(FULL, first, 0);
+		if (first >= total) break;
+		const int n = (int)(total - first < (unsigned)kCandCap ? total - first : (unsigned)kCandCap);
+		// ---- load the batch: records (coalesced float4 copy), objects, pose-set indices -------------------
+		const float4 *src_rec = p.cand_rec + 4ull * first;
+		for (int i = lane; i < 4 * n; i += 32) wm.cand[i] = src_rec[i];
+		for (int i = lane; i < n; i += 32) {
+			wm.cand_ids[i] = p.cand_obj[first + i];
+			wm.cand_pose[i] = p.cand_pose[first + i];
+		}
+		__syncwarp();
+		// ---- pose slots of the batch: candidates of one pose-set are adjacent; the slot of a run is the
+		//      index of its first candidate.  dead[slot] starts from the verdict bit (another batch may have
+		//      settled the pose-set already). -----------------------------------------------------------------
+		unsigned carry = 0;
+		for (int g = 0; g < (n + 31) / 32; ++g) {
+			const int i = 32 * g + lane;
+			const bool valid = i < n;
+			const uint32_t pose = valid ? wm.cand_pose[i] : 0u;
+			const bool start = valid && (i == 0 || wm.cand_pose[i - 1] != pose);
+			const unsigned sm = __ballot_sync(FULL, start);
+			const unsigned upto = sm & (0xffffffffu >> (31 - lane));
+			const unsigned slot = upto ? (unsigned)(32 * g + 31 - __clz((int)upto)) : carry;
+			if (valid) reinterpret_cast<float *>(wm.cand + 4 * i + 3)[1] = __uint_as_float(slot);
+			if (start) wm.dead[i] = (unsigned char)((p.verdict_bits[pose >> 5] >> (pose & 31u)) & 1u);
+			if (sm) carry = (unsigned)(32 * g + 31 - __clz((int)sm));
+		}
+		__syncwarp();
+		traverse_all<COUNT>(p, wm, m2, n, tv, lane, ctr);
+		__syncwarp();
+	}
+	if (COUNT && lane == 0) {
+#pragma unroll
+		for (int i = 0; i < CTR_N; ++i)
+			if (ctr[i]) atomicAdd(p.counters + i, ctr[i]);
+	}
+}
+
+template <class K>
+int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads, size_t smem, void *stream) {
+	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+	if (e != cudaSuccess) return (int)e;
+	int per_sm = 0;
+	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+	if (e != cudaSuccess) return (int)e;
+	if (per_sm < 1) per_sm = 1;
+	kernel<<<sm_count * per_sm, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
+	return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *stream) {
+	const size_t smem = (size_t)kBpWarpsPerCta * bp_warp_smem_bytes();
+	return count ? launch_persistent(broadphase_kernel<true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
+	             : launch_persistent(broadphase_kernel<false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
+}
+
+int launch_narrowphase(const KernelParams &p, int sm_count, bool count, void *stream) {
+	const size_t smem = (size_t)kWarpsPerCta * np_warp_smem_bytes();
+	return count ? launch_persistent(narrowphase_kernel<true>, p, sm_count, kWarpsPerCta * 32, smem, stream)
+	             : launch_persistent(narrowphase_kernel<false>, p, sm_count, kWarpsPerCta * 32, smem, stream);
+}
+
+}  // namespace mptcc

@@ -231,3 +231,30 @@ def test_sub_batch_pipeline(box_scene):
     b = box_scene.checker(sub_batch=1024).check_poses(poses)
     assert np.array_equal(a, b)
     assert_bits_equal(b, box_scene.oracle_bits(poses), len(poses), "sub-batches")
+
+
+@pytest.mark.parametrize("opts", [dict(split=0), dict(split=1, split_min=32), dict(split=1, split_min=32, split_cap=1),
+                                  dict(split=1, split_min=32, always_replay=1)])
+def test_split_pipeline_matches_fused_and_oracle(built, opts):
+    """Two-kernel pipeline (broadphase -> candidate list -> narrowphase) incl. the overflow fall-back
+    (split_cap=1 makes the candidate list too small for this scene)."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(123)
+    poses = scenes.random_poses_near_objects(rng, 30011, env, 2.0)
+    chk = sc.checker(**opts)
+    chk.enable_counters(True)
+    got = chk.check_poses(poses)
+    assert_bits_equal(got, sc.oracle_bits(poses), len(poses), "split %s" % (opts,))
+    c = chk.counters()
+    assert c["n_candidates"] > len(poses) * (1 if opts.get("split_cap") == 1 else 0)
+
+
+def test_split_pipeline_unit_box_and_quaternions(box_scene):
+    rng = scenes.SplitMix64(124)
+    poses = scenes.random_poses_tq7(rng, 50000, (-1.6,) * 3, (1.6,) * 3)
+    chk = box_scene.checker(split=1, split_min=32)
+    assert_bits_equal(chk.check_poses(poses, capi.POSE_TQ7), box_scene.oracle_bits(poses, O.POSE_TQ7), len(poses), "split TQ7")
+    poses = scenes.translation_poses(np.stack([rng.uniform(40000, -1.6, 1.6) for _ in range(3)], 1))
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "split translations")
