@@ -129,7 +129,10 @@ int mptcc_reset_counters(mptcc_ctx *ctx);
 /* Milliseconds of the kernels of the last host-buffer check call on device slot `slot`
  * (CUDA events on the launching stream). */
 int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
-/* Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1), "split_min", "split_cap", "always_replay". */
+/* With option "time_phases" = 1: device milliseconds of the three kernels of the last split-pipeline launch
+ * on `slot` (CUDA events on the launching stream): ms3 = {broadphase, narrowphase, overflow fall-back}. */
+int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3);
+/* Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1), "split_min", "split_cap", "always_replay", "time_phases". */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */

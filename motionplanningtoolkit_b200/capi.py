@@ -22,7 +22,7 @@ EXPORTS = [
     "mptcc_create", "mptcc_destroy", "mptcc_last_error", "mptcc_num_devices", "mptcc_set_environment",
     "mptcc_set_agent", "mptcc_check_poses", "mptcc_check_segments", "mptcc_check_omni_edges", "mptcc_check_poses_device",
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
-    "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_set_option",
+    "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
     "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb",
 ]
@@ -92,6 +92,8 @@ def load():
     L.mptcc_reset_counters.argtypes = [vp]
     L.mptcc_last_kernel_ms.restype = C.c_int
     L.mptcc_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.mptcc_last_phase_ms.restype = C.c_int
+    L.mptcc_last_phase_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.mptcc_set_option.restype = C.c_int
     L.mptcc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.mptcc_bvh_build.restype = C.c_int
@@ -257,6 +259,12 @@ class Checker:
         ms = C.c_float()
         self._check(self.lib.mptcc_last_kernel_ms(self.h, slot, C.byref(ms)))
         return ms.value
+
+    def last_phase_ms(self, slot=0):
+        """(broadphase, narrowphase, fall-back) ms of the last split-pipeline launch (option time_phases)."""
+        ms = (C.c_float * 3)()
+        self._check(self.lib.mptcc_last_phase_ms(self.h, slot, ms))
+        return tuple(ms)
 
     def set_option(self, name, value):
         self._check(self.lib.mptcc_set_option(self.h, name.encode(), int(value)))

@@ -343,6 +343,7 @@ struct Device {
 	DevBuf<unsigned long long> counters;
 	DevBuf<uint32_t> work_user;  // work counter of the device-buffer entry point
 	SplitBufs split[kPipe + 2];  // staging sets, device-buffer entry point, edge entry point
+	cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // option time_phases: around the pipeline kernels
 	// on-device edge interpolation (mptcc_check_omni_edges)
 	DevBuf<double> edge_in;
 	DevBuf<unsigned long long> edge_off;
@@ -369,6 +370,7 @@ struct mptcc_ctx {
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
 	long opt_sub_batch = 1 << 18;
 	long opt_always_replay = 0;
+	long opt_time_phases = 0;        // record CUDA events around the kernels of the split pipeline
 	long opt_split = 1;              // two-kernel pipeline for large single-link batches
 	long opt_split_min = 1 << 15;    // ... from this many pose-sets per launch
 	long opt_split_cap = 3;          // candidate list capacity, per pose-set
@@ -513,16 +515,24 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		CU(cudaMemsetAsync(sb->ctl.p, 0, 4 * sizeof(unsigned int), s));
 		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 		CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
+		const bool timed = ctx->opt_time_phases != 0;
+		if (timed)
+			for (auto &ev : d.phase_ev)
+				if (!ev) CU(cudaEventCreate(&ev));
+		if (timed) CU(cudaEventRecord(d.phase_ev[0], s));
 		int e = launch_broadphase(kp, d.sm_count, ctx->count, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "broadphase_kernel launch");
+		if (timed) CU(cudaEventRecord(d.phase_ev[1], s));
 		e = launch_narrowphase(kp, d.sm_count, ctx->count, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase_kernel launch");
+		if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
 		// overflow fall-back: the fused kernel returns at once unless the candidate list overflowed
 		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 		kp.run_if = kp.overflow;
 		kp.ppw_log2 = 4;  // atomicOr into the words the split kernels already wrote
 		e = launch_collide(kp, grid, ctx->count, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel (fall-back) launch");
+		if (timed) CU(cudaEventRecord(d.phase_ev[3], s));
 		ctx->ctr.n_kernel_launches += 3;
 		ctx->ctr.n_pose_sets += n;
 		return MPTCC_OK;
@@ -593,6 +603,8 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.counters.release();
 		d.work_user.release();
 		for (auto &sb : d.split) sb.release();
+		for (auto &ev : d.phase_ev)
+			if (ev) cudaEventDestroy(ev);
 		d.edge_in.release();
 		d.edge_off.release();
 		d.edge_poses.release();
@@ -931,6 +943,16 @@ int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms) {
 	return MPTCC_OK;
 }
 
+int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3) {
+	if (!ctx || !ms3 || slot < 0 || slot >= (int)ctx->devs.size()) return MPTCC_ERR_INVALID;
+	Device &d = ctx->devs[slot];
+	if (!d.phase_ev[0]) return fail(ctx, MPTCC_ERR_STATE, "no timed split-pipeline launch yet (option time_phases)");
+	CU(cudaSetDevice(d.id));
+	CU(cudaEventSynchronize(d.phase_ev[3]));
+	for (int k = 0; k < 3; ++k) CU(cudaEventElapsedTime(ms3 + k, d.phase_ev[k], d.phase_ev[k + 1]));
+	return MPTCC_OK;
+}
+
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	if (!ctx || !name) return MPTCC_ERR_INVALID;
 	const std::string k(name);
@@ -944,6 +966,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 		ctx->opt_steal_bottom = value != 0;
 	} else if (k == "no_steal") {
 		ctx->opt_no_steal = value != 0;
+	} else if (k == "time_phases") {
+		ctx->opt_time_phases = value != 0;
 	} else if (k == "split") {
 		ctx->opt_split = value != 0;
 	} else if (k == "split_min") {

@@ -2,7 +2,9 @@
 """Join ncu's per-SASS-instruction stall samples with nvdisasm line info -> hottest source lines.
 
 usage: ncu_hot_lines.py <report.ncu-rep> [kernel-substring] [top-N]
-The cubin is extracted from motionplanningtoolkit_b200/libmptcc.so (must be the build that was profiled).
+The cubin is extracted from motionplanningtoolkit_b200/libmptcc.so (must be the build that was profiled);
+NCU_CUBIN=split_kernels|collide_kernel picks the translation unit, NCU_SRC the file whose lines are shown
+(lines of other files of the unit are attributed to the same numbers, so read them with care).
 """
 import collections
 import csv
@@ -20,7 +22,7 @@ topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(os.path.join(ROOT, "motionplanningtoolkit_b200", "libmptcc.so"))],
                       cwd=tmp, stdout=subprocess.DEVNULL)
-cub = [f for f in os.listdir(tmp) if f.startswith("collide_kernel")][0]
+cub = [f for f in os.listdir(tmp) if f.startswith(os.environ.get("NCU_CUBIN", "collide_kernel"))][0]
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
 # offset -> (function, line)
 line_of = {}
@@ -38,7 +40,7 @@ for l in dis.splitlines():
     if m and cur_fn:
         line_of[(cur_fn, int(m.group(1), 16))] = cur_line
 
-src = open(os.path.join(ROOT, "motionplanningtoolkit_b200", "csrc", "collide_kernel.cu")).read().splitlines()
+src = open(os.path.join(ROOT, "motionplanningtoolkit_b200", "csrc", os.environ.get("NCU_SRC","collide_device.cuh"))).read().splitlines()
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 # the report may hold several kernels; each starts with a "Kernel Name" row followed by a header row
