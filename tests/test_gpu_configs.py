@@ -120,3 +120,20 @@ def test_on_device_edge_interpolation(built):
     hit = O.unpack_bits(sc.oracle_bits(poses), len(poses))
     want = np.array([not hit[segs[i]:segs[i + 1]].any() for i in range(n)])
     assert np.array_equal(got, want) and 0 < want.sum() < n
+
+
+@pytest.mark.parametrize("opts", [dict(split=0), dict(split=1, split_min=32)])
+def test_c5_single_object_terrain(built, opts):
+    """BASELINE C5, single-object variant: one ~1.0 M-triangle heightfield (depth-23 OBB tree) vs the merged
+    blimp; poses hover around the surface so that grazing cases are frequent."""
+    env = [scenes.terrain(708, 708)]
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(scenes.SEED_C5)
+    n = 20000
+    poses = scenes.random_poses_rt12(rng, n, (-95, -95, -10), (95, 95, 12))
+    chk = sc.checker(**opts)
+    want = sc.oracle_bits(poses)
+    assert_bits_equal(chk.check_poses(poses), want, n, "terrain %s" % (opts,))
+    f = O.unpack_bits(want, n).mean()
+    assert 0.1 < f < 0.9, f
