@@ -516,6 +516,12 @@ struct WarpMem {
 	unsigned char *dead;   // [kCandCap] per pose slot of the batch: already in collision
 };
 
+// Candidate records live in shared memory as 4 float4 (64 B).  Lanes fetch the SAME part k of DIFFERENT
+// records at once; with a plain layout all even (odd) candidates would hit the same 4 banks.  Part k of
+// candidate c is therefore stored at position (k + (c >> 1)) & 3 of its record: 8 consecutive candidates
+// cover all 32 banks and an LDS.128 of 8 lanes is one conflict-free wavefront.
+__device__ __forceinline__ unsigned rec_at(unsigned cand, unsigned k) { return 4u * cand + ((k + (cand >> 1)) & 3u); }
+
 // Hit bookkeeping of the fused kernel: one bit per pose slot of the warp's chunk, in registers.
 struct FusedTrav {
 	u64 hitmask, validmask;
@@ -729,8 +735,9 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 			uint2 pr = make_uint2(0u, 0u);
 			if (lane < k) {
 				pr = wm.leafq[lq + lane];
-				const float4 *rec = wm.cand + 4u * (pr.y >> 24);
-				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2], r3 = rec[3];
+				const unsigned lc = pr.y >> 24;
+				const float4 r0 = wm.cand[rec_at(lc, 0)], r1 = wm.cand[rec_at(lc, 1)], r2 = wm.cand[rec_at(lc, 2)],
+				             r3 = wm.cand[rec_at(lc, 3)];
 				if (!tv.dead(__float_as_uint(r3.y), wm)) {
 					RelF x;
 					x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
@@ -751,7 +758,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 				mm &= mm - 1;
 				const uint32_t t1 = __shfl_sync(FULL, pr.x, from), w2 = __shfl_sync(FULL, pr.y, from);
 				const uint32_t t2 = w2 & 0xffffffu, cand = w2 >> 24;
-				const unsigned src = __float_as_uint(wm.cand[4u * cand + 3].y);  // pose slot of this candidate
+				const unsigned src = __float_as_uint(wm.cand[rec_at(cand, 3)].y);  // pose slot of this candidate
 				const unsigned e = tv.object(cand, wm);
 				if (tv.dead(src, wm)) continue;
 				if (COUNT) ctr[CTR_EXACT] += 1;
@@ -804,12 +811,12 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 			const uint2 pr = cur;
 			has = false;
 			const unsigned tag = pr.y & 0xff000000u;
-			const float4 *rec = wm.cand + 4u * (pr.y >> 24);
-			const float4 r3 = rec[3];
+			const unsigned nc = pr.y >> 24;
+			const float4 r3 = wm.cand[rec_at(nc, 3)];
 			if (tv.dead(__float_as_uint(r3.y), wm)) {
 				top = bot;  // this lane's stack holds one candidate only, and its pose-set already collides
 			} else {
-				const float4 r0 = rec[0], r1 = rec[1], r2 = rec[2];
+				const float4 r0 = wm.cand[rec_at(nc, 0)], r1 = wm.cand[rec_at(nc, 1)], r2 = wm.cand[rec_at(nc, 2)];
 				RelF x;
 				x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
 				x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;

@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 						if (i < ncand) {
 							const uint32_t id = wm.cand_ids[i];
 							const unsigned src = id >> 26, e = id & 0x3ffffffu;
-							make_candidate_record(p, link_poses + (size_t)src * rec_len * p.n_links, p.objects[e], m2, src,
-							                      wm.cand + 4u * i);
+							float4 rec[4];
+							make_candidate_record(p, link_poses + (size_t)src * rec_len * p.n_links, p.objects[e], m2, src, rec);
+#pragma unroll
+							for (unsigned k = 0; k < 4; ++k) wm.cand[rec_at((unsigned)i, k)] = rec[k];
 						}
 					}
 					nrec = ncand;

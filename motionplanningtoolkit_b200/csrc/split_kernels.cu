@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const
 		const int n = (int)(total - first < (unsigned)kCandCap ? total - first : (unsigned)kCandCap);
 		// ---- load the batch: records (coalesced float4 copy), objects, pose-set indices -------------------
 		const float4 *src_rec = p.cand_rec + 4ull * first;
-		for (int i = lane; i < 4 * n; i += 32) wm.cand[i] = src_rec[i];
+		for (int i = lane; i < 4 * n; i += 32) wm.cand[rec_at((unsigned)i >> 2, (unsigned)i & 3u)] = src_rec[i];
 		for (int i = lane; i < n; i += 32) {
 			wm.cand_ids[i] = p.cand_obj[first + i];
 			wm.cand_pose[i] = p.cand_pose[first + i];
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const
 			const unsigned sm = __ballot_sync(FULL, start);
 			const unsigned upto = sm & (0xffffffffu >> (31 - lane));
 			const unsigned slot = upto ? (unsigned)(32 * g + 31 - __clz((int)upto)) : carry;
-			if (valid) reinterpret_cast<float *>(wm.cand + 4 * i + 3)[1] = __uint_as_float(slot);
+			if (valid) wm.cand[rec_at((unsigned)i, 3u)].y = __uint_as_float(slot);
 			if (start) wm.dead[i] = (unsigned char)((p.verdict_bits[pose >> 5] >> (pose & 31u)) & 1u);
 			if (sm) carry = (unsigned)(32 * g + 31 - __clz((int)sm));
 		}
