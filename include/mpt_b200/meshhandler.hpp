@@ -7,8 +7,8 @@
 // plus the batched form the call sites switch to:
 //   MeshHandler::collidingPoseSets(env, agent, poses) -> one bool per pose-set (one isInCollision each).
 //
-// Mesh files: Assimp is replaced by the flat .mptm format (tools/convert_meshes.py converts .dae/.3ds with
-// the sub-mesh semantics of AssimpMeshLoader::get, /root/reference/utilities/assimp_mesh_loader.hpp:20-60).
+// Mesh files: Assimp is replaced by mesh_loaders.hpp (.dae <triangles>, .3ds, and the flat .mptm format) with
+// the sub-mesh semantics of AssimpMeshLoader::get (/root/reference/utilities/assimp_mesh_loader.hpp:20-60).
 #pragma once
 
 #include <cstdint>
@@ -22,6 +22,7 @@
 
 #include "../mptcc.h"
 #include "fcl_types.hpp"
+#include "mesh_loaders.hpp"
 
 namespace fcl_helpers {
 // fcl_helpers::parseTransform (/root/reference/utilities/fcl_helpers.hpp:16-25): "x y z qw qx qy qz", read
@@ -35,44 +36,6 @@ inline fcl::Transform3f parseTransform(const std::string &transform) {
 }  // namespace fcl_helpers
 
 namespace mpt_b200 {
-
-struct SubMesh {
-	std::vector<double> xyz;     // [nv*3]
-	std::vector<uint32_t> tri;   // [nt*3]
-};
-
-// Stand-in for AssimpMeshLoader: one SubMesh per aiMesh, in order.
-class MptmMeshLoader {
-public:
-	explicit MptmMeshLoader(const std::string &file) : error(false) {
-		std::ifstream f(file.c_str(), std::ios::binary);
-		char magic[4];
-		uint32_t ver = 0, nsub = 0;
-		if (!f.is_open() || !f.read(magic, 4) || std::memcmp(magic, "MPTM", 4) != 0 ||
-		    !f.read(reinterpret_cast<char *>(&ver), 4) || ver != 1 || !f.read(reinterpret_cast<char *>(&nsub), 4)) {
-			fprintf(stderr, "%s: not a readable .mptm mesh (convert .dae/.3ds with tools/convert_meshes.py)\n", file.c_str());
-			error = true;
-			return;
-		}
-		meshes.resize(nsub);
-		for (auto &m : meshes) {
-			uint32_t nv = 0, nt = 0;
-			f.read(reinterpret_cast<char *>(&nv), 4);
-			f.read(reinterpret_cast<char *>(&nt), 4);
-			m.xyz.resize(3 * (size_t)nv);
-			m.tri.resize(3 * (size_t)nt);
-			f.read(reinterpret_cast<char *>(m.xyz.data()), sizeof(double) * m.xyz.size());
-			f.read(reinterpret_cast<char *>(m.tri.data()), sizeof(uint32_t) * m.tri.size());
-			if (!f) {
-				fprintf(stderr, "%s: truncated mesh file\n", file.c_str());
-				error = true;
-				return;
-			}
-		}
-	}
-	std::vector<SubMesh> meshes;
-	bool error;
-};
 
 inline mptcc_mesh as_c_mesh(const SubMesh &m) {
 	mptcc_mesh c;
@@ -90,7 +53,7 @@ public:
 	// mergeSubMeshes = false reproduces the reference: agentModel is overwritten for every non-empty
 	// sub-mesh, so only the last one collides (meshhandler.hpp:124-134).
 	explicit SimpleAgentMeshHandler(const std::string &filename, bool mergeSubMeshes = false) {
-		mpt_b200::MptmMeshLoader loader(filename);
+		mpt_b200::MeshFileLoader loader(filename);
 		if (loader.error) exit(0);
 		for (const auto &m : loader.meshes) {
 			if (m.xyz.empty() || m.tri.empty()) continue;
@@ -113,7 +76,7 @@ class StaticEnvironmentMeshHandler {
 public:
 	StaticEnvironmentMeshHandler(const std::string &filename, const std::string &pose, int nDevices = 1)
 	    : ctx(nullptr), agentKey() {
-		mpt_b200::MptmMeshLoader loader(filename);
+		mpt_b200::MeshFileLoader loader(filename);
 		if (loader.error) exit(0);
 		const fcl::Transform3f tf = fcl_helpers::parseTransform(pose);
 		for (const auto &m : loader.meshes)

@@ -130,3 +130,23 @@ def test_two_rank_sharding_matches_unsplit_run(built, tmp_path, n):
     mp.spawn(_gloo_worker, args=(2, port, n, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(os.path.join(str(tmp_path), "ok_%d.npy" % r))[0]
+
+
+def test_cpp_mesh_loaders_match_the_python_converter(built, tmp_path):
+    """include/mpt_b200/mesh_loaders.hpp (.dae / .3ds readers with Assimp's flags-0 sub-mesh rules)
+    reproduces the committed .mptm fixtures byte for byte.  Needs the reference's mesh files (build container)."""
+    ref = "/root/reference/mesh_models"
+    if not os.path.isdir(ref):
+        pytest.skip("reference fixtures are not present on this box")
+    exe = str(tmp_path / "mesh_convert")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "mesh_convert.cpp"), "-o", exe])
+    for src, name in (("agent_models/unit_box.dae", "unit_box"), ("agent_models/blimp.3ds", "blimp"),
+                      ("environment_models/model.dae", "model"), ("environment_models/divider.dae", "divider")):
+        out = str(tmp_path / (name + ".mptm"))
+        subprocess.check_call([exe, os.path.join(ref, src), out], stdout=subprocess.DEVNULL)
+        assert open(out, "rb").read() == open(os.path.join(meshio.DATA_DIR, name + ".mptm"), "rb").read(), name
+    # the flat format round-trips
+    out = str(tmp_path / "rt.mptm")
+    subprocess.check_call([exe, os.path.join(meshio.DATA_DIR, "blimp.mptm"), out], stdout=subprocess.DEVNULL)
+    assert open(out, "rb").read() == open(os.path.join(meshio.DATA_DIR, "blimp.mptm"), "rb").read()
