@@ -39,3 +39,18 @@ def test_map3d_safe_edges(built, tmp_path):
         assert bool(v[6]) == want_safe and bool(v[7]) == want_safe
         n_unsafe += not want_safe
     assert 0 < n_unsafe < n
+
+
+def test_prm_roadmap_batched_equals_sequential(built, tmp_path):
+    """BASELINE config 2 as a call-site change: the PRM roadmap built with one device call per
+    slice of milestones equals the roadmap built with one Map3D::safeEdge per edge."""
+    exe = str(tmp_path / "prm_roadmap")
+    libdir = os.path.join(ROOT, "motionplanningtoolkit_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "prm_roadmap.cpp"), "-o", exe,
+                           "-L", libdir, "-lmptcc", "-Wl,-rpath," + libdir])
+    box = os.path.join(meshio.DATA_DIR, "unit_box.mptm")
+    r = subprocess.run([exe, box, box, "300", "100"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "identical roadmaps: yes" in r.stdout
+    print(r.stdout)
