@@ -126,8 +126,8 @@ void mptcc_free_pinned(void *p);
 int mptcc_enable_counters(mptcc_ctx *ctx, int enable);
 int mptcc_get_counters(mptcc_ctx *ctx, mptcc_counters *out);
 int mptcc_reset_counters(mptcc_ctx *ctx);
-/* Milliseconds of the kernels of the last host-buffer check call on device slot `slot`
- * (CUDA events on the launching stream). */
+/* Device milliseconds of the last host-buffer check call on device slot `slot`: from the first kernel to the end
+ * of the last kernel (CUDA events on the launching streams; copies that overlap the kernels are inside). */
 int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
 /* With option "time_phases" = 1: device milliseconds of the three kernels of the last split-pipeline launch
  * on `slot` (CUDA events on the launching stream): ms3 = {broadphase, narrowphase, overflow fall-back}. */

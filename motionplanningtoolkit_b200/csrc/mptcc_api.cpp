@@ -483,6 +483,17 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.steal_bottom = ctx->opt_steal_bottom ? 1u : 0u;
 }
 
+// Candidate list buffers of the split pipeline for launches of up to n pose-sets.
+int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
+	if (!ctx->opt_split || ctx->link_model_h.size() != 1 || n < (uint64_t)ctx->opt_split_min) return MPTCC_OK;
+	const uint64_t cap64 = std::min<uint64_t>(n * (uint64_t)ctx->opt_split_cap, 0xfffffff0ull);
+	CU(sb.rec.reserve(4 * cap64));
+	CU(sb.obj.reserve(cap64));
+	CU(sb.pose.reserve(cap64));
+	CU(sb.ctl.reserve(4));
+	return MPTCC_OK;
+}
+
 // Enqueue (memsets +) kernels for n pose-sets already on the device.  Large single-link batches take the
 // split pipeline (broadphase kernel -> candidate list -> narrowphase kernel, then the fused kernel as a
 // conditional overflow fall-back); everything else the fused kernel.
@@ -501,10 +512,10 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	                   n < (1ull << 32) && !ctx->objects_h.empty();
 	if (split) {
 		const uint64_t cap64 = std::min<uint64_t>(n * (uint64_t)ctx->opt_split_cap, 0xfffffff0ull);
-		CU(sb->rec.reserve(4 * cap64));
-		CU(sb->obj.reserve(cap64));
-		CU(sb->pose.reserve(cap64));
-		CU(sb->ctl.reserve(4));
+		{
+			const int rrc = reserve_split(ctx, *sb, n);
+			if (rrc != MPTCC_OK) return rrc;
+		}
 		kp.cand_rec = sb->rec.p;
 		kp.cand_obj = sb->obj.p;
 		kp.cand_pose = sb->pose.p;
@@ -734,7 +745,8 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 	size_t max_jobs = 0;
 	for (size_t di = 0; di < nd; ++di) {
 		const uint64_t b = std::min(n_words, di * words_per_dev), e = std::min(n_words, (di + 1) * words_per_dev);
-		// split evenly into ceil(len/sub_words) pieces
+		// split evenly into ceil(len/sub_words) pieces (ramping the first pieces up to shorten the one copy no
+		// kernel can hide was measured slower: more, smaller launches)
 		const uint64_t len = e - b;
 		if (len == 0) continue;
 		const uint64_t pieces = (len + sub_words - 1) / sub_words;
@@ -743,7 +755,25 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 		max_jobs = std::max(max_jobs, jobs[di].size());
 		ctx->devs[di].last_ms = 0.f;
 	}
-	std::vector<std::vector<std::pair<cudaEvent_t, cudaEvent_t>>> timed(nd);
+	// Size every staging set for the largest job up front: inside the loop nothing is reallocated, so a
+	// staging set can be reused by the next job of ITS stream without any host-side wait (stream order protects
+	// the buffers) and the host only blocks once, at the end.
+	for (size_t di = 0; di < nd; ++di) {
+		if (jobs[di].empty()) continue;
+		Device &d = ctx->devs[di];
+		uint64_t max_cnt = 0, max_words = 0;
+		for (const Job &jb : jobs[di]) {
+			max_cnt = std::max<uint64_t>(max_cnt, std::min<uint64_t>(n, jb.w1 * 32) - jb.w0 * 32);
+			max_words = std::max<uint64_t>(max_words, jb.w1 - jb.w0);
+		}
+		CU(cudaSetDevice(d.id));
+		for (size_t k = 0; k < std::min<size_t>(jobs[di].size(), kPipe); ++k) {
+			CU(d.poses[k].reserve(max_cnt * rec));
+			CU(d.bits[k].reserve(max_words));
+			rc = reserve_split(ctx, d.split[k], max_cnt);
+			if (rc != MPTCC_OK) return rc;
+		}
+	}
 	// round-robin over devices so that every GPU's queue fills concurrently
 	for (size_t ji = 0; ji < max_jobs; ++ji) {
 		for (size_t di = 0; di < nd; ++di) {
@@ -753,19 +783,11 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 			const int k = (int)(ji % kPipe);
 			const uint64_t p0 = jb.w0 * 32, p1 = std::min<uint64_t>(n, jb.w1 * 32), cnt = p1 - p0;
 			CU(cudaSetDevice(d.id));
-			if (ji >= (size_t)kPipe) {
-				// staging set k is reused: its previous kernel must be done before the buffers are touched
-				CU(cudaStreamSynchronize(d.stream[k]));
-				float ms = 0.f;
-				if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms += ms;
-			}
-			CU(d.poses[k].reserve(cnt * rec));
-			CU(d.bits[k].reserve(jb.w1 - jb.w0));
 			CU(cudaMemcpyAsync(d.poses[k].p, poses + p0 * rec, sizeof(double) * cnt * rec, cudaMemcpyHostToDevice, d.stream[k]));
-			CU(cudaEventRecord(d.ev0[k], d.stream[k]));
+			if (ji < (size_t)kPipe) CU(cudaEventRecord(d.ev0[k], d.stream[k]));  // first kernel of this stream
 			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k], &d.split[k]);
 			if (rc != MPTCC_OK) return rc;
-			CU(cudaEventRecord(d.ev1[k], d.stream[k]));
+			CU(cudaEventRecord(d.ev1[k], d.stream[k]));  // re-recorded by every job: the last one counts
 			CU(cudaMemcpyAsync(verdict_bits + jb.w0, d.bits[k].p, sizeof(uint32_t) * (jb.w1 - jb.w0), cudaMemcpyDeviceToHost,
 			                   d.stream[k]));
 		}
@@ -777,8 +799,8 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 		const size_t used = std::min<size_t>(jobs[di].size(), kPipe);
 		for (size_t k = 0; k < used; ++k) {
 			CU(cudaStreamSynchronize(d.stream[k]));
-			float ms = 0.f;
-			if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms += ms;
+			float ms = 0.f;  // device time from the first kernel to the end of the last kernel of this stream
+			if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
 		}
 	}
 	return MPTCC_OK;
