@@ -373,7 +373,7 @@ struct RelF {
 // n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
 __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,
                                                  const float4 b0, const float4 b1, const float4 b2, const float4 b3,
-                                                 const RelF &x) {
+                                                 const RelF &x, float &center_d2) {
 	// M = R * [b axes as columns]
 	float M[9];
 #pragma unroll
@@ -396,6 +396,7 @@ __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a
 	const float tx = x.R[0] * c2x + x.R[1] * c2y + x.R[2] * c2z + (x.T[0] - c1x);
 	const float ty = x.R[3] * c2x + x.R[4] * c2y + x.R[5] * c2z + (x.T[1] - c1y);
 	const float tz = x.R[6] * c2x + x.R[7] * c2y + x.R[8] * c2z + (x.T[2] - c1z);
+	center_d2 = tx * tx + ty * ty + tz * tz;  // squared distance of the box centres (descent order heuristic)
 	const float T0 = tx * a0.x + ty * a0.y + tz * a0.z;
 	const float T1 = tx * a1.x + ty * a1.y + tz * a1.z;
 	const float T2 = tx * a2.x + ty * a2.y + tz * a2.z;
@@ -828,6 +829,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 				const uint32_t i2base = pr.y & kPlanIdxMask;
 				uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
 				bool ok0 = false, ok1 = false;
+				float d2_0 = 0.f, d2_1 = 0.f;
 				// the node that stays (fetched once) and the sibling line of the tree that is descended
 				const float4 *op = env_side ? nodes2 + 4ull * i2base : nodes1 + 4ull * pr.x;
 				const float4 *cp = env_side ? nodes1 + 4ull * pr.x : nodes2 + 4ull * i2base;
@@ -844,7 +846,9 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 					const float4 b0 = env_side ? o0 : c0, b1 = env_side ? o1 : c1, bb2 = env_side ? o2 : c2,
 					             b3 = env_side ? o3 : c3;
 					++n_tests;
-					if (obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x)) continue;
+					float d2;
+					if (obb_disjoint_f32(a0, a1, a2, a3, b0, b1, bb2, b3, x, d2)) continue;
+					if (k == 0) d2_0 = d2; else d2_1 = d2;
 					const int link1 = __float_as_int(a3.w), link2 = __float_as_int(b3.w);
 					const bool l1 = link1 < 0, l2 = link2 < 0;
 					if (l1 && l2) {
@@ -860,10 +864,17 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 					                       : make_uint2(i1, (uint32_t)link2 | tag);
 					if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
 				}
-				if (ok0) {
+				if (ok0 && ok1) {
+					// Both children overlap.  FCL would take child 0 first; the verdict does not depend on the
+					// order, and descending first into the child whose box centre is closer to the other box
+					// reaches a contact (if there is one) after fewer tests.
+					const bool swap = p.near_first && d2_1 < d2_0;
+					cur = swap ? plan1 : plan0;
+					has = true;
+					stk[top++ & M] = swap ? plan0 : plan1;
+				} else if (ok0) {
 					cur = plan0;
 					has = true;
-					if (ok1) stk[top++ & M] = plan1;
 				} else if (ok1) {
 					cur = plan1;
 					has = true;

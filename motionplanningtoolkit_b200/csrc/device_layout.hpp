@@ -100,6 +100,7 @@ struct KernelParams {
 	const unsigned int *run_if;     // fused kernel: return at once unless *run_if != 0 (nullptr: always run)
 	uint32_t *work_counter2;        // batch counter of the narrowphase kernel
 	unsigned long long *counters;  // [CTR_N] or nullptr
+	uint32_t near_first;           // 1: of two overlapping children, descend the closer one first
 	uint32_t steal_bottom;         // 1: thieves take the bottom (largest, most speculative) pending pair
 	uint32_t no_steal;             // 1: lanes never steal pending subtrees (experiment knob)
 	uint32_t always_replay;        // 1: replay FCL's path for every positive pair (ignore the certificate)

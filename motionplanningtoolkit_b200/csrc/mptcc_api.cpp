@@ -376,6 +376,7 @@ struct mptcc_ctx {
 	long opt_split_cap = 3;          // candidate list capacity, per pose-set
 	long opt_no_steal = 0;
 	long opt_steal_bottom = 0;
+	long opt_near_first = 1;
 	mptcc_counters ctr{};
 	int ctas_per_sm_cached = -1;
 	bool ctas_cached_count = false;
@@ -481,6 +482,7 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.work_counter2 = nullptr;
 	kp.no_steal = ctx->opt_no_steal ? 1u : 0u;
 	kp.steal_bottom = ctx->opt_steal_bottom ? 1u : 0u;
+	kp.near_first = ctx->opt_near_first ? 1u : 0u;
 }
 
 // Candidate list buffers of the split pipeline for launches of up to n pose-sets.
@@ -984,6 +986,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
+	} else if (k == "near_first") {
+		ctx->opt_near_first = value != 0;
 	} else if (k == "steal_bottom") {
 		ctx->opt_steal_bottom = value != 0;
 	} else if (k == "no_steal") {
