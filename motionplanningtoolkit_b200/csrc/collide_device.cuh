@@ -517,6 +517,18 @@ struct WarpMem {
 	unsigned char *dead;   // [kCandCap] per pose slot of the batch: already in collision
 };
 
+// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1)  [FCL-recalled C.7]; element `idx`
+// (0..8 -> R row-major, 9..11 -> T).
+__device__ __forceinline__ double rel_element(const DevObject &ob, const double *R2, const double *T2, int idx) {
+	if (idx < 9) {
+		const int r = idx / 3, cc = idx % 3;
+		return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
+	}
+	const int r = idx - 9;
+	const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
+	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
+}
+
 // Candidate records live in shared memory as 4 float4 (64 B).  Lanes fetch the SAME part k of DIFFERENT
 // records at once; with a plain layout all even (odd) candidates would hit the same 4 banks.  Part k of
 // candidate c is therefore stored at position (k + (c >> 1)) & 3 of its record: 8 consecutive candidates
@@ -537,6 +549,19 @@ struct FusedTrav {
 		return link_poses + (size_t)slot * stride;
 	}
 	__device__ __forceinline__ unsigned object(unsigned cand, const WarpMem &wm) const { return wm.cand_ids[cand] & 0x3ffffffu; }
+	// relativeTransform(object, pose) in fp64 -> wm.rel; lanes 0..11 compute one element each
+	__device__ __forceinline__ const double *exact_rel(const KernelParams &p, const WarpMem &wm, const DevObject &ob,
+	                                                   unsigned slot, unsigned cand, int lane) const {
+		__syncwarp();
+		if (lane < 12) {
+			double R2[9], T2[3];
+			Quat q;
+			decode_pose(pose_record(slot, cand, wm), p.pose_format, R2, T2, q, false);
+			wm.rel[lane] = rel_element(ob, R2, T2, lane);
+		}
+		__syncwarp();
+		return wm.rel;
+	}
 };
 
 // Hit bookkeeping of the narrowphase kernel (single-link agents): flags in shared memory per pose slot of
@@ -545,6 +570,7 @@ struct SplitTrav {
 	const double *poses;
 	unsigned rec_len;
 	uint32_t *verdict_bits;
+	unsigned batch_first;  // list index of candidate 0 of the current batch
 	__device__ __forceinline__ bool dead(unsigned slot, const WarpMem &wm) const { return wm.dead[slot] != 0; }
 	__device__ __forceinline__ bool all_done() const { return false; }
 	__device__ __forceinline__ void mark_hit(unsigned slot, unsigned cand, const WarpMem &wm, const KernelParams &, int lane) {
@@ -560,19 +586,12 @@ struct SplitTrav {
 		return poses + (size_t)wm.cand_pose[cand] * rec_len;
 	}
 	__device__ __forceinline__ unsigned object(unsigned cand, const WarpMem &wm) const { return wm.cand_ids[cand]; }
-};
-
-// relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1)  [FCL-recalled C.7]; element `idx`
-// (0..8 -> R row-major, 9..11 -> T).
-__device__ __forceinline__ double rel_element(const DevObject &ob, const double *R2, const double *T2, int idx) {
-	if (idx < 9) {
-		const int r = idx / 3, cc = idx % 3;
-		return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], R2[cc], R2[3 + cc], R2[6 + cc]);
+	// the broadphase kernel stored the fp64 relative transform next to the fp32 record
+	__device__ __forceinline__ const double *exact_rel(const KernelParams &p, const WarpMem &, const DevObject &, unsigned,
+	                                                   unsigned cand, int) const {
+		return p.cand_rel + 12ull * (batch_first + cand);
 	}
-	const int r = idx - 9;
-	const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
-	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
-}
+};
 
 // Phase A for one lane: pose record -> world AABB of the link exactly as fcl::CollisionObject::computeAABB
 // [FCL-recalled C.5] (identity quaternion: translated tight box; else the sphere box around
@@ -613,13 +632,18 @@ __device__ __forceinline__ void pose_world_box(const double *rec, uint32_t fmt, 
 // Phase C2 for one candidate: fp64 relativeTransform of (object, pose) -> fp32 record in the recentred
 // frames: R (9), T (3), S, pose slot, node_base and tri_base of the object's model.
 __device__ __forceinline__ void make_candidate_record(const KernelParams &p, const double *pose_rec, const DevObject &ob,
-                                                      const DevModel &m2, unsigned slot, float4 *rec) {
+                                                      const DevModel &m2, unsigned slot, float4 *rec,
+                                                      double *rel64 = nullptr) {
 	const DevModel &m1 = p.env.models[ob.model];
 	double R2[9], T2[3], rl[12];
 	Quat q;
 	decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
 #pragma unroll
 	for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
+	if (rel64 != nullptr) {
+#pragma unroll
+		for (int k = 0; k < 12; ++k) rel64[k] = rl[k];  // FCL's R (9), T (3) verbatim, for the exact pass
+	}
 	// recentred frames: x1 - C1 = R (x2 - C2) + (R C2 + T - C1)
 	float tf[3], tinf = 0.f;
 #pragma unroll
@@ -763,18 +787,12 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 				const unsigned e = tv.object(cand, wm);
 				if (tv.dead(src, wm)) continue;
 				if (COUNT) ctr[CTR_EXACT] += 1;
-				// fp64 relative transform of this candidate, FCL's operation order
+				// fp64 relative transform of this candidate, FCL's operation order: recomputed from the pose
+				// record into shared memory (fused kernel) or read from the candidate list (split pipeline)
 				const DevObject &ob = p.objects[e];
-				__syncwarp();
-				if (lane < 12) {
-					double R2[9], T2[3];
-					Quat q;
-					decode_pose(tv.pose_record(src, cand, wm), p.pose_format, R2, T2, q, false);
-					wm.rel[lane] = rel_element(ob, R2, T2, lane);
-				}
-				__syncwarp();
+				const double *rel = tv.exact_rel(p, wm, ob, src, cand, lane);
 				const DevModel &m1 = p.env.models[ob.model];
-				const bool hit = exact_tri_intersect_warp(wm.rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
+				const bool hit = exact_tri_intersect_warp(rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
 				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 				if (hit) {
 					// Path certificate.  FCL reports this contact only if every OBB pair on its descent to
@@ -785,7 +803,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 					// no test on the path can report "disjoint" and the replay is provably redundant
 					// (DESIGN.md "Path certificate").  mu = min over the two root-to-leaf chains, precomputed per
 					// triangle; it is 0 for degenerate boxes, which forces the replay.
-					const double mag = fabs(wm.rel[9]) + fabs(wm.rel[10]) + fabs(wm.rel[11]) + m1.cmax1 + m2.cmax1 +
+					const double mag = fabs(rel[9]) + fabs(rel[10]) + fabs(rel[11]) + m1.cmax1 + m2.cmax1 +
 					                   m1.esum + m2.esum;
 					const double mu = fmin((double)p.env.mu_chain[m1.tri_base + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
 					const bool certified = !p.always_replay && mu >= 1e-5 * mag;
@@ -793,7 +811,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 						tv.mark_hit(src, cand, wm, p, lane);
 					} else {
 						if (COUNT) ctr[CTR_PATH] += 1;
-						if (exact_path_reaches(p, m1, m2, wm.rel, t1, t2, lane)) tv.mark_hit(src, cand, wm, p, lane);
+						if (exact_path_reaches(p, m1, m2, rel, t1, t2, lane)) tv.mark_hit(src, cand, wm, p, lane);
 					}
 				}
 			}

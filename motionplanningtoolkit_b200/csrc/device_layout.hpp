@@ -92,6 +92,7 @@ struct KernelParams {
 	uint32_t *work_counter;
 	// split pipeline (split_kernels.cu): candidate list written by the broadphase kernel
 	float4 *cand_rec;               // [cand_cap][4] fp32 candidate records
+	double *cand_rel;               // [cand_cap][12] fp64 relativeTransform (R, T) of the candidate (exact pass)
 	uint32_t *cand_obj;             // [cand_cap] environment object of the candidate
 	uint32_t *cand_pose;            // [cand_cap] pose-set index of the candidate
 	unsigned int *cand_total;       // [1] candidates appended (can exceed cand_cap: then *overflow = 1)

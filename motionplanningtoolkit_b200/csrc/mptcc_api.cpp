@@ -317,10 +317,12 @@ constexpr int kPipe = 2;  // ping-pong staging sets per device
 // Buffers of the split pipeline (split_kernels.cu) for one launch slot; grow-only.
 struct SplitBufs {
 	DevBuf<float4> rec;
+	DevBuf<double> rel;
 	DevBuf<uint32_t> obj, pose;
 	DevBuf<unsigned int> ctl;  // [0] cand_total, [1] overflow, [2] narrowphase batch counter
 	void release() {
 		rec.release();
+		rel.release();
 		obj.release();
 		pose.release();
 		ctl.release();
@@ -473,6 +475,7 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.counters = ctx->count ? d.counters.p : nullptr;
 	kp.always_replay = ctx->opt_always_replay ? 1u : 0u;
 	kp.cand_rec = nullptr;
+	kp.cand_rel = nullptr;
 	kp.cand_obj = nullptr;
 	kp.cand_pose = nullptr;
 	kp.cand_total = nullptr;
@@ -490,6 +493,7 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 	if (!ctx->opt_split || ctx->link_model_h.size() != 1 || n < (uint64_t)ctx->opt_split_min) return MPTCC_OK;
 	const uint64_t cap64 = std::min<uint64_t>(n * (uint64_t)ctx->opt_split_cap, 0xfffffff0ull);
 	CU(sb.rec.reserve(4 * cap64));
+	CU(sb.rel.reserve(12 * cap64));
 	CU(sb.obj.reserve(cap64));
 	CU(sb.pose.reserve(cap64));
 	CU(sb.ctl.reserve(4));
@@ -519,6 +523,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			if (rrc != MPTCC_OK) return rrc;
 		}
 		kp.cand_rec = sb->rec.p;
+		kp.cand_rel = sb->rel.p;
 		kp.cand_obj = sb->obj.p;
 		kp.cand_pose = sb->pose.p;
 		kp.cand_total = sb->ctl.p;

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 							for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
 							const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
 							float4 rec[4];
-							make_candidate_record(p, chunk_poses + (size_t)sl * rec_len, p.objects[e], m2, 0u, rec);
+							make_candidate_record(p, chunk_poses + (size_t)sl * rec_len, p.objects[e], m2, 0u, rec, p.cand_rel + 12ull * dst);
 							float4 *out = p.cand_rec + 4ull * dst;
 							out[0] = rec[0];
 							out[1] = rec[1];
@@ -203,6 +203,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const
 		first = __shfl_sync(FULL, first, 0);
 		if (first >= total) break;
 		const int n = (int)(total - first < (unsigned)kCandCap ? total - first : (unsigned)kCandCap);
+		tv.batch_first = first;
 		// ---- load the batch: records (coalesced float4 copy), objects, pose-set indices -------------------
 		const float4 *src_rec = p.cand_rec + 4ull * first;
 		for (int i = lane; i < 4 * n; i += 32) wm.cand[rec_at((unsigned)i >> 2, (unsigned)i & 3u)] = src_rec[i];
