@@ -375,7 +375,7 @@ struct mptcc_ctx {
 	long opt_time_phases = 0;        // record CUDA events around the kernels of the split pipeline
 	long opt_split = 1;              // two-kernel pipeline for large single-link batches
 	long opt_split_min = 1 << 15;    // ... from this many pose-sets per launch
-	long opt_split_cap = 3;          // candidate list capacity, per pose-set
+	long opt_split_cap = 3;          // candidate list capacity, per pose-set (grows after an overflow, see check_poses)
 	long opt_no_steal = 0;
 	long opt_steal_bottom = 0;
 	long opt_near_first = 1;
@@ -799,17 +799,25 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 			                   d.stream[k]));
 		}
 	}
+	bool overflowed = false;
 	for (size_t di = 0; di < nd; ++di) {
 		Device &d = ctx->devs[di];
 		if (jobs[di].empty()) continue;
 		CU(cudaSetDevice(d.id));
 		const size_t used = std::min<size_t>(jobs[di].size(), kPipe);
+		unsigned int ctl[kPipe][4] = {};
+		for (size_t k = 0; k < used; ++k)  // [1] = overflow flag of the last split launch of this staging set
+			if (d.split[k].ctl.p) CU(cudaMemcpyAsync(ctl[k], d.split[k].ctl.p, sizeof ctl[k], cudaMemcpyDeviceToHost, d.stream[k]));
 		for (size_t k = 0; k < used; ++k) {
 			CU(cudaStreamSynchronize(d.stream[k]));
 			float ms = 0.f;  // device time from the first kernel to the end of the last kernel of this stream
 			if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
+			overflowed = overflowed || ctl[k][1] != 0;
 		}
 	}
+	// The fused fall-back already produced the right verdicts; a scene this dense gets a longer candidate list
+	// from the next call on.
+	if (overflowed && ctx->opt_split_cap < 64) ctx->opt_split_cap = std::min<long>(64, ctx->opt_split_cap * 2);
 	return MPTCC_OK;
 }
 
