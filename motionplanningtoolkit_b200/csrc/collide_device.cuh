@@ -366,7 +366,7 @@ __device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const Dev
 struct RelF {
 	float R[9];
 	float T[3];
-	float S;  // tri filter scale (see tri_maybe_f32)
+	float S;  // tri filter scale (see tri_filter_f32)
 };
 
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
@@ -440,19 +440,26 @@ __device__ __forceinline__ F3 f3cross(const F3 &l, const F3 &r) {
 __device__ __forceinline__ float f3dot(const F3 &a, const F3 &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float f3maxabs(const F3 &a) { return fmaxf(fabsf(a.x), fmaxf(fabsf(a.y), fabsf(a.z))); }
 
-// One SAT axis of the fp32 filter: true => separated by more than eps along ax.  p1 is the origin.
-__device__ __forceinline__ bool axis_separates(const F3 &ax, const F3 &p2, const F3 &p3, const F3 &q1, const F3 &q2,
-                                               const F3 &q3, float eps) {
+// One SAT axis of the fp32 filter: the larger of the two one-sided gaps along ax (p1 is the origin).
+// gap > eps: certainly separated; gap < -eps: the projections certainly overlap (also in FCL's fp64 test).
+__device__ __forceinline__ float axis_gap(const F3 &ax, const F3 &p2, const F3 &p3, const F3 &q1, const F3 &q2,
+                                          const F3 &q3) {
 	const float a2 = f3dot(ax, p2), a3 = f3dot(ax, p3);
 	const float b1 = f3dot(ax, q1), b2 = f3dot(ax, q2), b3 = f3dot(ax, q3);
 	const float mnP = fminf(0.0f, fminf(a2, a3)), mxP = fmaxf(0.0f, fmaxf(a2, a3));
 	const float mnQ = fminf(b1, fminf(b2, b3)), mxQ = fmaxf(b1, fmaxf(b2, b3));
-	return (mnP - mxQ > eps) || (mnQ - mxP > eps);
+	return fmaxf(mnP - mxQ, mnQ - mxP);
 }
 
-// fp32 triangle filter: false => the fp64 test of FCL certainly finds a separating axis (no contact);
-// true => undecided, the pair must be re-decided in fp64.
-__device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, const float4 P3, const float4 Q1,
+// fp32 triangle filter, three-valued:
+//   TRI_SEPARATED : some axis separates by more than the error bound -> FCL's fp64 test finds that axis too
+//   TRI_INTERSECT : on all 17 axes the projections overlap by more than the error bound -> FCL's fp64 test
+//                   finds no separating axis and reports the contact (degenerate, near-zero axes never qualify:
+//                   their projections are all ~0, inside the band)
+//   TRI_UNCERTAIN : anything else (including NaN) -> re-decided in fp64
+constexpr int TRI_SEPARATED = 0, TRI_UNCERTAIN = 1, TRI_INTERSECT = 2;
+
+__device__ __forceinline__ int tri_filter_f32(const float4 P1, const float4 P2, const float4 P3, const float4 Q1,
                                               const float4 Q2, const float4 Q3, const RelF &x) {
 	const F3 o{P1.x, P1.y, P1.z};
 	const F3 p2 = f3sub(F3{P2.x, P2.y, P2.z}, o), p3 = f3sub(F3{P3.x, P3.y, P3.z}, o);
@@ -478,27 +485,38 @@ __device__ __forceinline__ bool tri_maybe_f32(const float4 P1, const float4 P2, 
 	const F3 e1 = p2, e2 = f3sub(p3, p2), e3 = F3{-p3.x, -p3.y, -p3.z};
 	const F3 f1 = f3sub(q2, q1), f2 = f3sub(q3, q2), f3 = f3sub(q1, q3);
 	const F3 n1 = f3cross(e1, e2), m1 = f3cross(f1, f2);
-	bool sep = false;
-	sep |= axis_separates(n1, p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(m1, p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e1, f1), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e1, f2), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e1, f3), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e2, f1), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e2, f2), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e2, f3), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e3, f1), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e3, f2), p2, p3, q1, q2, q3, eps2);
-	sep |= axis_separates(f3cross(e3, f3), p2, p3, q1, q2, q3, eps2);
-	if (!sep) {
-		sep |= axis_separates(f3cross(e1, n1), p2, p3, q1, q2, q3, eps3);
-		sep |= axis_separates(f3cross(e2, n1), p2, p3, q1, q2, q3, eps3);
-		sep |= axis_separates(f3cross(e3, n1), p2, p3, q1, q2, q3, eps3);
-		sep |= axis_separates(f3cross(f1, m1), p2, p3, q1, q2, q3, eps3);
-		sep |= axis_separates(f3cross(f2, m1), p2, p3, q1, q2, q3, eps3);
-		sep |= axis_separates(f3cross(f3, m1), p2, p3, q1, q2, q3, eps3);
+	// largest gap over the degree-2 axes and over the degree-3 axes (NaN-safe: fmaxf drops NaN, so NaNs are
+	// tracked separately through `ok`)
+	float g2 = axis_gap(n1, p2, p3, q1, q2, q3);
+	bool ok = g2 == g2;
+#define AX2(u, v)                                                   \
+	{                                                               \
+		const float g = axis_gap(f3cross(u, v), p2, p3, q1, q2, q3); \
+		ok = ok && (g == g);                                        \
+		g2 = fmaxf(g2, g);                                          \
 	}
-	return !sep;
+	{
+		const float g = axis_gap(m1, p2, p3, q1, q2, q3);
+		ok = ok && (g == g);
+		g2 = fmaxf(g2, g);
+	}
+	AX2(e1, f1) AX2(e1, f2) AX2(e1, f3) AX2(e2, f1) AX2(e2, f2) AX2(e2, f3) AX2(e3, f1) AX2(e3, f2) AX2(e3, f3)
+	if (ok && g2 > eps2) return TRI_SEPARATED;
+	float g3 = axis_gap(f3cross(e1, n1), p2, p3, q1, q2, q3);
+	ok = ok && (g3 == g3);
+#define AX3(u, v)                                                   \
+	{                                                               \
+		const float g = axis_gap(f3cross(u, v), p2, p3, q1, q2, q3); \
+		ok = ok && (g == g);                                        \
+		g3 = fmaxf(g3, g);                                          \
+	}
+	AX3(e2, n1) AX3(e3, n1) AX3(f1, m1) AX3(f2, m1) AX3(f3, m1)
+#undef AX2
+#undef AX3
+	if (!ok || !(eps2 == eps2) || !(eps3 == eps3)) return TRI_UNCERTAIN;
+	if (g3 > eps3) return TRI_SEPARATED;
+	if (g2 < -eps2 && g3 < -eps3) return TRI_INTERSECT;
+	return TRI_UNCERTAIN;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -756,7 +774,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 			// ---- 3. leaf phase: up to 32 triangle pairs -------------------------------------------------
 			const int k = lq < 32 ? lq : 32;
 			lq -= k;
-			bool maybe = false;
+			int verdict = TRI_SEPARATED;
 			uint2 pr = make_uint2(0u, 0u);
 			if (lane < k) {
 				pr = wm.leafq[lq + lane];
@@ -773,11 +791,13 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 					const float4 *t2 = tris2 + 3ull * (pr.y & 0xffffffu);
 					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
 					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
-					maybe = tri_maybe_f32(P1, P2, P3, Q1, Q2, Q3, x);
+					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
 				}
 			}
 			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
-			unsigned mm = __ballot_sync(FULL, maybe);
+			// pairs the filter could not separate: certain contacts skip the fp64 triangle test
+			unsigned mm = __ballot_sync(FULL, verdict != TRI_SEPARATED);
+			const unsigned sure = __ballot_sync(FULL, verdict == TRI_INTERSECT);
 			while (mm) {
 				const int from = __ffs(mm) - 1;
 				mm &= mm - 1;
@@ -786,14 +806,16 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 				const unsigned src = __float_as_uint(wm.cand[rec_at(cand, 3)].y);  // pose slot of this candidate
 				const unsigned e = tv.object(cand, wm);
 				if (tv.dead(src, wm)) continue;
-				if (COUNT) ctr[CTR_EXACT] += 1;
+				if (COUNT && !(((sure >> from) & 1u) && !p.always_replay)) ctr[CTR_EXACT] += 1;
 				// fp64 relative transform of this candidate, FCL's operation order: recomputed from the pose
 				// record into shared memory (fused kernel) or read from the candidate list (split pipeline)
 				const DevObject &ob = p.objects[e];
 				const double *rel = tv.exact_rel(p, wm, ob, src, cand, lane);
 				const DevModel &m1 = p.env.models[ob.model];
-				const bool hit = exact_tri_intersect_warp(rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
-				                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
+				const bool hit = ((sure >> from) & 1u) && !p.always_replay
+				                     ? true
+				                     : exact_tri_intersect_warp(rel, p.env.tri64 + 9ull * (m1.tri_base + t1),
+				                                                p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 				if (hit) {
 					// Path certificate.  FCL reports this contact only if every OBB pair on its descent to
 					// the two leaves passed obbDisjoint.  Each of those boxes contains its triangle, the two
