@@ -563,6 +563,15 @@ struct FusedTrav {
 	__device__ __forceinline__ void mark_hit(unsigned slot, unsigned, const WarpMem &, const KernelParams &, int) {
 		hitmask |= 1ull << slot;
 	}
+	// every lane may bring one certified hit (slot >= 0); the mask stays warp-uniform
+	__device__ __forceinline__ void mark_hits_per_lane(int slot, unsigned, const WarpMem &, int) {
+		unsigned b = __ballot_sync(0xffffffffu, slot >= 0);
+		while (b) {
+			const int l = __ffs(b) - 1;
+			b &= b - 1;
+			hitmask |= 1ull << __shfl_sync(0xffffffffu, slot, l);
+		}
+	}
 	__device__ __forceinline__ const double *pose_record(unsigned slot, unsigned, const WarpMem &) const {
 		return link_poses + (size_t)slot * stride;
 	}
@@ -594,6 +603,15 @@ struct SplitTrav {
 	__device__ __forceinline__ void mark_hit(unsigned slot, unsigned cand, const WarpMem &wm, const KernelParams &, int lane) {
 		__syncwarp();
 		if (lane == 0) {
+			wm.dead[slot] = 1;
+			const uint32_t pose = wm.cand_pose[cand];
+			atomicOr(verdict_bits + (pose >> 5), 1u << (pose & 31u));
+		}
+		__syncwarp();
+	}
+	__device__ __forceinline__ void mark_hits_per_lane(int slot, unsigned cand, const WarpMem &wm, int) {
+		__syncwarp();
+		if (slot >= 0) {
 			wm.dead[slot] = 1;
 			const uint32_t pose = wm.cand_pose[cand];
 			atomicOr(verdict_bits + (pose >> 5), 1u << (pose & 31u));
@@ -774,7 +792,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 			// ---- 3. leaf phase: up to 32 triangle pairs -------------------------------------------------
 			const int k = lq < 32 ? lq : 32;
 			lq -= k;
-			int verdict = TRI_SEPARATED;
+			int verdict = TRI_SEPARATED, fast_slot = -1;
 			uint2 pr = make_uint2(0u, 0u);
 			if (lane < k) {
 				pr = wm.leafq[lq + lane];
@@ -792,9 +810,25 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
 					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
 					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
+					if (verdict == TRI_INTERSECT && !p.always_replay) {
+						// Certain contact: try the path certificate (below) right here, every lane for its own
+						// pair, so the dependent loads of all pairs overlap instead of queueing in the
+						// warp-serial loop.  |T|_1 of the exact transform is bounded from the recentred fp32
+						// translation of the record (a larger magnitude only makes the certificate stricter).
+						const DevModel &m1 = p.env.models[p.objects[tv.object(lc, wm)].model];
+						const double t1n = (double)((fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2])) * 1.000001f);
+						const double mag = t1n + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+						                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 +
+						                   m2.cmax1 + m1.esum + m2.esum;
+						const double mu = fmin((double)p.env.mu_chain[__float_as_uint(r3.w) + pr.x],
+						                       (double)p.agent.mu_chain[m2.tri_base + (pr.y & 0xffffffu)]);
+						fast_slot = mu >= 1e-5 * mag ? (int)__float_as_uint(r3.y) : -1;
+					}
 				}
 			}
 			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
+			tv.mark_hits_per_lane(fast_slot, pr.y >> 24, wm, lane);
+			if (fast_slot >= 0) verdict = TRI_SEPARATED;  // settled
 			// pairs the filter could not separate: certain contacts skip the fp64 triangle test
 			unsigned mm = __ballot_sync(FULL, verdict != TRI_SEPARATED);
 			const unsigned sure = __ballot_sync(FULL, verdict == TRI_INTERSECT);
