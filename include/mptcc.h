@@ -97,6 +97,16 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes);
 int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n_pose_sets, const double *poses, int pose_format,
                       uint32_t *verdict_bits);
 
+/* The same call split in two, for callers that stream batches (a planner that prepares slice k+1 while slice
+ * k is being checked): submit enqueues the copies and kernels and returns a ticket at once; wait blocks until
+ * that ticket (and every earlier one) is complete, ticket 0 = everything submitted.  poses and verdict_bits
+ * must stay valid until the wait returns and should be pinned (mptcc_alloc_pinned), otherwise the copies
+ * are staged synchronously by the driver and submit does not overlap anything.  Up to 4 submits may be
+ * outstanding; a further submit first waits for the oldest.  mptcc_check_poses == submit + wait. */
+int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n_pose_sets, const double *poses, int pose_format,
+                       uint32_t *verdict_bits, uint64_t *ticket);
+int mptcc_wait(mptcc_ctx *ctx, uint64_t ticket);
+
 /* Map3D::safeEdge semantics for many edges at once (/root/reference/workspaces/map3d.hpp:33-37):
  * segment s owns pose-sets [seg_begin[s], seg_begin[s+1]); segment_safe[s] = 1 iff none collides
  * (an empty segment is safe). */

@@ -20,7 +20,7 @@ _ERR_NAMES = {1: "INVALID", 2: "STATE", 3: "NO_DEVICE", 4: "CUDA", 5: "NOMEM", 6
 # every symbol include/mptcc.h declares (tests check that the library exports exactly these)
 EXPORTS = [
     "mptcc_create", "mptcc_destroy", "mptcc_last_error", "mptcc_num_devices", "mptcc_set_environment",
-    "mptcc_set_agent", "mptcc_check_poses", "mptcc_check_segments", "mptcc_check_omni_edges", "mptcc_check_poses_device",
+    "mptcc_set_agent", "mptcc_check_poses", "mptcc_submit_poses", "mptcc_wait", "mptcc_check_segments", "mptcc_check_omni_edges", "mptcc_check_poses_device",
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
@@ -76,6 +76,10 @@ def load():
     L.mptcc_check_segments.argtypes = [vp, C.c_uint64, C.POINTER(C.c_uint64), vp, C.c_int, C.POINTER(C.c_uint8)]
     L.mptcc_check_omni_edges.restype = C.c_int
     L.mptcc_check_omni_edges.argtypes = [vp, C.c_uint64, vp, C.c_double, vp]
+    L.mptcc_submit_poses.restype = C.c_int
+    L.mptcc_submit_poses.argtypes = [vp, C.c_uint64, vp, C.c_int, vp, C.POINTER(C.c_uint64)]
+    L.mptcc_wait.restype = C.c_int
+    L.mptcc_wait.argtypes = [vp, C.c_uint64]
     L.mptcc_check_poses_device.restype = C.c_int
     L.mptcc_check_poses_device.argtypes = [vp, C.c_int, C.c_uint64, vp, C.c_int, vp, vp]
     L.mptcc_synchronize.restype = C.c_int
@@ -221,6 +225,22 @@ class Checker:
         bits = out if out is not None else np.zeros((n + 31) // 32, np.uint32)
         self._check(self.lib.mptcc_check_poses(self.h, n, p.ctypes.data, fmt, bits.ctypes.data))
         return bits
+
+    def submit_poses(self, poses, out, fmt=POSE_RT12):
+        """check_poses without the final wait: returns a ticket for wait().  `poses` (contiguous float64) and
+        `out` (uint32 verdict words) must stay alive until then; pinned arrays make the copies asynchronous."""
+        if not (isinstance(poses, np.ndarray) and poses.dtype == np.float64 and poses.flags.c_contiguous):
+            raise ValueError("submit_poses needs a C-contiguous float64 array (it is read after the call returns)")
+        n = poses.size // max(1, self._rec(fmt))
+        if out.dtype != np.uint32 or out.size < (n + 31) // 32:
+            raise ValueError("out: uint32[ceil(n/32)]")
+        t = C.c_uint64(0)
+        self._check(self.lib.mptcc_submit_poses(self.h, n, poses.ctypes.data, fmt, out.ctypes.data, C.byref(t)))
+        return t.value
+
+    def wait(self, ticket=0):
+        """Blocks until `ticket` (0 = everything submitted) and all earlier submits are complete."""
+        self._check(self.lib.mptcc_wait(self.h, ticket))
 
     def check_segments(self, seg_begin, poses, fmt=POSE_RT12):
         sb = np.ascontiguousarray(seg_begin, dtype=np.uint64)

@@ -312,7 +312,8 @@ struct DevPack {
 	}
 };
 
-constexpr int kPipe = 2;  // ping-pong staging sets per device
+constexpr int kPipe = 2;      // ping-pong staging sets per device
+constexpr int kInFlight = 4;  // mptcc_submit_poses calls that may be outstanding before submit waits for the oldest
 
 // Buffers of the split pipeline (split_kernels.cu) for one launch slot; grow-only.
 struct SplitBufs {
@@ -354,6 +355,10 @@ struct Device {
 	DevBuf<unsigned char> edge_safe;
 	DevBuf<uint32_t> edge_work;
 	float last_ms = 0.f;
+	// per outstanding submit: completion events of the two streams, overflow flags read back (pinned)
+	cudaEvent_t done[kInFlight][kPipe] = {};
+	unsigned int *ctl_h[kInFlight] = {};
+	size_t used[kInFlight] = {};
 };
 
 }  // namespace
@@ -380,6 +385,7 @@ struct mptcc_ctx {
 	long opt_steal_bottom = 0;
 	long opt_near_first = 1;
 	mptcc_counters ctr{};
+	uint64_t submitted = 0, completed = 0;  // tickets of mptcc_submit_poses
 	int ctas_per_sm_cached = -1;
 	bool ctas_cached_count = false;
 };
@@ -598,6 +604,12 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 			if (cudaEventCreate(&d.ev0[k]) != cudaSuccess || cudaEventCreate(&d.ev1[k]) != cudaSuccess) return MPTCC_ERR_CUDA;
 			if (d.work[k].reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
 		}
+		for (int t = 0; t < kInFlight; ++t) {
+			for (int k = 0; k < kPipe; ++k)
+				if (cudaEventCreateWithFlags(&d.done[t][k], cudaEventDisableTiming) != cudaSuccess) return MPTCC_ERR_CUDA;
+			if (cudaMallocHost(reinterpret_cast<void **>(&d.ctl_h[t]), sizeof(unsigned int) * 4 * kPipe) != cudaSuccess)
+				return MPTCC_ERR_CUDA;
+		}
 		if (d.work_user.reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (d.counters.reserve(CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
@@ -629,6 +641,11 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.edge_bits.release();
 		d.edge_safe.release();
 		d.edge_work.release();
+		for (int t = 0; t < kInFlight; ++t) {
+			for (int k = 0; k < kPipe; ++k)
+				if (d.done[t][k]) cudaEventDestroy(d.done[t][k]);
+			if (d.ctl_h[t]) cudaFreeHost(d.ctl_h[t]);
+		}
 		for (int k = 0; k < kPipe; ++k) {
 			d.poses[k].release();
 			d.bits[k].release();
@@ -732,12 +749,55 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 	return MPTCC_OK;
 }
 
+int mptcc_wait(mptcc_ctx *ctx, uint64_t ticket) {
+	if (!ctx) return MPTCC_ERR_INVALID;
+	if (ticket == 0) ticket = ctx->submitted;
+	if (ticket > ctx->submitted) return fail(ctx, MPTCC_ERR_INVALID, "unknown ticket");
+	bool overflowed = false;
+	// the streams run the submits in order: waiting for a ticket completes every earlier one
+	for (uint64_t t = ctx->completed + 1; t <= ticket; ++t) {
+		const int slot = (int)((t - 1) % kInFlight);
+		for (Device &d : ctx->devs) {
+			if (d.used[slot] == 0) continue;
+			CU(cudaSetDevice(d.id));
+			for (size_t k = 0; k < d.used[slot]; ++k) {
+				CU(cudaEventSynchronize(d.done[slot][k]));
+				overflowed = overflowed || d.ctl_h[slot][4 * k + 1] != 0;  // [1] = overflow flag of the last split launch
+				if (t == ctx->submitted) {
+					float ms = 0.f;  // device time from the first kernel to the end of the last kernel of this stream
+					if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
+				}
+			}
+			d.used[slot] = 0;
+		}
+		ctx->completed = t;
+	}
+	// The fused fall-back already produced the right verdicts; a scene this dense gets a longer candidate list
+	// from the next call on.
+	if (overflowed && ctx->opt_split_cap < 64) ctx->opt_split_cap = std::min<long>(64, ctx->opt_split_cap * 2);
+	return MPTCC_OK;
+}
+
 int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, uint32_t *verdict_bits) {
+	uint64_t ticket = 0;
+	const int rc = mptcc_submit_poses(ctx, n, poses, fmt, verdict_bits, &ticket);
+	if (rc != MPTCC_OK) return rc;
+	return mptcc_wait(ctx, ticket);
+}
+
+int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, uint32_t *verdict_bits, uint64_t *ticket) {
 	int rc = check_ready(ctx);
 	if (rc != MPTCC_OK) return rc;
+	if (!ticket) return fail(ctx, MPTCC_ERR_INVALID, "null ticket");
 	if (fmt != MPTCC_POSE_RT12 && fmt != MPTCC_POSE_TQ7) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
+	*ticket = ctx->submitted;  // an empty batch completes with whatever is outstanding
 	if (n == 0) return MPTCC_OK;
 	if (!poses || !verdict_bits) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
+	if (ctx->submitted - ctx->completed >= (uint64_t)kInFlight) {
+		rc = mptcc_wait(ctx, ctx->completed + 1);
+		if (rc != MPTCC_OK) return rc;
+	}
+	const int tslot = (int)(ctx->submitted % kInFlight);
 	const size_t rec = (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size();  // doubles per pose-set
 	const uint64_t n_words = (n + 31) / 32;
 	const size_t nd = ctx->devs.size();
@@ -799,25 +859,23 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 			                   d.stream[k]));
 		}
 	}
-	bool overflowed = false;
+	// completion marker of this submit on both streams + the overflow flags of its last split launches
 	for (size_t di = 0; di < nd; ++di) {
 		Device &d = ctx->devs[di];
+		d.used[tslot] = 0;
 		if (jobs[di].empty()) continue;
 		CU(cudaSetDevice(d.id));
 		const size_t used = std::min<size_t>(jobs[di].size(), kPipe);
-		unsigned int ctl[kPipe][4] = {};
-		for (size_t k = 0; k < used; ++k)  // [1] = overflow flag of the last split launch of this staging set
-			if (d.split[k].ctl.p) CU(cudaMemcpyAsync(ctl[k], d.split[k].ctl.p, sizeof ctl[k], cudaMemcpyDeviceToHost, d.stream[k]));
 		for (size_t k = 0; k < used; ++k) {
-			CU(cudaStreamSynchronize(d.stream[k]));
-			float ms = 0.f;  // device time from the first kernel to the end of the last kernel of this stream
-			if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
-			overflowed = overflowed || ctl[k][1] != 0;
+			d.ctl_h[tslot][4 * k + 1] = 0;
+			if (d.split[k].ctl.p)
+				CU(cudaMemcpyAsync(d.ctl_h[tslot] + 4 * k, d.split[k].ctl.p, sizeof(unsigned int) * 4, cudaMemcpyDeviceToHost,
+				                   d.stream[k]));
+			CU(cudaEventRecord(d.done[tslot][k], d.stream[k]));
 		}
+		d.used[tslot] = used;
 	}
-	// The fused fall-back already produced the right verdicts; a scene this dense gets a longer candidate list
-	// from the next call on.
-	if (overflowed && ctx->opt_split_cap < 64) ctx->opt_split_cap = std::min<long>(64, ctx->opt_split_cap * 2);
+	*ticket = ++ctx->submitted;
 	return MPTCC_OK;
 }
 

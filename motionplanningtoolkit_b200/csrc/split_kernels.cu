@@ -21,11 +21,16 @@ namespace {
 constexpr int kBpWarpsPerCta = 8;
 
 // per-warp shared memory of the broadphase kernel: pose boxes + cluster queue + candidate ids
+#ifndef MPTCC_NP_BATCH
+#define MPTCC_NP_BATCH MPTCC_CAND_CAP
+#endif
+constexpr int kNpBatch = MPTCC_NP_BATCH;  // candidates a narrowphase warp traverses together
+
 __host__ __device__ constexpr unsigned bp_warp_smem_bytes() { return 6u * 32u * 8u + kClusterQueueCap * 4u + kCandCap * 4u + 32u * 4u; }
 
 // per-warp shared memory of the narrowphase kernel
 __host__ __device__ constexpr unsigned np_warp_smem_bytes() {
-	return kLeafQueueCap * 8u + kCandCap * 64u + 16u * 8u + kCandCap * 4u + kCandCap * 4u + kCandCap + 32u;
+	return kLeafQueueCap * 8u + kNpBatch * 64u + 16u * 8u + kNpBatch * 4u + kNpBatch * 4u + kNpBatch + 32u;
 }
 
 template <bool COUNT>
@@ -40,7 +45,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 	wm.clq = reinterpret_cast<uint32_t *>(base);
 	base += kClusterQueueCap * 4;
 	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
-	base += kCandCap * 4;
+	base += kNpBatch * 4;
 	unsigned *pfx = reinterpret_cast<unsigned *>(base);  // [32] first list position of each pose slot's run
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 			// ---- phase C1 ---------------------------------------------------------------------------------
 			constexpr int kPer = 32 / kClusterSize;
 			int c = 0;
-			for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
+			for (; c < ncl && ncand <= kNpBatch - 32; c += kPer) {
 				const int idx = c + lane / kClusterSize;
 				bool ov = false;
 				unsigned sl = 0, eobj = 0;
@@ -116,7 +121,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 			}
 			__syncwarp();
 			// ---- flush: group by pose slot, phase C2, append to the global candidate list --------------------
-			if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
+			if (ncand > kNpBatch - 32 || (!more && ncl == 0)) {
 				if (ncand > 0) {
 					// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
 					int mine = 0;
@@ -163,8 +168,22 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 }
 
 
+#ifndef MPTCC_NP_WARPS
+#define MPTCC_NP_WARPS 8
+#endif
+#ifndef MPTCC_NP_CTAS
+#define MPTCC_NP_CTAS 2
+#endif
+constexpr int kNpWarpsPerCta = MPTCC_NP_WARPS;
+
+#ifdef MPTCC_NP_MAXREG
+#define NP_BOUNDS __maxnreg__(MPTCC_NP_MAXREG)
+#else
+#define NP_BOUNDS __launch_bounds__(kNpWarpsPerCta * 32, MPTCC_NP_CTAS)
+#endif
+
 template <bool COUNT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const __grid_constant__ KernelParams p) {
+__global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
@@ -173,15 +192,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const
 	wm.leafq = reinterpret_cast<uint2 *>(base);
 	base += kLeafQueueCap * 8;
 	wm.cand = reinterpret_cast<float4 *>(base);
-	base += kCandCap * 64;
+	base += kNpBatch * 64;
 	wm.rel = reinterpret_cast<double *>(base);
 	base += 16 * 8;
 	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
-	base += kCandCap * 4;
+	base += kNpBatch * 4;
 	wm.cand_pose = reinterpret_cast<uint32_t *>(base);
-	base += kCandCap * 4;
+	base += kNpBatch * 4;
 	wm.dead = base;
-	base += kCandCap;
+	base += kNpBatch;
 	wm.donor = base;
 
 	// An overflowed list has holes (a flush that did not fit wrote nothing): leave the whole launch to the
@@ -199,10 +218,10 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) narrowphase_kernel(const
 
 	while (true) {
 		unsigned first = 0;
-		if (lane == 0) first = atomicAdd(p.work_counter2, (unsigned)kCandCap);
+		if (lane == 0) first = atomicAdd(p.work_counter2, (unsigned)kNpBatch);
 		first = __shfl_sync(FULL, first, 0);
 		if (first >= total) break;
-		const int n = (int)(total - first < (unsigned)kCandCap ? total - first : (unsigned)kCandCap);
+		const int n = (int)(total - first < (unsigned)kNpBatch ? total - first : (unsigned)kNpBatch);
 		tv.batch_first = first;
 		// ---- load the batch: records (coalesced float4 copy), objects, pose-set indices -------------------
 		const float4 *src_rec = p.cand_rec + 4ull * first;
@@ -243,6 +262,10 @@ template <class K>
 int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads, size_t smem, void *stream) {
 	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	if (e != cudaSuccess) return (int)e;
+#ifdef MPTCC_CARVEOUT
+	e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, MPTCC_CARVEOUT);
+	if (e != cudaSuccess) return (int)e;
+#endif
 	int per_sm = 0;
 	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
 	if (e != cudaSuccess) return (int)e;
@@ -260,9 +283,9 @@ int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *str
 }
 
 int launch_narrowphase(const KernelParams &p, int sm_count, bool count, void *stream) {
-	const size_t smem = (size_t)kWarpsPerCta * np_warp_smem_bytes();
-	return count ? launch_persistent(narrowphase_kernel<true>, p, sm_count, kWarpsPerCta * 32, smem, stream)
-	             : launch_persistent(narrowphase_kernel<false>, p, sm_count, kWarpsPerCta * 32, smem, stream);
+	const size_t smem = (size_t)kNpWarpsPerCta * np_warp_smem_bytes();
+	return count ? launch_persistent(narrowphase_kernel<true>, p, sm_count, kNpWarpsPerCta * 32, smem, stream)
+	             : launch_persistent(narrowphase_kernel<false>, p, sm_count, kNpWarpsPerCta * 32, smem, stream);
 }
 
 }  // namespace mptcc

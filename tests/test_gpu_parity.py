@@ -258,3 +258,36 @@ def test_split_pipeline_unit_box_and_quaternions(box_scene):
     assert_bits_equal(chk.check_poses(poses, capi.POSE_TQ7), box_scene.oracle_bits(poses, O.POSE_TQ7), len(poses), "split TQ7")
     poses = scenes.translation_poses(np.stack([rng.uniform(40000, -1.6, 1.6) for _ in range(3)], 1))
     assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "split translations")
+
+
+def test_submit_wait_matches_synchronous_calls(box_scene):
+    """mptcc_submit_poses / mptcc_wait: several batches in flight (more than the library keeps outstanding, so a
+    submit has to retire the oldest itself), pinned and pageable buffers, tickets waited out of order."""
+    rng = scenes.SplitMix64(93)
+    chk = box_scene.checker(sub_batch=4096, split=1, split_min=32)
+    batches, outs, pinned = [], [], []
+    for i in range(7):
+        n = 9000 + 517 * i
+        poses = scenes.random_poses_rt12(rng, n, (-1.6,) * 3, (1.6,) * 3)
+        if i % 2 == 0:  # pinned buffers: the copies really are asynchronous
+            pp, pb = capi.PinnedArray(poses.size, np.float64), capi.PinnedArray((n + 31) // 32, np.uint32)
+            pp.array[:] = poses.ravel()
+            pinned += [pp, pb]
+            batches.append(pp.array)
+            outs.append(pb.array)
+        else:
+            batches.append(np.ascontiguousarray(poses).ravel())
+            outs.append(np.zeros((n + 31) // 32, np.uint32))
+    tickets = [chk.submit_poses(b, o) for b, o in zip(batches, outs)]
+    assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+    chk.wait(tickets[3])
+    chk.wait(tickets[1])  # already complete: returns at once
+    chk.wait(0)
+    for i, (b, o) in enumerate(zip(batches, outs)):
+        n = 9000 + 517 * i
+        want = box_scene.oracle_bits(b.reshape(n, 12))
+        assert_bits_equal(o, want, n, "submit/wait batch %d" % i)
+        assert np.array_equal(o, chk.check_poses(b.reshape(n, 12)))
+    with pytest.raises(capi.MptccError):
+        chk.wait(tickets[-1] + 100)  # never issued
+    assert chk.submit_poses(np.zeros(0), np.zeros(0, np.uint32)) == tickets[-1] + 7  # empty: nothing new to wait for
