@@ -73,6 +73,41 @@ public:
 				}
 		return safe;
 	}
+	// safeEdges in two halves: submitEdges enqueues the device work and returns, PendingEdges::get() waits and
+	// folds the pose-set verdicts into one bool per edge.  Lets a planner expand its next slice of edges while
+	// this one is on the GPU.
+	class PendingEdges {
+	public:
+		std::vector<bool> get() {
+			const std::vector<bool> &hit = verdicts->get();
+			std::vector<bool> safe(begin.size() - 1, true);
+			for (size_t i = 0; i + 1 < begin.size(); ++i)
+				for (size_t k = begin[i]; k < begin[i + 1]; ++k)
+					if (hit[k]) {
+						safe[i] = false;
+						break;
+					}
+			return safe;
+		}
+
+	private:
+		friend class Map3D;
+		std::shared_ptr<PendingVerdicts> verdicts;
+		std::vector<size_t> begin;
+	};
+	PendingEdges submitEdges(const Agent &agent, const std::vector<Edge> &edges, double dt) const {
+		auto agentMeshes = agent.getMeshes();
+		std::vector<std::vector<fcl::Transform3f> > all;
+		PendingEdges out;
+		out.begin.assign(1, 0);
+		for (const auto &e : edges) {
+			auto poses = agent.getPoses(e, dt);
+			all.insert(all.end(), poses.begin(), poses.end());
+			out.begin.push_back(all.size());
+		}
+		out.verdicts = MeshHandler::submitPoseSets(mesh, agentMeshes, all);
+		return out;
+	}
 	// Edges of translation-only agents (Omnidirectional): only (start, end) cross the PCIe bus, the poses
 	// are interpolated on the device.  result[i] == safeEdge(agent, Edge(start_i, end_i), dt).
 	std::vector<bool> safeStraightEdges(const Agent &agent, const std::vector<double> &startEnd, double dt) const {

@@ -16,8 +16,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
+#include <map>
+#include <memory>
 #include <sstream>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../mptcc.h"
@@ -124,6 +127,76 @@ private:
 	mutable std::vector<const SimpleAgentMeshHandler *> agentKey;
 };
 
+namespace mpt_b200 {
+// Pinned staging blocks for the asynchronous calls, reused between batches (cudaMallocHost is far too slow
+// to sit on a per-call path).  Not thread-safe, like the rest of the shim.
+class PinnedPool {
+public:
+	static void *take(size_t bytes) {
+		std::vector<std::pair<void *, size_t> > &f = blocks();
+		size_t best = f.size();
+		for (size_t i = 0; i < f.size(); ++i)
+			if (f[i].second >= bytes && (best == f.size() || f[i].second < f[best].second)) best = i;
+		if (best != f.size()) {
+			void *p = f[best].first;
+			sizes()[p] = f[best].second;
+			f.erase(f.begin() + (long)best);
+			return p;
+		}
+		const size_t cap = bytes < 4096 ? 4096 : bytes + bytes / 2;
+		void *p = mptcc_alloc_pinned(cap);
+		if (!p) {
+			fprintf(stderr, "mpt_b200: cannot allocate %zu bytes of pinned memory\n", cap);
+			exit(1);
+		}
+		sizes()[p] = cap;
+		return p;
+	}
+	static void give(void *p) {
+		if (p) blocks().push_back(std::make_pair(p, sizes()[p]));
+	}
+
+private:
+	static std::vector<std::pair<void *, size_t> > &blocks() {
+		static std::vector<std::pair<void *, size_t> > b;
+		return b;
+	}
+	static std::map<void *, size_t> &sizes() {
+		static std::map<void *, size_t> s;
+		return s;
+	}
+};
+}  // namespace mpt_b200
+
+// Verdicts of a batch whose device work is still in flight (MeshHandler::submitPoseSets): get() waits for it.
+class PendingVerdicts {
+public:
+	PendingVerdicts() : env(nullptr), ctx(nullptr), done(true) {}
+	~PendingVerdicts() { finish(); }
+	// one bool per pose-set of the submitted batch, true = in collision
+	const std::vector<bool> &get() {
+		finish();
+		return verdict;
+	}
+
+private:
+	friend class MeshHandler;
+	PendingVerdicts(const PendingVerdicts &);
+	PendingVerdicts &operator=(const PendingVerdicts &);
+	struct Part {
+		double *rec;
+		uint32_t *bits;
+		std::vector<size_t> index;
+		uint64_t ticket;
+	};
+	void finish();
+	const StaticEnvironmentMeshHandler *env;
+	mptcc_ctx *ctx;
+	std::vector<Part> parts;
+	std::vector<bool> verdict;
+	bool done;
+};
+
 class MeshHandler {
 public:
 	// [P][L] transforms -> pose records.  All transforms of a batch built from matrices / translations use
@@ -183,6 +256,47 @@ public:
 		return verdict;
 	}
 
+	// collidingPoseSets without the wait: the copies and kernels are enqueued (mptcc_submit_poses, pinned
+	// staging) and the caller goes on preparing its next batch; verdicts = result->get().  Results of earlier
+	// submits complete first; up to four may be outstanding.
+	static std::shared_ptr<PendingVerdicts> submitPoseSets(const StaticEnvironmentMeshHandler &environment,
+	                                                       const std::vector<const SimpleAgentMeshHandler *> &agent,
+	                                                       const std::vector<std::vector<fcl::Transform3f> > &poses) {
+		std::shared_ptr<PendingVerdicts> out(new PendingVerdicts);
+		out->verdict.assign(poses.size(), false);
+		if (poses.empty() || agent.empty()) return out;
+		out->env = &environment;
+		out->ctx = environment.getCollisionChecker(agent);
+		for (int quat = 0; quat < 2; ++quat) {
+			std::vector<std::vector<fcl::Transform3f> > part;
+			PendingVerdicts::Part pt;
+			for (size_t i = 0; i < poses.size(); ++i) {
+				if (poses[i].empty()) continue;
+				if ((int)poses[i][0].builtFromQuaternion() == quat) {
+					part.push_back(poses[i]);
+					pt.index.push_back(i);
+				}
+			}
+			if (part.empty()) continue;
+			std::vector<double> rec;
+			if (packPoses(part, agent.size(), quat != 0, rec) != 0) {
+				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
+				exit(1);
+			}
+			const size_t words = (part.size() + 31) / 32;
+			pt.rec = static_cast<double *>(mpt_b200::PinnedPool::take(rec.size() * sizeof(double)));
+			pt.bits = static_cast<uint32_t *>(mpt_b200::PinnedPool::take(words * sizeof(uint32_t)));
+			memcpy(pt.rec, rec.data(), rec.size() * sizeof(double));
+			pt.ticket = 0;
+			out->done = false;
+			out->parts.push_back(pt);
+			environment.check(mptcc_submit_poses(out->ctx, part.size(), pt.rec, quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
+			                                     pt.bits, &out->parts.back().ticket),
+			                  "mptcc_submit_poses");
+		}
+		return out;
+	}
+
 	// straight, translation-only edges (start xyz, end xyz) interpolated ON THE DEVICE with the
 	// rule of Omnidirectional::getPoses (agents/omnidirectional.hpp:202-247); result[i] = edge i is safe.
 	static std::vector<bool> safeStraightEdges(const StaticEnvironmentMeshHandler &environment,
@@ -215,3 +329,15 @@ public:
 		return false;
 	}
 };
+
+inline void PendingVerdicts::finish() {
+	if (done) return;
+	done = true;
+	for (Part &pt : parts) {
+		env->check(mptcc_wait(ctx, pt.ticket), "mptcc_wait");
+		for (size_t k = 0; k < pt.index.size(); ++k) verdict[pt.index[k]] = (pt.bits[k >> 5] >> (k & 31)) & 1u;
+		mpt_b200::PinnedPool::give(pt.rec);
+		mpt_b200::PinnedPool::give(pt.bits);
+	}
+	parts.clear();
+}
