@@ -697,17 +697,31 @@ __device__ __forceinline__ void make_candidate_record(const KernelParams &p, con
 	rec[3] = make_float4(S, __uint_as_float(slot), __uint_as_float(m1.node_base), __uint_as_float(m1.tri_base));
 }
 
-// One step of the lane-per-pose walk of the threaded broadphase tree; returns true and the cluster when the
-// lane's (fp32, outward-rounded) box touches a leaf.
-__device__ __forceinline__ bool bp_tree_step(const KernelParams &p, unsigned &node, const float *amin, const float *amax,
+// Pose box -> the integer grid of the broadphase tree (device_layout.hpp), rounded outward by one extra cell
+// (the fp32 evaluation of (x - origin) * inv_cell is off by < 0.02 cells).  Non-finite boxes keep the old
+// behaviour of the float test: NaN "overlaps" everything, +-inf saturates.
+__device__ __forceinline__ void quantize_pose_box(const KernelParams &p, const float *amin, const float *amax, int *qmin,
+                                                  int *qmax) {
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float lo = (amin[k] - p.bp_origin[k]) * p.bp_inv_cell[k], hi = (amax[k] - p.bp_origin[k]) * p.bp_inv_cell[k];
+		qmin[k] = (int)floorf(fminf(fmaxf(lo, -2.0f), 65538.0f)) - 1;  // NaN -> -3
+		qmax[k] = (int)ceilf(fmaxf(fminf(hi, 65538.0f), -2.0f)) + 1;   // NaN -> 65539
+	}
+}
+
+// One step of the lane-per-pose walk of the threaded broadphase tree (one 16-byte node per visit); returns
+// true and the cluster when the lane's quantized box touches a leaf.
+__device__ __forceinline__ bool bp_tree_step(const KernelParams &p, unsigned &node, const int *qmin, const int *qmax,
                                              unsigned &cluster) {
-	const float4 lo = __ldg(p.bp_nodes + 2ull * node), hi = __ldg(p.bp_nodes + 2ull * node + 1);
-	const bool ov = !(lo.x > amax[0] || lo.y > amax[1] || lo.z > amax[2] || hi.x < amin[0] || hi.y < amin[1] ||
-	                  hi.z < amin[2]);
-	const int esc = __float_as_int(lo.w), leaf = __float_as_int(hi.w);
-	cluster = (unsigned)leaf;
-	node = (ov && leaf < 0) ? node + 1u : (unsigned)esc;
-	return ov && leaf >= 0;
+	const uint4 nd = __ldg(p.bp_nodes + node);
+	const int lx = (int)(nd.x & 0xffffu), ly = (int)(nd.x >> 16), lz = (int)(nd.y & 0xffffu);
+	const int hx = (int)(nd.y >> 16), hy = (int)(nd.z & 0xffffu), hz = (int)(nd.z >> 16);
+	const bool ov = !(lx > qmax[0] || ly > qmax[1] || lz > qmax[2] || hx < qmin[0] || hy < qmin[1] || hz < qmin[2]);
+	const bool leaf = (nd.w >> 31) != 0u;
+	cluster = nd.w & 0x7fffffffu;
+	node = (leaf || ov) ? node + 1u : nd.w;  // (a leaf's escape is the next node in pre-order)
+	return ov && leaf;
 }
 
 // FCL's exact closed-interval AABB::overlap(environment object, agent link) in fp64 [FCL-recalled C.6];

@@ -21,13 +21,15 @@
 //
 // Broadphase tree (bp_nodes): the objects are sorted along a Morton curve and cut into clusters of
 // kClusterSize consecutive objects; a binary tree over the cluster sequence is stored in pre-order
-// ("threaded": no stack needed).  Node n = 2 float4:
-//   [0] = (box min xyz rounded down, int-bits escape)   escape = index of the next node once this
-//                                                       subtree is done (n_bp_nodes = end)
-//   [1] = (box max xyz rounded up,   int-bits cluster)  cluster >= 0: leaf for objects
-//                                                       [cluster*kClusterSize, +kClusterSize); -1: inner,
-//                                                       the first child is node n+1.
-// The fp32 boxes are conservative; every object of a touched cluster is re-tested in fp64.
+// ("threaded": no stack needed).  Node n = one uint4 (16 B, one load per visit):
+//   x = qmin.x | qmin.y << 16,  y = qmin.z | qmax.x << 16,  z = qmax.y | qmax.z << 16
+//       the node box on a 16-bit grid over the scene box, q(x) = (x - bp_origin) * bp_inv_cell, minima rounded
+//       down and maxima up (the scene spans 65 000 cells);
+//   w = inner node: escape = index of the next node once this subtree is done (n_bp_nodes = end), the first
+//       child is node n+1;  leaf: 0x80000000 | cluster, for objects [cluster*kClusterSize, +kClusterSize)
+//       (a leaf's escape is n+1).
+// A pose box is moved to the same grid with one more cell of slack (quantize_pose_box).
+// The grid boxes are conservative; every object of a touched cluster is re-tested in fp64.
 #pragma once
 
 #include <cstdint>
@@ -79,8 +81,9 @@ struct KernelParams {
 	const double *obj_aabb;      // [6][n_objects_pad] world AABB min xyz, max xyz (exact fp64), component-major,
 	                             // same order, padded with empty boxes to a multiple of kClusterSize
 	uint32_t n_objects_pad;
-	const float4 *bp_nodes;      // broadphase tree, 2 float4 per node (see below)
+	const uint4 *bp_nodes;       // broadphase tree, one uint4 per node (see above)
 	uint32_t n_bp_nodes;
+	float bp_origin[3], bp_inv_cell[3];
 	const uint32_t *link_model;  // [n_links] agent-pack model id of link j
 	uint32_t n_objects;
 	uint32_t n_links;

@@ -194,8 +194,18 @@ uint32_t morton10(double x) {  // x in [0,1)
 
 struct BpBuilder {
 	const std::vector<DevObject> &objs;
-	std::vector<float4> nodes;
-	explicit BpBuilder(const std::vector<DevObject> &o) : objs(o) {}
+	std::vector<uint4> nodes;
+	float origin[3], inv_cell[3];  // grid of the 16-bit node boxes: q(x) = (x - origin) * inv_cell
+	explicit BpBuilder(const std::vector<DevObject> &o) : objs(o) {
+		double lo[3], hi[3];
+		cluster_box(0, (objs.size() + kClusterSize - 1) / kClusterSize, lo, hi);
+		for (int k = 0; k < 3; ++k) {
+			origin[k] = round_down_f32(lo[k]);
+			const double extent = hi[k] - (double)origin[k];
+			// the scene spans 65 000 of the 65 536 cells: rounding never pushes a box past the last cell
+			inv_cell[k] = extent > 0.0 && std::isfinite(extent) ? (float)(65000.0 / extent) : 1.0f;
+		}
+	}
 
 	void cluster_box(size_t c0, size_t c1, double lo[3], double hi[3]) const {
 		for (int k = 0; k < 3; ++k) {
@@ -210,24 +220,34 @@ struct BpBuilder {
 			}
 	}
 
+	// cell index of x, rounded outward (down for a box minimum, up for a maximum); fp64 here, the 1e-6
+	// covers its rounding.  Non-finite boxes cover the whole grid.
+	uint32_t cell(double x, int k, bool up) const {
+		const double q = (x - (double)origin[k]) * (double)inv_cell[k];
+		if (!(q == q)) return up ? 65535u : 0u;
+		const double r = up ? std::ceil(q + 1e-6) : std::floor(q - 1e-6);
+		return (uint32_t)std::min(65535.0, std::max(0.0, r));
+	}
+
 	// pre-order emission of the subtree over clusters [c0, c1)
 	void emit(size_t c0, size_t c1) {
-		const size_t me = nodes.size() / 2;
+		const size_t me = nodes.size();
 		double lo[3], hi[3];
 		cluster_box(c0, c1, lo, hi);
-		nodes.push_back(make_float4(round_down_f32(lo[0]), round_down_f32(lo[1]), round_down_f32(lo[2]), 0.f));
-		nodes.push_back(make_float4(round_up_f32(hi[0]), round_up_f32(hi[1]), round_up_f32(hi[2]), 0.f));
-		int32_t leaf = -1;
+		uint4 nd;
+		nd.x = cell(lo[0], 0, false) | (cell(lo[1], 1, false) << 16);
+		nd.y = cell(lo[2], 2, false) | (cell(hi[0], 0, true) << 16);
+		nd.z = cell(hi[1], 1, true) | (cell(hi[2], 2, true) << 16);
+		nd.w = 0u;
+		nodes.push_back(nd);
 		if (c1 - c0 == 1) {
-			leaf = (int32_t)c0;
+			nodes[me].w = 0x80000000u | (uint32_t)c0;  // leaf: its escape is simply the next node
 		} else {
 			const size_t mid = c0 + (c1 - c0) / 2;
 			emit(c0, mid);
 			emit(mid, c1);
+			nodes[me].w = (uint32_t)nodes.size();  // escape
 		}
-		const int32_t escape = (int32_t)(nodes.size() / 2);
-		std::memcpy(&nodes[2 * me].w, &escape, 4);
-		std::memcpy(&nodes[2 * me + 1].w, &leaf, 4);
 	}
 };
 
@@ -338,7 +358,7 @@ struct Device {
 	DevPack env, agent;
 	DevBuf<DevObject> objects;
 	DevBuf<double> obj_aabb;
-	DevBuf<float4> bp_nodes;
+	DevBuf<uint4> bp_nodes;
 	DevBuf<uint32_t> link_model;
 	DevBuf<double> poses[kPipe];
 	DevBuf<uint32_t> bits[kPipe];
@@ -368,7 +388,8 @@ struct mptcc_ctx {
 	HostPack env_h, agent_h;
 	std::vector<DevObject> objects_h;
 	std::vector<double> obj_aabb_h;
-	std::vector<float4> bp_nodes_h;
+	std::vector<uint4> bp_nodes_h;
+	float bp_origin[3] = {0.f, 0.f, 0.f}, bp_inv_cell[3] = {1.f, 1.f, 1.f};
 	std::vector<uint32_t> link_model_h;
 	bool env_set = false, agent_set = false;
 	std::string err;
@@ -474,7 +495,11 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.obj_aabb = d.obj_aabb.p;
 	kp.n_objects_pad = (uint32_t)(ctx->obj_aabb_h.size() / 6);
 	kp.bp_nodes = d.bp_nodes.p;
-	kp.n_bp_nodes = (uint32_t)(ctx->bp_nodes_h.size() / 2);
+	kp.n_bp_nodes = (uint32_t)ctx->bp_nodes_h.size();
+	for (int k = 0; k < 3; ++k) {
+		kp.bp_origin[k] = ctx->bp_origin[k];
+		kp.bp_inv_cell[k] = ctx->bp_inv_cell[k];
+	}
 	kp.link_model = d.link_model.p;
 	kp.n_objects = (uint32_t)ctx->objects_h.size();
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
@@ -714,6 +739,10 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 		BpBuilder bp(ctx->objects_h);
 		bp.emit(0, (ctx->objects_h.size() + kClusterSize - 1) / kClusterSize);
 		ctx->bp_nodes_h.swap(bp.nodes);
+		for (int k = 0; k < 3; ++k) {
+			ctx->bp_origin[k] = bp.origin[k];
+			ctx->bp_inv_cell[k] = bp.inv_cell[k];
+		}
 	}
 	const int rc = upload_scene_part(ctx, true);
 	if (rc != MPTCC_OK) return rc;

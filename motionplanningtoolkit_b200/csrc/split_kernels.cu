@@ -68,6 +68,8 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 		// ---- phase A ------------------------------------------------------------------------------------
 		float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
 		if (valid) pose_world_box(chunk_poses + (size_t)lane * rec_len, p.pose_format, m2, wm.box + lane, amin, amax);
+		int qmin[3], qmax[3];
+		quantize_pose_box(p, amin, amax, qmin, qmax);
 		__syncwarp();
 		unsigned node = valid ? 0u : p.n_bp_nodes;
 		int ncl = 0, ncand = 0;
@@ -81,7 +83,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 					break;
 				}
 				unsigned cl = 0;
-				const bool leaf_hit = act && bp_tree_step(p, node, amin, amax, cl);
+				const bool leaf_hit = act && bp_tree_step(p, node, qmin, qmax, cl);
 				const unsigned m = __ballot_sync(FULL, leaf_hit);
 				if (m) {
 					if (leaf_hit) wm.clq[ncl + __popc(m & lt)] = ((unsigned)lane << 27) | cl;
