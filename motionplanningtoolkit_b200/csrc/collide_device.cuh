@@ -415,6 +415,7 @@ __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a
 	dj |= fabsf(T0 * B[0] + T1 * B[3] + T2 * B[6]) > eb0 + (F[0] * ea0 + F[3] * ea1 + F[6] * ea2) + mg;
 	dj |= fabsf(T0 * B[1] + T1 * B[4] + T2 * B[7]) > eb1 + (F[1] * ea0 + F[4] * ea1 + F[7] * ea2) + mg;
 	dj |= fabsf(T0 * B[2] + T1 * B[5] + T2 * B[8]) > eb2 + (F[2] * ea0 + F[5] * ea1 + F[8] * ea2) + mg;
+#ifndef MPTCC_OBB_FACE_ONLY
 	// A0 x B0..2
 	dj |= fabsf(T2 * B[3] - T1 * B[6]) > ea1 * F[6] + ea2 * F[3] + eb1 * F[2] + eb2 * F[1] + mg;
 	dj |= fabsf(T2 * B[4] - T1 * B[7]) > ea1 * F[7] + ea2 * F[4] + eb0 * F[2] + eb2 * F[0] + mg;
@@ -427,6 +428,7 @@ __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a
 	dj |= fabsf(T1 * B[0] - T0 * B[3]) > ea0 * F[3] + ea1 * F[0] + eb1 * F[8] + eb2 * F[7] + mg;
 	dj |= fabsf(T1 * B[1] - T0 * B[4]) > ea0 * F[4] + ea1 * F[1] + eb0 * F[8] + eb2 * F[6] + mg;
 	dj |= fabsf(T1 * B[2] - T0 * B[5]) > ea0 * F[5] + ea1 * F[2] + eb0 * F[7] + eb1 * F[6] + mg;
+#endif
 	return dj;
 }
 
