@@ -369,6 +369,21 @@ struct RelF {
 	float S;  // tri filter scale (see tri_filter_f32)
 };
 
+// One 256-bit read-only load (sm_100: LDG.E.256): half a node.  The L1 data pipe spends one wavefront per
+// 32-byte sector an instruction touches; the per-lane gathers of the traversal touch a different sector in
+// every lane, so a node fetched as four 16-byte loads costs four wavefronts per lane and as two 32-byte
+// loads two -- that pipe is what bounds the narrowphase kernel.
+struct F8 {
+	float4 a, b;
+};
+__device__ __forceinline__ F8 ldg256(const float4 *p) {
+	F8 r;
+	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
+	    : "l"(p));
+	return r;
+}
+
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
 // n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
 __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,
@@ -923,14 +938,15 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 				// the node that stays (fetched once) and the sibling line of the tree that is descended
 				const float4 *op = env_side ? nodes2 + 4ull * i2base : nodes1 + 4ull * pr.x;
 				const float4 *cp = env_side ? nodes1 + 4ull * pr.x : nodes2 + 4ull * i2base;
-				const float4 o0 = __ldg(op), o1 = __ldg(op + 1), o2 = __ldg(op + 2), o3 = __ldg(op + 3);
+				const F8 oA = ldg256(op), oB = ldg256(op + 2);
+				const float4 o0 = oA.a, o1 = oA.b, o2 = oB.a, o3 = oB.b;
 #pragma unroll
 				for (int k = 0; k < 2; ++k) {
 					if (k == 1 && single) break;
 					const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
 					const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
-					const float4 c0 = __ldg(cp + 4 * k), c1 = __ldg(cp + 4 * k + 1), c2 = __ldg(cp + 4 * k + 2),
-					             c3 = __ldg(cp + 4 * k + 3);
+					const F8 cA = ldg256(cp + 4 * k), cB = ldg256(cp + 4 * k + 2);
+					const float4 c0 = cA.a, c1 = cA.b, c2 = cB.a, c3 = cB.b;
 					const float4 a0 = env_side ? c0 : o0, a1 = env_side ? c1 : o1, a2 = env_side ? c2 : o2,
 					             a3 = env_side ? c3 : o3;
 					const float4 b0 = env_side ? o0 : c0, b1 = env_side ? o1 : c1, bb2 = env_side ? o2 : c2,
