@@ -376,14 +376,15 @@ struct RelF {
 struct F8 {
 	float4 a, b;
 };
+#define MPTCC_LD256(HINT)                                                                                       \
+	asm("ld.global.nc" HINT ".v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                                           \
+	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w) \
+	    : "l"(p))
 __device__ __forceinline__ F8 ldg256(const float4 *p) {
 	F8 r;
-	asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-	    : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.a.z), "=f"(r.a.w), "=f"(r.b.x), "=f"(r.b.y), "=f"(r.b.z), "=f"(r.b.w)
-	    : "l"(p));
+	MPTCC_LD256("");
 	return r;
 }
-
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
 // n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
 __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,

@@ -113,7 +113,10 @@ struct KernelParams {
 // index of the counters in KernelParams::counters
 enum { CTR_CAND = 0, CTR_BV = 1, CTR_LEAF = 2, CTR_EXACT = 3, CTR_PATH = 4, CTR_N = 5 };
 
-constexpr int kClusterSize = 8;
+#ifndef MPTCC_CLUSTER
+#define MPTCC_CLUSTER 8
+#endif
+constexpr int kClusterSize = MPTCC_CLUSTER;
 constexpr int kWarpsPerCta = 8;
 constexpr int kLeafQueueCap = 96;   // a node step appends <= 64 pairs; the leaf phase runs at >= 32
 constexpr int kClusterQueueCap = 64;  // (pose, cluster) entries waiting for the exact AABB test
