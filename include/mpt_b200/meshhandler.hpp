@@ -201,21 +201,28 @@ class MeshHandler {
 public:
 	// [P][L] transforms -> pose records.  All transforms of a batch built from matrices / translations use
 	// RT12; all built from quaternions use TQ7; a mixed batch is split by the callers below.
-	static int packPoses(const std::vector<std::vector<fcl::Transform3f> > &poses, size_t links, bool quat,
-	                     std::vector<double> &out) {
-		out.clear();
-		for (const auto &set : poses) {
+	static int packPoses(const std::vector<std::vector<fcl::Transform3f> > &poses, const std::vector<size_t> &index,
+	                     size_t links, bool quat, double *out) {
+		for (size_t i : index) {
+			const std::vector<fcl::Transform3f> &set = poses[i];
 			if (set.size() != links) return -1;
 			for (const auto &tf : set) {
 				if (quat) {
-					const double r[7] = {tf.getTranslation()[0], tf.getTranslation()[1], tf.getTranslation()[2],
-					                     tf.getQuatRotation().getW(), tf.getQuatRotation().getX(),
-					                     tf.getQuatRotation().getY(), tf.getQuatRotation().getZ()};
-					out.insert(out.end(), r, r + 7);
+					const fcl::Quaternion3f &q = tf.getQuatRotation();
+					out[0] = tf.getTranslation()[0];
+					out[1] = tf.getTranslation()[1];
+					out[2] = tf.getTranslation()[2];
+					out[3] = q.getW();
+					out[4] = q.getX();
+					out[5] = q.getY();
+					out[6] = q.getZ();
+					out += 7;
 				} else {
-					out.insert(out.end(), tf.getRotation().data(), tf.getRotation().data() + 9);
-					const double t[3] = {tf.getTranslation()[0], tf.getTranslation()[1], tf.getTranslation()[2]};
-					out.insert(out.end(), t, t + 3);
+					memcpy(out, tf.getRotation().data(), 9 * sizeof(double));
+					out[9] = tf.getTranslation()[0];
+					out[10] = tf.getTranslation()[1];
+					out[11] = tf.getTranslation()[2];
+					out += 12;
 				}
 			}
 		}
@@ -227,33 +234,7 @@ public:
 	static std::vector<bool> collidingPoseSets(const StaticEnvironmentMeshHandler &environment,
 	                                           const std::vector<const SimpleAgentMeshHandler *> &agent,
 	                                           const std::vector<std::vector<fcl::Transform3f> > &poses) {
-		std::vector<bool> verdict(poses.size(), false);
-		if (poses.empty() || agent.empty()) return verdict;
-		mptcc_ctx *ctx = environment.getCollisionChecker(agent);
-		// split by constructor kind (pose-sets whose links mix kinds are not produced by any agent)
-		for (int quat = 0; quat < 2; ++quat) {
-			std::vector<std::vector<fcl::Transform3f> > part;
-			std::vector<size_t> index;
-			for (size_t i = 0; i < poses.size(); ++i) {
-				if (poses[i].empty()) continue;  // no agent objects: never in collision (Blimp::getPoses stub)
-				if ((int)poses[i][0].builtFromQuaternion() == quat) {
-					part.push_back(poses[i]);
-					index.push_back(i);
-				}
-			}
-			if (part.empty()) continue;
-			std::vector<double> rec;
-			if (packPoses(part, agent.size(), quat != 0, rec) != 0) {
-				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
-				exit(1);
-			}
-			std::vector<uint32_t> bits((part.size() + 31) / 32, 0u);
-			environment.check(mptcc_check_poses(ctx, part.size(), rec.data(), quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
-			                                    bits.data()),
-			                  "mptcc_check_poses");
-			for (size_t k = 0; k < part.size(); ++k) verdict[index[k]] = (bits[k >> 5] >> (k & 31)) & 1u;
-		}
-		return verdict;
+		return submitPoseSets(environment, agent, poses)->get();
 	}
 
 	// collidingPoseSets without the wait: the copies and kernels are enqueued (mptcc_submit_poses, pinned
@@ -267,31 +248,25 @@ public:
 		if (poses.empty() || agent.empty()) return out;
 		out->env = &environment;
 		out->ctx = environment.getCollisionChecker(agent);
+		// split by constructor kind (pose-sets whose links mix kinds are not produced by any agent); a pose-set
+		// without transforms has no agent objects and is never in collision (Blimp::getPoses stub)
 		for (int quat = 0; quat < 2; ++quat) {
-			std::vector<std::vector<fcl::Transform3f> > part;
 			PendingVerdicts::Part pt;
-			for (size_t i = 0; i < poses.size(); ++i) {
-				if (poses[i].empty()) continue;
-				if ((int)poses[i][0].builtFromQuaternion() == quat) {
-					part.push_back(poses[i]);
-					pt.index.push_back(i);
-				}
-			}
-			if (part.empty()) continue;
-			std::vector<double> rec;
-			if (packPoses(part, agent.size(), quat != 0, rec) != 0) {
+			for (size_t i = 0; i < poses.size(); ++i)
+				if (!poses[i].empty() && (int)poses[i][0].builtFromQuaternion() == quat) pt.index.push_back(i);
+			if (pt.index.empty()) continue;
+			const size_t n = pt.index.size(), words = (n + 31) / 32;
+			pt.rec = static_cast<double *>(mpt_b200::PinnedPool::take(n * agent.size() * (quat ? 7 : 12) * sizeof(double)));
+			pt.bits = static_cast<uint32_t *>(mpt_b200::PinnedPool::take(words * sizeof(uint32_t)));
+			if (packPoses(poses, pt.index, agent.size(), quat != 0, pt.rec) != 0) {
 				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
 				exit(1);
 			}
-			const size_t words = (part.size() + 31) / 32;
-			pt.rec = static_cast<double *>(mpt_b200::PinnedPool::take(rec.size() * sizeof(double)));
-			pt.bits = static_cast<uint32_t *>(mpt_b200::PinnedPool::take(words * sizeof(uint32_t)));
-			memcpy(pt.rec, rec.data(), rec.size() * sizeof(double));
 			pt.ticket = 0;
 			out->done = false;
 			out->parts.push_back(pt);
-			environment.check(mptcc_submit_poses(out->ctx, part.size(), pt.rec, quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
-			                                     pt.bits, &out->parts.back().ticket),
+			environment.check(mptcc_submit_poses(out->ctx, n, pt.rec, quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12, pt.bits,
+			                                     &out->parts.back().ticket),
 			                  "mptcc_submit_poses");
 		}
 		return out;
