@@ -292,13 +292,13 @@ public:
 	                          const std::vector<const SimpleAgentMeshHandler *> &agent,
 	                          const std::vector<std::vector<fcl::Transform3f> > &poses, bool checkSelfCollision = false,
 	                          bool debug = false) {
-		if (checkSelfCollision) {
-			// no caller in the reference enables it (map3d.hpp:33,36 default false); SURVEY 8f N4
-			fprintf(stderr, "MeshHandler::isInCollision: checkSelfCollision is not implemented on the GPU path\n");
-			exit(1);
-		}
 		(void)debug;  // contact points are not computed (enable_contact = false in the reference as well)
+		// meshhandler.hpp:205-219: the links of every pose-set are also tested against each other
+		const bool self = checkSelfCollision && !agent.empty() && !poses.empty();
+		mptcc_ctx *ctx = self ? environment.getCollisionChecker(agent) : nullptr;
+		if (self) environment.check(mptcc_set_option(ctx, "self_collision", 1), "mptcc_set_option");
 		const std::vector<bool> v = collidingPoseSets(environment, agent, poses);
+		if (self) environment.check(mptcc_set_option(ctx, "self_collision", 0), "mptcc_set_option");
 		for (bool b : v)
 			if (b) return true;
 		return false;

@@ -142,7 +142,12 @@ int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
 /* With option "time_phases" = 1: device milliseconds of the three kernels of the last split-pipeline launch
  * on `slot` (CUDA events on the launching stream): ms3 = {broadphase, narrowphase, overflow fall-back}. */
 int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3);
-/* Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1), "split_min", "split_cap", "always_replay", "time_phases". */
+/* Behaviour: "self_collision" (0/1, default 0) = the checkSelfCollision argument of
+ * MeshHandler::isInCollision (/root/reference/utilities/meshhandler.hpp:187-219): every later check also
+ * tests the links of each pose-set against each other (pairs with overlapping world AABBs, same mesh-mesh
+ * narrowphase) and reports self-collision OR environment collision.
+ * Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1),
+ * "split_min", "split_cap", "always_replay", "time_phases", "near_first", "no_steal", "steal_bottom". */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */

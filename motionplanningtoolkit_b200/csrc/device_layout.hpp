@@ -142,6 +142,9 @@ int collide_max_ctas_per_sm(bool count);
 // split_kernels.cu: broadphase kernel (poses -> candidate list) and narrowphase kernel (candidate list ->
 // verdict bits); single-link agents.
 int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *stream);
+// self_kernel.cu: link-vs-link test of every pose-set (checkSelfCollision); p.env = the agent's pack,
+// p.objects = one DevObject per link.  ORs into verdict_bits.
+int launch_self_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
 int launch_narrowphase(const KernelParams &p, int sm_count, bool count, void *stream);
 
 // edge_kernels.cu

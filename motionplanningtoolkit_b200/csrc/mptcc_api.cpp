@@ -360,6 +360,7 @@ struct Device {
 	DevBuf<double> obj_aabb;
 	DevBuf<uint4> bp_nodes;
 	DevBuf<uint32_t> link_model;
+	DevBuf<DevObject> self_objects;  // one per link (model id only): the "objects" of the self-collision kernel
 	DevBuf<double> poses[kPipe];
 	DevBuf<uint32_t> bits[kPipe];
 	DevBuf<uint32_t> work[kPipe];
@@ -391,6 +392,7 @@ struct mptcc_ctx {
 	std::vector<uint4> bp_nodes_h;
 	float bp_origin[3] = {0.f, 0.f, 0.f}, bp_inv_cell[3] = {1.f, 1.f, 1.f};
 	std::vector<uint32_t> link_model_h;
+	std::vector<DevObject> self_objects_h;
 	bool env_set = false, agent_set = false;
 	std::string err;
 	bool count = false;
@@ -405,6 +407,7 @@ struct mptcc_ctx {
 	long opt_no_steal = 0;
 	long opt_steal_bottom = 0;
 	long opt_near_first = 1;
+	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
 	mptcc_counters ctr{};
 	uint64_t submitted = 0, completed = 0;  // tickets of mptcc_submit_poses
 	int ctas_per_sm_cached = -1;
@@ -470,6 +473,7 @@ int upload_scene_part(mptcc_ctx *ctx, bool env) {
 		} else {
 			CU(d.agent.upload(ctx->agent_h, d.stream[0]));
 			CU(d.link_model.upload(ctx->link_model_h, d.stream[0]));
+			CU(d.self_objects.upload(ctx->self_objects_h, d.stream[0]));
 		}
 		CU(cudaStreamSynchronize(d.stream[0]));
 	}
@@ -485,6 +489,8 @@ int check_ready(mptcc_ctx *ctx) {
 		return fail(ctx, MPTCC_ERR_LIMIT, "BVH deeper than 64 levels is not supported by the exact path replay");
 	if (stack_guard_for(ctx) > (unsigned)kLaneStackCap)
 		return fail(ctx, MPTCC_ERR_LIMIT, "BVH depths exceed the per-lane traversal stack (depth1 + depth2 + 2 <= 64)");
+	if (ctx->opt_self_collision && 2u * ctx->agent_h.max_depth + 2u > (unsigned)kLaneStackCap)
+		return fail(ctx, MPTCC_ERR_LIMIT, "agent BVH too deep for the self-collision traversal (2 * depth + 2 <= 64)");
 	return MPTCC_OK;
 }
 
@@ -534,6 +540,24 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 // Enqueue (memsets +) kernels for n pose-sets already on the device.  Large single-link batches take the
 // split pipeline (broadphase kernel -> candidate list -> narrowphase kernel, then the fused kernel as a
 // conditional overflow fall-back); everything else the fused kernel.
+// checkSelfCollision: after the environment kernels of a launch, OR the link-vs-link verdicts into its words.
+int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, int grid, cudaStream_t s) {
+	if (!ctx->opt_self_collision || ctx->link_model_h.size() < 2) return MPTCC_OK;
+	KernelParams kp = kp_env;
+	kp.env = kp.agent;
+	kp.objects = d.self_objects.p;
+	kp.n_objects = (uint32_t)ctx->link_model_h.size();
+	kp.run_if = nullptr;
+	kp.ppw_log2 = 5;
+	CU(cudaMemsetAsync(kp.work_counter, 0, sizeof(uint32_t), s));
+	const uint64_t need = ((kp.n_pose_sets + 31) / 32 + kWarpsPerCta - 1) / kWarpsPerCta;
+	const int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, need));
+	const int e = launch_self_collide(kp, g, ctx->count, s);
+	if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "self_collide_kernel launch");
+	ctx->ctr.n_kernel_launches++;
+	return MPTCC_OK;
+}
+
 int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
                    uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr) {
 	KernelParams kp;
@@ -584,7 +608,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		if (timed) CU(cudaEventRecord(d.phase_ev[3], s));
 		ctx->ctr.n_kernel_launches += 3;
 		ctx->ctr.n_pose_sets += n;
-		return MPTCC_OK;
+		return enqueue_self(ctx, d, kp, grid, s);
 	}
 	CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 	if (kp.ppw_log2 < 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
@@ -596,7 +620,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel launch");
 	ctx->ctr.n_kernel_launches++;
 	ctx->ctr.n_pose_sets += n;
-	return MPTCC_OK;
+	return enqueue_self(ctx, d, kp, grid, s);
 }
 
 }  // namespace
@@ -655,6 +679,7 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.obj_aabb.release();
 		d.bp_nodes.release();
 		d.link_model.release();
+		d.self_objects.release();
 		d.counters.release();
 		d.work_user.release();
 		for (auto &sb : d.split) sb.release();
@@ -772,6 +797,8 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 		seen[key] = id;
 		ctx->link_model_h.push_back(id);
 	}
+	ctx->self_objects_h.assign(ctx->link_model_h.size(), DevObject{});
+	for (size_t j = 0; j < ctx->link_model_h.size(); ++j) ctx->self_objects_h[j].model = ctx->link_model_h[j];
 	const int rc = upload_scene_part(ctx, false);
 	if (rc != MPTCC_OK) return rc;
 	ctx->agent_set = true;
@@ -1086,6 +1113,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
+	} else if (k == "self_collision") {
+		ctx->opt_self_collision = value != 0;
 	} else if (k == "near_first") {
 		ctx->opt_near_first = value != 0;
 	} else if (k == "steal_bottom") {

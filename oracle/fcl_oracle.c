@@ -1001,14 +1001,57 @@ typedef struct {
 	int fmt;
 	uint64_t begin, end;
 	uint32_t *bits;
+	int check_self;
 	orc_counters ctr;
 } slice_job;
+
+/* checkSelfCollision (/root/reference/utilities/meshhandler.hpp:205-219): the links of ONE pose-set are put
+ * in their own DynamicAABBTreeCollisionManager and collide(cdata, callback) runs selfCollisionRecurse: every
+ * pair of leaves whose AABBs overlap (closed intervals) reaches defaultCollisionFunction until a contact is
+ * found.  The verdict is "some overlapping pair of link meshes collides".
+ * [deviation] Which link of a pair becomes object 1 depends, in FCL, on the tree that
+ * HierarchyTree::topdown_0 builds with std::nth_element, whose partition is unspecified; this restatement
+ * fixes the orientation to (lower link index, higher link index). */
+int orc_self_collision(int n_links, orc_model *const *links, const double *pose_set, int fmt, orc_counters *counters) {
+	orc_counters local;
+	memset(&local, 0, sizeof local);
+	orc_counters *ctr = counters ? counters : &local;
+	if (n_links < 2) return 0;
+	xform *tf = (xform *)malloc(sizeof(xform) * (size_t)n_links);
+	aabb *box = (aabb *)malloc(sizeof(aabb) * (size_t)n_links);
+	const int rl = fmt == ORC_POSE_TQ7 ? 7 : 12;
+	for (int k = 0; k < n_links; ++k) {
+		xform_decode(pose_set + (size_t)rl * (size_t)k, fmt, &tf[k]);
+		compute_local_aabb(links[k]);
+		object_world_aabb(links[k], &tf[k], &box[k]);
+	}
+	int hit = 0;
+	for (int a = 0; a < n_links && !hit; ++a)
+		for (int b = a + 1; b < n_links && !hit; ++b) {
+			ctr->n_aabb_tests++;
+			if (!aabb_overlap(&box[a], &box[b])) continue;
+			trav tv;
+			tv.m1 = links[a];
+			tv.m2 = links[b];
+			tv.num_contacts = 0;
+			tv.ctr = ctr;
+			ctr->n_obj_pairs++;
+			relative_transform(&tf[a], &tf[b], &tv.R, tv.T);
+			collision_recurse(&tv, 0, 0);
+			hit = tv.num_contacts > 0;
+		}
+	free(tf);
+	free(box);
+	return hit;
+}
 
 static void *slice_run(void *arg) {
 	slice_job *j = (slice_job *)arg;
 	const size_t stride = (size_t)rec_len(j->fmt) * (size_t)j->n_links;
 	for (uint64_t p = j->begin; p < j->end; ++p) {
-		int hit = orc_is_in_collision(j->env, j->n_links, j->links, 1, j->poses + stride * p, j->fmt, &j->ctr);
+		/* meshhandler.hpp:205-219: the self-collision of a pose-set is checked first and settles the call */
+		int hit = j->check_self && orc_self_collision(j->n_links, j->links, j->poses + stride * p, j->fmt, &j->ctr);
+		if (!hit) hit = orc_is_in_collision(j->env, j->n_links, j->links, 1, j->poses + stride * p, j->fmt, &j->ctr);
 		if (hit) j->bits[p >> 5] |= (1u << (p & 31));
 	}
 	return NULL;
@@ -1021,8 +1064,23 @@ static orc_model *model_shallow_copy(const orc_model *m) {
 	return c;
 }
 
+static int verdicts_impl(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                         const double *poses, int fmt, uint32_t *verdict_bits, int n_threads, orc_counters *counters,
+                         int check_self);
+
 int orc_verdicts(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
                  const double *poses, int fmt, uint32_t *verdict_bits, int n_threads, orc_counters *counters) {
+	return verdicts_impl(env, n_links, links, n_pose_sets, poses, fmt, verdict_bits, n_threads, counters, 0);
+}
+
+int orc_verdicts_self(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                      const double *poses, int fmt, uint32_t *verdict_bits, int n_threads, orc_counters *counters) {
+	return verdicts_impl(env, n_links, links, n_pose_sets, poses, fmt, verdict_bits, n_threads, counters, 1);
+}
+
+static int verdicts_impl(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                         const double *poses, int fmt, uint32_t *verdict_bits, int n_threads, orc_counters *counters,
+                         int check_self) {
 	size_t n_words = (size_t)((n_pose_sets + 31) / 32);
 	memset(verdict_bits, 0, sizeof(uint32_t) * n_words);
 	if (n_threads < 1) n_threads = 1;
@@ -1039,6 +1097,7 @@ int orc_verdicts(const orc_env *env, int n_links, orc_model *const *links, uint6
 		if (e > n_pose_sets) e = n_pose_sets;
 		jobs[t].env = env; jobs[t].n_links = n_links; jobs[t].links = priv; jobs[t].poses = poses;
 		jobs[t].fmt = fmt; jobs[t].begin = b; jobs[t].end = e; jobs[t].bits = verdict_bits;
+		jobs[t].check_self = check_self;
 	}
 	if (n_threads == 1) {
 		slice_run(&jobs[0]);

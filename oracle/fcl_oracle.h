@@ -73,6 +73,13 @@ int orc_verdicts(const orc_env *env, int n_links, orc_model *const *links, uint6
                  const double *poses, int pose_format, uint32_t *verdict_bits, int n_threads,
                  orc_counters *counters);
 
+/* The same with checkSelfCollision = true (meshhandler.hpp:205-219): bit = the links of the pose-set collide
+ * with each other OR with the environment.  orc_self_collision is the per-pose-set self test alone. */
+int orc_verdicts_self(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                      const double *poses, int pose_format, uint32_t *verdict_bits, int n_threads, orc_counters *counters);
+int orc_self_collision(int n_links, orc_model *const *links, const double *pose_set, int pose_format,
+                       orc_counters *counters);
+
 /* Structure-free second oracle: verdict = exists object, link with overlapping world AABBs and a
  * triangle pair for which Intersect::intersect_Triangle(...,R,T) holds.  No BVH, no OBB tests. */
 int orc_verdicts_bruteforce(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,

@@ -56,6 +56,10 @@ def lib():
         L.orc_verdicts.restype = C.c_int
         L.orc_verdicts.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_uint64, dp, C.c_int, u32p, C.c_int,
                                    C.POINTER(Counters)]
+        L.orc_verdicts_self.restype = C.c_int
+        L.orc_verdicts_self.argtypes = L.orc_verdicts.argtypes
+        L.orc_self_collision.restype = C.c_int
+        L.orc_self_collision.argtypes = [C.c_int, C.POINTER(vp), dp, C.c_int, C.POINTER(Counters)]
         L.orc_verdicts_bruteforce.restype = C.c_int
         L.orc_verdicts_bruteforce.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_uint64, dp, C.c_int, u32p]
         L.orc_obb_overlap.restype = C.c_int
@@ -172,6 +176,23 @@ def verdicts(env, links, poses, fmt=POSE_RT12, n_threads=1, counters=None):
     c = counters if counters is not None else Counters()
     lib().orc_verdicts(env.h, len(links), _links(links), n, _dp(p), fmt, _u32p(bits), n_threads, C.byref(c))
     return bits
+
+
+def verdicts_self(env, links, poses, fmt=POSE_RT12, n_threads=1, counters=None):
+    """verdicts() with checkSelfCollision = true: bit = self-collision of the pose-set OR environment collision."""
+    p, n = _poses(poses, len(links), fmt)
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    c = counters if counters is not None else Counters()
+    lib().orc_verdicts_self(env.h, len(links), _links(links), n, _dp(p), fmt, _u32p(bits), n_threads, C.byref(c))
+    return bits
+
+
+def self_collision(links, pose_set, fmt=POSE_RT12, counters=None):
+    """Do the links of ONE pose-set collide with each other (meshhandler.hpp:205-219)?"""
+    p, n = _poses(pose_set, len(links), fmt)
+    assert n == 1
+    c = counters if counters is not None else Counters()
+    return bool(lib().orc_self_collision(len(links), _links(links), _dp(p), fmt, C.byref(c)))
 
 
 def verdicts_bruteforce(env, links, poses, fmt=POSE_RT12):

@@ -33,6 +33,10 @@ class Scene:
     def oracle_bits(self, poses, fmt=O.POSE_RT12, n_threads=8, counters=None):
         return O.verdicts(self.oenv, self.olinks, poses, fmt, n_threads, counters)
 
+    def oracle_bits_self(self, poses, fmt=O.POSE_RT12, n_threads=8, counters=None):
+        """checkSelfCollision = true: self-collision of the pose-set OR environment collision."""
+        return O.verdicts_self(self.oenv, self.olinks, poses, fmt, n_threads, counters)
+
     def brute_bits(self, poses, fmt=O.POSE_RT12):
         return O.verdicts_bruteforce(self.oenv, self.olinks, poses, fmt)
 

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from helpers import Scene, assert_bits_equal, env_bbox, unit_box
-from motionplanningtoolkit_b200 import meshio, scenes
+from motionplanningtoolkit_b200 import capi, meshio, scenes
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -137,3 +137,65 @@ def test_c5_single_object_terrain(built, opts):
     assert_bits_equal(chk.check_poses(poses), want, n, "terrain %s" % (opts,))
     f = O.unpack_bits(want, n).mean()
     assert 0.1 < f < 0.9, f
+
+
+def _independent_link_poses(rng, n, n_links, lo, hi):
+    """[n, n_links, 12]: every link gets its own random rigid pose (so that some pose-sets self-collide and
+    some do not)."""
+    return np.stack([scenes.random_poses_rt12(rng, n, lo, hi) for _ in range(n_links)], axis=1)
+
+
+def test_self_collision_unit_box_links(built):
+    """checkSelfCollision = true == oracle (self-collision of the pose-set OR environment)."""
+    b = unit_box()
+    sc = Scene([b], [b, b, b, b])
+    rng = scenes.SplitMix64(0x5E1F)
+    poses = _independent_link_poses(rng, 20000, 4, (-2.2,) * 3, (2.2,) * 3)
+    # exact contacts: axis-aligned links one unit apart
+    T = np.zeros((64, 4, 3))
+    T[:, 1, 0] = 1.0
+    T[:, 2, 0] = np.linspace(2.0, 2.0 + 2.0 ** -50, 64)
+    T[:, 3, 1] = np.linspace(0.9, 1.1, 64)
+    T[:, :, 2] += 7.0  # away from the environment box at the origin
+    poses = np.concatenate([poses, scenes.translation_poses(T.reshape(-1, 3)).reshape(64, 4, 12)])
+    n = len(poses)
+    want_self = sc.oracle_bits_self(poses)
+    want_env = sc.oracle_bits(poses)
+    assert O.unpack_bits(want_self, n).sum() > O.unpack_bits(want_env, n).sum() > 0
+    assert not O.unpack_bits(want_self, n).all()
+    chk = sc.checker(self_collision=1)
+    assert_bits_equal(chk.check_poses(poses), want_self, n, "self-collision on")
+    chk.set_option("self_collision", 0)
+    assert_bits_equal(chk.check_poses(poses), want_env, n, "self-collision off")
+    # quaternion records
+    tq = np.stack([scenes.random_poses_tq7(rng, 5000, (-2.0,) * 3, (2.0,) * 3) for _ in range(4)], axis=1)
+    chk.set_option("self_collision", 1)
+    assert_bits_equal(chk.check_poses(tq, capi.POSE_TQ7), sc.oracle_bits_self(tq, O.POSE_TQ7), len(tq), "self TQ7")
+
+
+def test_self_collision_mesh_links_and_snake(built):
+    """Two blimps as links (deep trees, degenerate triangles -> path replay) near the divider; and the
+    reference's snake pose-sets, whose trailers all sit at the same place (always self-colliding)."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    blimp = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [blimp, blimp])
+    rng = scenes.SplitMix64(0x5E20)
+    lo, hi = env_bbox(env, 3.0)
+    base = scenes.random_poses_rt12(rng, 3000, lo, hi)
+    other = scenes.random_poses_rt12(rng, 3000, (-6.0,) * 3, (6.0,) * 3)  # second blimp: random offset from the first
+    second = base.copy()
+    second[:, 9:12] += other[:, 9:12]
+    second[:, 0:9] = other[:, 0:9]
+    poses = np.stack([base, second], axis=1)
+    n = len(poses)
+    want = sc.oracle_bits_self(poses)
+    frac = O.unpack_bits(want, n).mean()
+    assert 0.1 < frac < 0.9, frac
+    for opts in (dict(self_collision=1), dict(self_collision=1, always_replay=1)):
+        assert_bits_equal(sc.checker(**opts).check_poses(poses), want, n, "blimp pair %s" % (opts,))
+    b = unit_box()
+    snake = Scene([b], [b] * 11, env_pose7=(-100.0, 0, 0, 1, 0, 0, 0))
+    sp = scenes.snake_state_poses(scenes.snake_random_states(rng, 2000, (-4, -4), (4, 4)))
+    want = snake.oracle_bits_self(sp)
+    assert O.unpack_bits(want, 2000).all()
+    assert_bits_equal(snake.checker(self_collision=1).check_poses(sp), want, 2000, "snake self")

@@ -54,3 +54,15 @@ def test_prm_roadmap_batched_equals_sequential(built, tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     assert "identical roadmaps: yes" in r.stdout
     print(r.stdout)
+
+
+def test_is_in_collision_with_self_collision_flag(built, tmp_path):
+    """SURVEY 8f N4 through the reference's own signature: isInCollision(env, agent, poses, checkSelfCollision)."""
+    exe = str(tmp_path / "self_collision_check")
+    libdir = os.path.join(ROOT, "motionplanningtoolkit_b200")
+    subprocess.check_call(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "self_collision_check.cpp"), "-o", exe,
+                           "-L", libdir, "-lmptcc", "-Wl,-rpath," + libdir])
+    r = subprocess.run([exe, os.path.join(meshio.DATA_DIR, "unit_box.mptm")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.split() == ["apart", "0", "0", "touching", "0", "1", "overlapping", "0", "1", "just_apart", "0", "0"]

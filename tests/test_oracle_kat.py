@@ -145,3 +145,28 @@ def test_golden_vectors(built, path):
     bits = sc.oracle_bits(g["poses"], int(g["fmt"]), counters=ctr)
     assert np.array_equal(bits, g["bits"])
     assert ctr.n_bv_tests == int(g["n_bv_tests"]) and ctr.n_leaf_tests == int(g["n_leaf_tests"])
+
+
+def test_self_collision_known_answers():
+    """checkSelfCollision (meshhandler.hpp:205-219): unit cubes as links; closed-interval contact counts."""
+    b = unit_box()
+    m = O.Model(*b)
+    links = [m, m, m]
+    env = O.Environment([m], (100.0, 0, 0, 1, 0, 0, 0))  # far away: only the self test can fire
+
+    def case(T):
+        return scenes.translation_poses(np.array(T, float)).reshape(1, 3, 12)
+
+    touching = case([[0, 0, 0], [1.0, 0, 0], [2.5, 0, 0]])      # links 0-1 share a face
+    apart = case([[0, 0, 0], [1.5, 0, 0], [3.0, 0, 0]])
+    last_two = case([[0, 0, 0], [1.5, 0, 0], [2.4, 0.3, 0]])    # only links 1-2 overlap
+    assert O.self_collision(links, touching) and not O.self_collision(links, apart) and O.self_collision(links, last_two)
+    batch = np.concatenate([touching, apart, last_two, apart])
+    assert list(O.unpack_bits(O.verdicts_self(env, links, batch), 4)) == [True, False, True, False]
+    assert not O.unpack_bits(O.verdicts(env, links, batch), 4).any()
+    # a single-link agent has nothing to collide with
+    assert not O.self_collision([m], scenes.translation_poses(np.zeros((1, 3))).reshape(1, 1, 12))
+    # environment collision OR self-collision
+    env2 = O.Environment([m], (3.0, 0, 0, 1, 0, 0, 0))           # touches link 2 of `apart` (x = 3.0)
+    assert list(O.unpack_bits(O.verdicts_self(env2, links, batch), 4)) == [True, True, True, True]
+    assert list(O.unpack_bits(O.verdicts(env2, links, batch), 4)) == [True, True, True, True]
