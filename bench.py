@@ -189,6 +189,18 @@ def run_ours(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
+    # N > 1: run this rank (and first-touch its pinned staging buffers) on the CPUs next to its GPU, so that
+    # eight ranks do not pull their host buffers across the socket interconnect
+    cpus_before = os.sched_getaffinity(0)
+    numa_bound = False
+    if world > 1:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+            numa_bound = os.sched_getaffinity(0) != cpus_before
+        except Exception:
+            numa_bound = False
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -294,7 +306,8 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32 traversal + f64 exact re-decide", "data": "synthetic", "config": workload_config(world, per_gpu),
+        "dtype": "f32 traversal + f64 exact re-decide", "data": "synthetic",
+        "config": dict(workload_config(world, per_gpu), host_cpu_affinity="gpu-local (NVML)" if numa_bound else "unbound"),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": per_gpu * 96 * world,
                 "d2h_bytes_per_step": n_words * 4 * world, "ms_per_step": 1e3 * e2e_s / args.steps},
         "e2e_pipelined": {"value": total_poses / pipe_s, "unit": UNIT, "calls_in_flight": 2,
@@ -306,6 +319,7 @@ def run_ours(args):
 
     if rank == 0:
         # ---- parity on a sample + CPU baseline + roofline (rank 0, N = 1 only for the CPU timing) -----
+        os.sched_setaffinity(0, cpus_before)          # the CPU oracle may use every host core again
         threads = os.cpu_count() or 1
         sample_poses = host_poses[0].array            # whole batch 0 if the budget allows (about 2 s at 0.5 M poses/s)
         budget = 15.0 if world == 1 else 4.0
