@@ -385,6 +385,34 @@ __device__ __forceinline__ F8 ldg256(const float4 *p) {
 	MPTCC_LD256("");
 	return r;
 }
+__device__ __forceinline__ void stg256(float4 *p, const float4 a, const float4 b) {
+	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
+	             "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+	             : "memory");
+}
+__device__ __forceinline__ void stg256(double *p, double a, double b, double c, double d) {
+	asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+// A pose record (12 doubles RT12 / 7 doubles TQ7) into registers; 32-byte aligned RT12 records (96 B) take
+// three 256-bit loads instead of twelve 64-bit ones.
+__device__ __forceinline__ void load_pose_record(const double *rec, uint32_t fmt, bool aligned32, double *out) {
+	if (fmt == 0u && aligned32) {
+#pragma unroll
+		for (int k = 0; k < 3; ++k)
+			asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+			    : "=d"(out[4 * k]), "=d"(out[4 * k + 1]), "=d"(out[4 * k + 2]), "=d"(out[4 * k + 3])
+			    : "l"(rec + 4 * k));
+	} else if (fmt == 0u) {
+#pragma unroll
+		for (int k = 0; k < 12; ++k) out[k] = rec[k];
+	} else {
+#pragma unroll
+		for (int k = 0; k < 7; ++k) out[k] = rec[k];
+#pragma unroll
+		for (int k = 7; k < 12; ++k) out[k] = 0.0;
+	}
+}
+
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
 // n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
 __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,

@@ -50,6 +50,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
 	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const bool aligned32 = (reinterpret_cast<unsigned long long>(p.poses) & 31ull) == 0ull;
 	const unsigned lt = (1u << lane) - 1u;
 	const DevModel &m2 = p.agent.models[p.link_model[0]];
 	unsigned long long n_cand_total = 0;
@@ -67,7 +68,11 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 
 		// ---- phase A ------------------------------------------------------------------------------------
 		float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
-		if (valid) pose_world_box(chunk_poses + (size_t)lane * rec_len, p.pose_format, m2, wm.box + lane, amin, amax);
+		if (valid) {
+			double rec[12];
+			load_pose_record(chunk_poses + (size_t)lane * rec_len, p.pose_format, aligned32, rec);
+			pose_world_box(rec, p.pose_format, m2, wm.box + lane, amin, amax);
+		}
 		int qmin[3], qmax[3];
 		quantize_pose_box(p, amin, amax, qmin, qmax);
 		__syncwarp();
@@ -149,12 +154,16 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 							for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
 							const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
 							float4 rec[4];
-							make_candidate_record(p, chunk_poses + (size_t)sl * rec_len, p.objects[e], m2, 0u, rec, p.cand_rel + 12ull * dst);
+							double pose[12], rel[12];
+							load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
+							make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
 							float4 *out = p.cand_rec + 4ull * dst;
-							out[0] = rec[0];
-							out[1] = rec[1];
-							out[2] = rec[2];
-							out[3] = rec[3];
+							stg256(out, rec[0], rec[1]);
+							stg256(out + 2, rec[2], rec[3]);
+							double *orel = p.cand_rel + 12ull * dst;
+							stg256(orel, rel[0], rel[1], rel[2], rel[3]);
+							stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
+							stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
 							p.cand_obj[dst] = e;
 							p.cand_pose[dst] = (uint32_t)(pose0 + sl);
 						}
