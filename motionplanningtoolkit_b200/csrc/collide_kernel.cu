@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 	const unsigned ppw = 1u << p.ppw_log2;
 	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
 	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const bool aligned32 = (reinterpret_cast<unsigned long long>(p.poses) & 31ull) == 0ull;
 	const unsigned lt = (1u << lane) - 1u;
 	unsigned long long ctr[CTR_N];
 #pragma unroll
@@ -62,8 +63,11 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 				const bool valid = slot < nvalid;
 				// ---- phase A: lane-per-pose decode + world AABB (CollisionObject::computeAABB) -------
 				float amin[3] = {0.f, 0.f, 0.f}, amax[3] = {0.f, 0.f, 0.f};
-				if (valid)
-					pose_world_box(link_poses + (size_t)slot * rec_len * p.n_links, p.pose_format, m2, wm.box + lane, amin, amax);
+				if (valid) {
+					double rec[12];
+					load_pose_record(link_poses + (size_t)slot * rec_len * p.n_links, p.pose_format, aligned32, rec);
+					pose_world_box(rec, p.pose_format, m2, wm.box + lane, amin, amax);
+				}
 				int qmin[3], qmax[3];
 				quantize_pose_box(p, amin, amax, qmin, qmax);
 				__syncwarp();
@@ -130,7 +134,9 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 							const uint32_t id = wm.cand_ids[i];
 							const unsigned src = id >> 26, e = id & 0x3ffffffu;
 							float4 rec[4];
-							make_candidate_record(p, link_poses + (size_t)src * rec_len * p.n_links, p.objects[e], m2, src, rec);
+							double pose[12];
+							load_pose_record(link_poses + (size_t)src * rec_len * p.n_links, p.pose_format, aligned32, pose);
+							make_candidate_record(p, pose, p.objects[e], m2, src, rec);
 #pragma unroll
 							for (unsigned k = 0; k < 4; ++k) wm.cand[rec_at((unsigned)i, k)] = rec[k];
 						}
