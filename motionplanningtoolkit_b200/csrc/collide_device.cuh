@@ -1,4 +1,5 @@
-// collide_device.cuh -- device code shared by the kernels of libmptcc (collide_kernel.cu, split_kernels.cu): batched agent-mesh vs environment-mesh collision.
+// collide_device.cuh -- device code shared by the kernels of libmptcc (collide_kernel.cu, split_kernels.cu,
+// self_kernel.cu): batched agent-mesh vs environment-mesh collision.
 //
 // Replaces, per pose-set, one MeshHandler::isInCollision (/root/reference/utilities/meshhandler.hpp:187-243):
 //   broadphase  : world-AABB overlap of every (environment object, agent link) pair, fp64, the exact
@@ -9,10 +10,15 @@
 //                 positive pair additionally replays FCL's own root-to-leaf sequence of fp64 OBB tests
 //                 [FCL-recalled C.7-C.9], so the verdict bit equals FCL's.
 //
-// Mapping: one warp owns `ppw` consecutive pose-sets (persistent warps, dynamic fetch).  Phase 1 is
-// lane-per-pose (pose decode, AABB broadphase); phase 2 is warp-per-candidate: the 32 lanes pop up to
-// 32 node pairs from a shared-memory stack, test them, and push the children of the survivors.
-// Leaf pairs are queued and tested 32 at a time.  First contact ends the pose-set.
+// Mapping.  Broadphase phases are lane-per-pose (pose decode, world AABB, stackless walk of the cluster tree)
+// and lane-per-(pose, object) (exact AABB::overlap); they produce candidates (pose-set, object) with a
+// 64-byte fp32 record of the relative transform.  The narrowphase (traverse_all) gives every lane its own
+// candidate and its own depth-first stack (local memory); idle lanes take the next unstarted candidate or
+// steal a pending sub-tree from a busy lane, warp-synchronously.  Leaf pairs are queued and tested 32 at a
+// time.  First contact ends the pose-set.  The same code runs in the fused kernel (collide_kernel.cu: a warp
+// owns `ppw` consecutive pose-sets), in the two kernels of the split pipeline (split_kernels.cu) and in the
+// link-vs-link kernel (self_kernel.cu); a small policy type (FusedTrav / SplitTrav / SelfTrav) says where hits
+// are recorded and where the exact pass finds a candidate's poses.
 //
 // Error bounds of the fp32 pass are derived in DESIGN.md ("fp32 filter bounds").
 #pragma once

@@ -3,8 +3,8 @@
 //   broadphase_kernel  : phases A-C2 of collide_device.cuh for chunks of 32 pose-sets.  It has no traversal
 //                        state, so it runs at a much higher occupancy than the fused kernel and hides the
 //                        latency of its dependent loads (pose records, tree walk, object boxes) with warps.
-//                        Output: a global list of candidates (pose-set, environment object, fp32 record),
-//                        the candidates of one pose-set adjacent.
+//                        Output: a global list of candidates (pose-set, environment object, fp32 record, fp64
+//                        relative transform), the candidates of one pose-set adjacent.
 //   narrowphase_kernel : persistent warps take batches of kCandCap candidates from that list, whatever
 //                        pose-sets they belong to, and run the depth-first lane traversal (traverse_all) on
 //                        them: no chunk boundaries, always a full table, perfect load balance.  Hits are
@@ -20,12 +20,12 @@ namespace {
 
 constexpr int kBpWarpsPerCta = 8;
 
-// per-warp shared memory of the broadphase kernel: pose boxes + cluster queue + candidate ids
 #ifndef MPTCC_NP_BATCH
 #define MPTCC_NP_BATCH MPTCC_CAND_CAP
 #endif
 constexpr int kNpBatch = MPTCC_NP_BATCH;  // candidates a narrowphase warp traverses together
 
+// per-warp shared memory of the broadphase kernel: pose boxes + cluster queue + candidate ids
 __host__ __device__ constexpr unsigned bp_warp_smem_bytes() { return 6u * 32u * 8u + kClusterQueueCap * 4u + kCandCap * 4u + 32u * 4u; }
 
 // per-warp shared memory of the narrowphase kernel
