@@ -291,3 +291,24 @@ def test_submit_wait_matches_synchronous_calls(box_scene):
     with pytest.raises(capi.MptccError):
         chk.wait(tickets[-1] + 100)  # never issued
     assert chk.submit_poses(np.zeros(0), np.zeros(0, np.uint32)) == tickets[-1] + 7  # empty: nothing new to wait for
+
+
+@pytest.mark.parametrize("n", [1000, 40000])
+@pytest.mark.parametrize("offset_doubles", [0, 1, 3])
+def test_device_resident_buffers_any_alignment(box_scene, n, offset_doubles):
+    """mptcc_check_poses_device: poses already in HBM, on the caller's stream; the 256-bit record loads are only
+    taken for 32-byte aligned buffers, every other alignment goes through the scalar loads."""
+    import torch
+    rng = scenes.SplitMix64(94 + offset_doubles)
+    poses = scenes.random_poses_rt12(rng, n, (-1.6,) * 3, (1.6,) * 3)
+    want = box_scene.oracle_bits(poses)
+    chk = box_scene.checker(split_min=32768)
+    buf = torch.zeros(poses.size + 8, dtype=torch.float64, device="cuda")
+    buf[offset_doubles:offset_doubles + poses.size] = torch.from_numpy(poses.ravel()).cuda()
+    bits = torch.zeros((n + 31) // 32, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        chk.check_poses_device(n, buf.data_ptr() + 8 * offset_doubles, bits.data_ptr(), capi.POSE_RT12, 0, stream.cuda_stream)
+    stream.synchronize()
+    got = bits.cpu().numpy().view(np.uint32)
+    assert_bits_equal(got, want, n, "device buffers, offset %d doubles" % offset_doubles)
