@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 	wm.clq = reinterpret_cast<uint32_t *>(base);
 	base += kClusterQueueCap * 4;
 	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
-	base += kNpBatch * 4;
+	base += kCandCap * 4;
 	unsigned *pfx = reinterpret_cast<unsigned *>(base);  // [32] first list position of each pose slot's run
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 			// ---- phase C1 ---------------------------------------------------------------------------------
 			constexpr int kPer = 32 / kClusterSize;
 			int c = 0;
-			for (; c < ncl && ncand <= kNpBatch - 32; c += kPer) {
+			for (; c < ncl && ncand <= kCandCap - 32; c += kPer) {
 				const int idx = c + lane / kClusterSize;
 				bool ov = false;
 				unsigned sl = 0, eobj = 0;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 			}
 			__syncwarp();
 			// ---- flush: group by pose slot, phase C2, append to the global candidate list --------------------
-			if (ncand > kNpBatch - 32 || (!more && ncl == 0)) {
+			if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
 				if (ncand > 0) {
 					// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
 					int mine = 0;
