@@ -150,3 +150,14 @@ def test_cpp_mesh_loaders_match_the_python_converter(built, tmp_path):
     out = str(tmp_path / "rt.mptm")
     subprocess.check_call([exe, os.path.join(meshio.DATA_DIR, "blimp.mptm"), out], stdout=subprocess.DEVNULL)
     assert open(out, "rb").read() == open(os.path.join(meshio.DATA_DIR, "blimp.mptm"), "rb").read()
+
+
+@pytest.mark.parametrize("example", ["omnidirectional_demo", "prm_roadmap", "self_collision_check", "mesh_convert"])
+def test_examples_compile_as_cxx11_against_the_shim(built, example, tmp_path):
+    """The drop-in headers are C++11 like the reference (CMakeLists.txt: -std=c++11) and link against libmptcc only."""
+    libdir = os.path.join(ROOT, "motionplanningtoolkit_b200")
+    exe = str(tmp_path / example)
+    r = subprocess.run(["g++", "-std=c++11", "-Wall", "-Wextra", "-Werror", "-O1", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", example + ".cpp"), "-o", exe, "-L", libdir, "-lmptcc",
+                        "-Wl,-rpath," + libdir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
