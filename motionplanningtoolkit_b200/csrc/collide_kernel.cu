@@ -2,6 +2,7 @@
 // one warp (see collide_device.cuh for the algorithm).  Used for small batches, multi-link agents and as the
 // overflow fall-back of the split pipeline (split_kernels.cu).
 #include "collide_device.cuh"
+#include "launch_cache.hpp"
 
 namespace mptcc {
 namespace {
@@ -178,15 +179,8 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 int collide_max_ctas_per_sm(bool count) {
 	int n = 0;
 	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes();
-	cudaError_t e;
-	if (count) {
-		cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, collide_kernel<true>, kWarpsPerCta * 32, smem);
-	} else {
-		cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, collide_kernel<false>, kWarpsPerCta * 32, smem);
-	}
-	if (e != cudaSuccess) {
+	const void *k = count ? reinterpret_cast<const void *>(collide_kernel<true>) : reinterpret_cast<const void *>(collide_kernel<false>);
+	if (prepare_kernel(k, kWarpsPerCta * 32, smem, &n) != cudaSuccess) {
 		cudaGetLastError();
 		return 0;
 	}
@@ -196,16 +190,13 @@ int collide_max_ctas_per_sm(bool count) {
 int launch_collide(const KernelParams &p, int grid_ctas, bool count, void *stream) {
 	const size_t smem = (size_t)kWarpsPerCta * warp_smem_bytes();
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaError_t e;
-	if (count) {
-		e = cudaFuncSetAttribute(collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
+	const void *k = count ? reinterpret_cast<const void *>(collide_kernel<true>) : reinterpret_cast<const void *>(collide_kernel<false>);
+	const cudaError_t e = prepare_kernel(k, kWarpsPerCta * 32, smem, nullptr);
+	if (e != cudaSuccess) return (int)e;
+	if (count)
 		collide_kernel<true><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
-	} else {
-		e = cudaFuncSetAttribute(collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
+	else
 		collide_kernel<false><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
-	}
 	return (int)cudaGetLastError();
 }
 

@@ -9,6 +9,7 @@
 // Pair orientation: FCL's depends on the unspecified partition of std::nth_element inside its tree build; this
 // path (and the oracle) use (lower link index, higher link index).
 #include "collide_device.cuh"
+#include "launch_cache.hpp"
 
 namespace mptcc {
 namespace {
@@ -166,16 +167,14 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) self_collide_kernel(cons
 int launch_self_collide(const KernelParams &p, int grid_ctas, bool count, void *stream) {
 	const size_t smem = (size_t)kWarpsPerCta * self_warp_smem_bytes();
 	cudaStream_t s = static_cast<cudaStream_t>(stream);
-	cudaError_t e;
-	if (count) {
-		e = cudaFuncSetAttribute(self_collide_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
+	const void *k = count ? reinterpret_cast<const void *>(self_collide_kernel<true>)
+	                      : reinterpret_cast<const void *>(self_collide_kernel<false>);
+	const cudaError_t e = prepare_kernel(k, kWarpsPerCta * 32, smem, nullptr);
+	if (e != cudaSuccess) return (int)e;
+	if (count)
 		self_collide_kernel<true><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
-	} else {
-		e = cudaFuncSetAttribute(self_collide_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		if (e != cudaSuccess) return (int)e;
+	else
 		self_collide_kernel<false><<<grid_ctas, kWarpsPerCta * 32, smem, s>>>(p);
-	}
 	return (int)cudaGetLastError();
 }
 

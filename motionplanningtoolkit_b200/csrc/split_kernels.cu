@@ -14,6 +14,7 @@
 // is launched right after with run_if = overflow, recomputes the launch (verdict bits only ever get set for
 // colliding pose-sets, so OR-ing both results is exact).
 #include "collide_device.cuh"
+#include "launch_cache.hpp"
 
 namespace mptcc {
 namespace {
@@ -271,14 +272,8 @@ __global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParam
 
 template <class K>
 int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads, size_t smem, void *stream) {
-	cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-	if (e != cudaSuccess) return (int)e;
-#ifdef MPTCC_CARVEOUT
-	e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, MPTCC_CARVEOUT);
-	if (e != cudaSuccess) return (int)e;
-#endif
 	int per_sm = 0;
-	e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
+	const cudaError_t e = prepare_kernel(reinterpret_cast<const void *>(kernel), threads, smem, &per_sm);
 	if (e != cudaSuccess) return (int)e;
 	if (per_sm < 1) per_sm = 1;
 	kernel<<<sm_count * per_sm, threads, smem, static_cast<cudaStream_t>(stream)>>>(p);
