@@ -199,3 +199,41 @@ def test_self_collision_mesh_links_and_snake(built):
     want = snake.oracle_bits_self(sp)
     assert O.unpack_bits(want, 2000).all()
     assert_bits_equal(snake.checker(self_collision=1).check_poses(sp), want, 2000, "snake self")
+
+
+def test_c5_full_size_properties(built):
+    """BASELINE C5 at its full size (2000 objects / 1.14 M triangles, 2^20 pose-sets): size-independent properties
+    of the verdict function, plus the oracle on a sample.
+      * the two-kernel pipeline, the fused kernel and the forced path replay give the same words;
+      * a verdict depends on its own pose-set only: permuting the batch permutes the bits, and checking the
+        batch in two halves (different sub-batch cuts, different warps) gives the same bits;
+      * the oracle agrees on every 53rd pose-set."""
+    env = scenes.synthetic_environment(2000)
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    n = 1 << 20
+    rng = scenes.SplitMix64(0x5EED0005)
+    lo, hi = env_bbox(env)
+    n_near = (n * 2) // 5
+    poses = np.concatenate([scenes.random_poses_rt12(rng, n - n_near, lo, hi),
+                            scenes.random_poses_near_objects(rng, n_near, env, 3.0)])
+    chk = sc.checker()
+    split = chk.check_poses(poses)
+    bits = O.unpack_bits(split, n)
+    assert 0.2 < bits.mean() < 0.5
+    chk.set_option("split", 0)
+    assert np.array_equal(chk.check_poses(poses), split), "fused kernel != split pipeline"
+    chk.set_option("split", 1)
+    chk.set_option("always_replay", 1)
+    assert np.array_equal(chk.check_poses(poses), split), "path certificate != full replay"
+    chk.set_option("always_replay", 0)
+    perm = np.argsort(rng.uniform(n, 0.0, 1.0), kind="stable")
+    assert np.array_equal(O.unpack_bits(chk.check_poses(poses[perm]), n), bits[perm]), "not permutation-equivariant"
+    cut = 419_431  # not a multiple of 32: the halves start on different word / warp boundaries
+    two = np.concatenate([O.unpack_bits(chk.check_poses(poses[:cut]), cut),
+                          O.unpack_bits(chk.check_poses(poses[cut:]), n - cut)])
+    assert np.array_equal(two, bits), "verdicts depend on the batch cut"
+    sample = np.arange(0, n, 53)
+    want = O.unpack_bits(sc.oracle_bits(poses[sample], n_threads=16), len(sample))
+    assert np.array_equal(bits[sample], want), "%d of %d sampled verdicts differ from the oracle" % (
+        int((bits[sample] != want).sum()), len(sample))
