@@ -333,6 +333,7 @@ struct DevPack {
 };
 
 constexpr int kPipe = 2;      // ping-pong staging sets per device
+constexpr size_t kSmallBytes = 64 << 10;  // pose bytes up to which a blocking call takes the zero-copy path
 constexpr int kInFlight = 4;  // mptcc_submit_poses calls that may be outstanding before submit waits for the oldest
 
 // Buffers of the split pipeline (split_kernels.cu) for one launch slot; grow-only.
@@ -376,6 +377,9 @@ struct Device {
 	DevBuf<unsigned char> edge_safe;
 	DevBuf<uint32_t> edge_work;
 	float last_ms = 0.f;
+	// planner-sized calls: poses / verdict words in pinned host memory the kernel reads and writes in place
+	double *small_in = nullptr;
+	uint32_t *small_out = nullptr;
 	// per outstanding submit: completion events of the two streams, overflow flags read back (pinned)
 	cudaEvent_t done[kInFlight][kPipe] = {};
 	unsigned int *ctl_h[kInFlight] = {};
@@ -559,7 +563,7 @@ int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, int grid
 }
 
 int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
-                   uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr) {
+                   uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr, bool whole_words = false) {
 	KernelParams kp;
 	fill_params(ctx, d, kp);
 	const int grid = grid_for(ctx, d);
@@ -568,7 +572,8 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	kp.n_pose_sets = n;
 	kp.verdict_bits = d_bits;
 	kp.work_counter = d_work;
-	kp.ppw_log2 = pick_ppw_log2(ctx, n, grid);
+	// whole_words: every warp owns complete verdict words and writes them with plain stores (no zeroing, no atomics)
+	kp.ppw_log2 = whole_words ? 5u : pick_ppw_log2(ctx, n, grid);
 	const bool split = sb != nullptr && ctx->opt_split && ctx->link_model_h.size() == 1 && n >= (uint64_t)ctx->opt_split_min &&
 	                   n < (1ull << 32) && !ctx->objects_h.empty();
 	if (split) {
@@ -659,6 +664,9 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 			if (cudaMallocHost(reinterpret_cast<void **>(&d.ctl_h[t]), sizeof(unsigned int) * 4 * kPipe) != cudaSuccess)
 				return MPTCC_ERR_CUDA;
 		}
+		if (cudaHostAlloc(reinterpret_cast<void **>(&d.small_in), kSmallBytes, cudaHostAllocMapped) != cudaSuccess ||
+		    cudaHostAlloc(reinterpret_cast<void **>(&d.small_out), kSmallBytes / 56 / 8 + 64, cudaHostAllocMapped) != cudaSuccess)
+			return MPTCC_ERR_CUDA;
 		if (d.work_user.reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (d.counters.reserve(CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
@@ -691,6 +699,8 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.edge_bits.release();
 		d.edge_safe.release();
 		d.edge_work.release();
+		if (d.small_in) cudaFreeHost(d.small_in);
+		if (d.small_out) cudaFreeHost(d.small_out);
 		for (int t = 0; t < kInFlight; ++t) {
 			for (int k = 0; k < kPipe; ++k)
 				if (d.done[t][k]) cudaEventDestroy(d.done[t][k]);
@@ -835,6 +845,24 @@ int mptcc_wait(mptcc_ctx *ctx, uint64_t ticket) {
 }
 
 int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, uint32_t *verdict_bits) {
+	// Planner-sized calls (one edge, a few hundred pose-sets): no copies are enqueued at all -- the poses are put in
+	// pinned host memory the fused kernel reads in place, the verdict words are stored straight into pinned
+	// memory, and the only CUDA calls are one 4-byte memset, the launch and the synchronise.
+	if (ctx && n > 0 && poses && verdict_bits && (fmt == MPTCC_POSE_RT12 || fmt == MPTCC_POSE_TQ7) &&
+	    ctx->submitted == ctx->completed && ctx->opt_ppw == 0 && !ctx->opt_self_collision && !ctx->devs.empty()) {
+		const size_t bytes = n * (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size() * sizeof(double);
+		if (bytes <= kSmallBytes && check_ready(ctx) == MPTCC_OK) {
+			Device &d = ctx->devs[0];
+			CU(cudaSetDevice(d.id));
+			std::memcpy(d.small_in, poses, bytes);
+			const int rc = enqueue_kernel(ctx, d, n, d.small_in, fmt, d.small_out, d.work[0].p, d.stream[0], nullptr, true);
+			if (rc != MPTCC_OK) return rc;
+			CU(cudaStreamSynchronize(d.stream[0]));
+			std::memcpy(verdict_bits, d.small_out, sizeof(uint32_t) * ((n + 31) / 32));
+			d.last_ms = 0.f;
+			return MPTCC_OK;
+		}
+	}
 	uint64_t ticket = 0;
 	const int rc = mptcc_submit_poses(ctx, n, poses, fmt, verdict_bits, &ticket);
 	if (rc != MPTCC_OK) return rc;

@@ -25,4 +25,13 @@ for n in (1, 10, 100, 1000, 10000):
     for _ in range(calls):
         chk.check_poses(poses, out=out)
     dt = (time.perf_counter() - t0) / calls
-    print("n=%6d pose-sets per call: %8.1f us per call  (%.2f us per pose-set)" % (n, dt * 1e6, dt * 1e6 / n))
+    pp, pb = capi.PinnedArray(poses.shape, np.float64), capi.PinnedArray(out.shape, np.uint32)
+    pp.array[...] = poses
+    for _ in range(50):
+        chk.check_poses(pp.array, out=pb.array)
+    t0 = time.perf_counter()
+    for _ in range(calls):
+        chk.check_poses(pp.array, out=pb.array)
+    dtp = (time.perf_counter() - t0) / calls
+    print("n=%6d pose-sets per call: %8.1f us per call pageable, %8.1f us pinned  (%.2f us per pose-set)"
+          % (n, dt * 1e6, dtp * 1e6, dt * 1e6 / n))
