@@ -234,7 +234,36 @@ public:
 	static std::vector<bool> collidingPoseSets(const StaticEnvironmentMeshHandler &environment,
 	                                           const std::vector<const SimpleAgentMeshHandler *> &agent,
 	                                           const std::vector<std::vector<fcl::Transform3f> > &poses) {
+		// one edge or so: the blocking C call has a copy-free path for up to 64 KB of poses
+		if (!poses.empty() && !agent.empty() && poses.size() * agent.size() * 12 * sizeof(double) <= (64u << 10))
+			return collidingPoseSetsBlocking(environment, agent, poses);
 		return submitPoseSets(environment, agent, poses)->get();
+	}
+
+	static std::vector<bool> collidingPoseSetsBlocking(const StaticEnvironmentMeshHandler &environment,
+	                                                   const std::vector<const SimpleAgentMeshHandler *> &agent,
+	                                                   const std::vector<std::vector<fcl::Transform3f> > &poses) {
+		std::vector<bool> verdict(poses.size(), false);
+		mptcc_ctx *ctx = environment.getCollisionChecker(agent);
+		std::vector<double> rec;
+		std::vector<uint32_t> bits;
+		for (int quat = 0; quat < 2; ++quat) {
+			std::vector<size_t> index;
+			for (size_t i = 0; i < poses.size(); ++i)
+				if (!poses[i].empty() && (int)poses[i][0].builtFromQuaternion() == quat) index.push_back(i);
+			if (index.empty()) continue;
+			rec.resize(index.size() * agent.size() * (quat ? 7 : 12));
+			bits.assign((index.size() + 31) / 32, 0u);
+			if (packPoses(poses, index, agent.size(), quat != 0, rec.data()) != 0) {
+				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
+				exit(1);
+			}
+			environment.check(mptcc_check_poses(ctx, index.size(), rec.data(), quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
+			                                    bits.data()),
+			                  "mptcc_check_poses");
+			for (size_t k = 0; k < index.size(); ++k) verdict[index[k]] = (bits[k >> 5] >> (k & 31)) & 1u;
+		}
+		return verdict;
 	}
 
 	// collidingPoseSets without the wait: the copies and kernels are enqueued (mptcc_submit_poses, pinned
