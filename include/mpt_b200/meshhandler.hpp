@@ -234,8 +234,8 @@ public:
 	static std::vector<bool> collidingPoseSets(const StaticEnvironmentMeshHandler &environment,
 	                                           const std::vector<const SimpleAgentMeshHandler *> &agent,
 	                                           const std::vector<std::vector<fcl::Transform3f> > &poses) {
-		// one edge or so: the blocking C call has a copy-free path for up to 64 KB of poses
-		if (!poses.empty() && !agent.empty() && poses.size() * agent.size() * 12 * sizeof(double) <= (64u << 10))
+		// one edge or so: the blocking C call has a copy-free path for up to 256 KB of poses
+		if (!poses.empty() && !agent.empty() && poses.size() * agent.size() * 12 * sizeof(double) <= (256u << 10))
 			return collidingPoseSetsBlocking(environment, agent, poses);
 		return submitPoseSets(environment, agent, poses)->get();
 	}

@@ -333,7 +333,7 @@ struct DevPack {
 };
 
 constexpr int kPipe = 2;      // ping-pong staging sets per device
-constexpr size_t kSmallBytes = 64 << 10;  // pose bytes up to which a blocking call takes the zero-copy path
+constexpr size_t kSmallBytes = 256 << 10;  // pose bytes up to which a blocking call takes the zero-copy path
 constexpr int kInFlight = 4;  // mptcc_submit_poses calls that may be outstanding before submit waits for the oldest
 
 // Buffers of the split pipeline (split_kernels.cu) for one launch slot; grow-only.

@@ -16,7 +16,7 @@ rng = scenes.SplitMix64(7)
 chk = capi.Checker(1)
 chk.set_environment([box])
 chk.set_agent([box])
-for n in (1, 10, 100, 1000, 10000):
+for n in (1, 10, 100, 500, 1000, 2000, 10000):
     poses = scenes.random_poses_rt12(rng, n, (-2,) * 3, (2,) * 3)
     out = np.zeros((n + 31) // 32, np.uint32)
     for _ in range(50):
