@@ -93,7 +93,9 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes);
 /* ---- queries: host buffers ---------------------------------------------------------------- */
 /* One MeshHandler::isInCollision per pose-set.  poses: [n_pose_sets][n_links] records of
  * pose_format; verdict_bits: ceil(n/32) words, bit i%32 of word i/32 = 1 <=> pose-set i collides.
- * Pose-sets are split in contiguous slices over the context's devices. */
+ * Pose-sets are split in contiguous slices over the context's devices (sub-batches ping-pong over two streams so
+ * that copies overlap kernels); a call with at most 256 KB of poses -- one edge -- is served without any copy
+ * from pinned, device-mapped staging memory on the first device. */
 int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n_pose_sets, const double *poses, int pose_format,
                       uint32_t *verdict_bits);
 
