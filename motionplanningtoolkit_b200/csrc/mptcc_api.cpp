@@ -4,6 +4,9 @@
 // C.1, C.5]; build with -ffp-contract=off.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <thread>
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -730,9 +733,32 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 	ctx->obj_aabb_h.clear();
 	ctx->bp_nodes_h.clear();
 	ctx->env_set = false;
+	// The OBB trees of the objects are independent: built by a few host threads, a block of objects at a time
+	// (the flattening below stays sequential so that the packed order is the object order).
+	constexpr int kBlock = 256;
+	std::vector<HostBvh> block;
+	std::vector<char> block_ok;
 	for (int i = 0; i < n_objects; ++i) {
-		HostBvh b;
-		if (!build_bvh(meshes[i].xyz, meshes[i].nv, meshes[i].tri, meshes[i].nt, b))
+		if (i % kBlock == 0) {
+			const int cnt = std::min(kBlock, n_objects - i);
+			block.assign((size_t)cnt, HostBvh());
+			block_ok.assign((size_t)cnt, 0);
+			std::atomic<int> next(0);
+			auto work = [&]() {
+				for (int k = next.fetch_add(1); k < cnt; k = next.fetch_add(1)) {
+					const mptcc_mesh &m = meshes[i + k];
+					block_ok[(size_t)k] = build_bvh(m.xyz, m.nv, m.tri, m.nt, block[(size_t)k]) ? 1 : 0;
+				}
+			};
+			const unsigned hw = std::thread::hardware_concurrency();
+			const int n_threads = std::max(1, std::min<int>({(int)(hw ? hw : 1u), 16, cnt}));
+			std::vector<std::thread> pool;
+			for (int t = 1; t < n_threads; ++t) pool.emplace_back(work);
+			work();
+			for (auto &t : pool) t.join();
+		}
+		const HostBvh &b = block[(size_t)(i % kBlock)];
+		if (!block_ok[(size_t)(i % kBlock)])
 			return fail(ctx, MPTCC_ERR_INVALID, "environment object " + std::to_string(i) + " has an empty mesh");
 		DevObject o;
 		std::memset(&o, 0, sizeof o);
