@@ -381,8 +381,8 @@ struct Device {
 	DevBuf<uint32_t> edge_work;
 	float last_ms = 0.f;
 	// planner-sized calls: poses / verdict words in pinned host memory the kernel reads and writes in place
-	double *small_in = nullptr;
-	uint32_t *small_out = nullptr;
+	double *small_in = nullptr, *small_in_dev = nullptr;     // host address / the device's address of the same memory
+	uint32_t *small_out = nullptr, *small_out_dev = nullptr;
 	// per outstanding submit: completion events of the two streams, overflow flags read back (pinned)
 	cudaEvent_t done[kInFlight][kPipe] = {};
 	unsigned int *ctl_h[kInFlight] = {};
@@ -670,6 +670,9 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 		if (cudaHostAlloc(reinterpret_cast<void **>(&d.small_in), kSmallBytes, cudaHostAllocMapped) != cudaSuccess ||
 		    cudaHostAlloc(reinterpret_cast<void **>(&d.small_out), kSmallBytes / 56 / 8 + 64, cudaHostAllocMapped) != cudaSuccess)
 			return MPTCC_ERR_CUDA;
+		if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_in_dev), d.small_in, 0) != cudaSuccess ||
+		    cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_out_dev), d.small_out, 0) != cudaSuccess)
+			return MPTCC_ERR_CUDA;
 		if (d.work_user.reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (d.counters.reserve(CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
 		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
@@ -881,7 +884,7 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 			Device &d = ctx->devs[0];
 			CU(cudaSetDevice(d.id));
 			std::memcpy(d.small_in, poses, bytes);
-			const int rc = enqueue_kernel(ctx, d, n, d.small_in, fmt, d.small_out, d.work[0].p, d.stream[0], nullptr, true);
+			const int rc = enqueue_kernel(ctx, d, n, d.small_in_dev, fmt, d.small_out_dev, d.work[0].p, d.stream[0], nullptr, true);
 			if (rc != MPTCC_OK) return rc;
 			CU(cudaStreamSynchronize(d.stream[0]));
 			std::memcpy(verdict_bits, d.small_out, sizeof(uint32_t) * ((n + 31) / 32));
