@@ -149,7 +149,8 @@ int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3);
  * tests the links of each pose-set against each other (pairs with overlapping world AABBs, same mesh-mesh
  * narrowphase) and reports self-collision OR environment collision.
  * Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1),
- * "split_min", "split_cap", "always_replay", "time_phases", "near_first", "no_steal", "steal_bottom". */
+ * "split_min", "split_cap", "long_batches" (-1 = by launch size), "always_replay", "time_phases", "near_first",
+ * "no_steal", "steal_bottom". */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */

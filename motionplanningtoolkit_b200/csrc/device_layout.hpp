@@ -145,7 +145,7 @@ int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *str
 // self_kernel.cu: link-vs-link test of every pose-set (checkSelfCollision); p.env = the agent's pack,
 // p.objects = one DevObject per link.  ORs into verdict_bits.
 int launch_self_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
-int launch_narrowphase(const KernelParams &p, int sm_count, bool count, void *stream);
+int launch_narrowphase(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream);
 
 // edge_kernels.cu
 int launch_expand_omni_edges(const double *d_edges, const unsigned long long *d_offsets, unsigned long long n_edges,

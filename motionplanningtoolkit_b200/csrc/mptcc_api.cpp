@@ -414,6 +414,7 @@ struct mptcc_ctx {
 	long opt_no_steal = 0;
 	long opt_steal_bottom = 0;
 	long opt_near_first = 1;
+	long opt_long_batches = -1;      // narrowphase batches of 128 instead of 96 candidates: -1 = by launch size
 	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
 	mptcc_counters ctr{};
 	uint64_t submitted = 0, completed = 0;  // tickets of mptcc_submit_poses
@@ -604,7 +605,11 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		int e = launch_broadphase(kp, d.sm_count, ctx->count, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "broadphase_kernel launch");
 		if (timed) CU(cudaEventRecord(d.phase_ev[1], s));
-		e = launch_narrowphase(kp, d.sm_count, ctx->count, s);
+		// ~1.4 candidates per pose-set on the benchmark scenes: long batches once every resident warp (2 CTAs x 8
+		// warps per SM) can expect at least four of them
+		const bool long_batches = ctx->opt_long_batches == 1 ||
+		                          (ctx->opt_long_batches < 0 && n >= (uint64_t)d.sm_count * 16u * 128u * 3u);
+		e = launch_narrowphase(kp, d.sm_count, ctx->count, long_batches, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase_kernel launch");
 		if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
 		// overflow fall-back: the fused kernel returns at once unless the candidate list overflowed
@@ -1170,6 +1175,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "ctas_per_sm") {
 		if (value < 0 || value > 32) return fail(ctx, MPTCC_ERR_INVALID, "ctas_per_sm: 0..32");
 		ctx->opt_ctas_per_sm = value;
+	} else if (k == "long_batches") {
+		ctx->opt_long_batches = value < 0 ? -1 : (value != 0);
 	} else if (k == "self_collision") {
 		ctx->opt_self_collision = value != 0;
 	} else if (k == "near_first") {

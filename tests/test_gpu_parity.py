@@ -234,7 +234,8 @@ def test_sub_batch_pipeline(box_scene):
 
 
 @pytest.mark.parametrize("opts", [dict(split=0), dict(split=1, split_min=32), dict(split=1, split_min=32, split_cap=1),
-                                  dict(split=1, split_min=32, always_replay=1)])
+                                  dict(split=1, split_min=32, always_replay=1),
+                                  dict(split=1, split_min=32, long_batches=1), dict(split=1, split_min=32, long_batches=0)])
 def test_split_pipeline_matches_fused_and_oracle(built, opts):
     """Two-kernel pipeline (broadphase -> candidate list -> narrowphase) incl. the overflow fall-back
     (split_cap=1 makes the candidate list too small for this scene)."""
