@@ -343,7 +343,7 @@ def run_ours(args):
         if phase_ms is not None:
             # dominant kernel = narrowphase_kernel: it does the OBB and triangle tests (64 n_bv + 72 n_leaf); the
             # 96-byte pose records are read by the broadphase kernel
-            kernel_name, kernel_ms = "narrowphase_kernel<false>", float(phase_ms[1])
+            kernel_name, kernel_ms = "narrowphase_kernel<false, 128>", float(phase_ms[1])
             kernel_alg = 64.0 * bv + 72.0 * lf
         else:
             kernel_name, kernel_ms, kernel_alg = "collide_kernel<false>", step_ms, alg_bytes_per_pose

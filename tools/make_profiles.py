@@ -78,7 +78,7 @@ def kernel(rep, name, cubin):
 launches()
 t = kernel("prof_%s_narrowphase.ncu-rep" % tag, "narrowphase_kernel", "split_kernels")
 kernel("prof_%s_broadphase.ncu-rep" % tag, "broadphase_kernel", "split_kernels")
-json.dump({"dram_bytes_per_launch": t, "kernel": "narrowphase_kernel<false>",
+json.dump({"dram_bytes_per_launch": t, "kernel": "narrowphase_kernel<false, 128>",
            "source": "profiles/%s_narrowphase_kernel_metrics.txt (ncu --set full, one launch on the C5 batch)" % tag},
           open(os.path.join(P, "traffic.json"), "w"))
 print("traffic", t)
