@@ -203,6 +203,8 @@ def test_gpu_matches_golden_vectors(built, path):
     chk = capi.Checker(1)
     chk.set_environment(env, g["pose7"])
     chk.set_agent(links)
+    if "self_collision" in g.files and int(g["self_collision"]):
+        chk.set_option("self_collision", 1)
     got = chk.check_poses(g["poses"], int(g["fmt"]))
     assert_bits_equal(got, g["bits"], g["poses"].shape[0], os.path.basename(path))
 

@@ -131,6 +131,8 @@ def _golden_scene(name):
         return [box], [box]
     if name.startswith("c4_"):
         return [box], [box] * 11
+    if name.startswith("n4_"):
+        return [box], [box] * 4
     agent = meshio.agent_submesh(blimp, "last" if "_last_" in name else "merge")
     env = meshio.environment_submeshes(meshio.load_mptm("divider" if "divider" in name else "model"))
     return env, [agent]
@@ -142,7 +144,8 @@ def test_golden_vectors(built, path):
     env, links = _golden_scene(os.path.basename(path))
     sc = Scene(env, links, g["pose7"])
     ctr = O.Counters()
-    bits = sc.oracle_bits(g["poses"], int(g["fmt"]), counters=ctr)
+    with_self = "self_collision" in g.files and int(g["self_collision"])
+    bits = (sc.oracle_bits_self if with_self else sc.oracle_bits)(g["poses"], int(g["fmt"]), counters=ctr)
     assert np.array_equal(bits, g["bits"])
     assert ctr.n_bv_tests == int(g["n_bv_tests"]) and ctr.n_leaf_tests == int(g["n_leaf_tests"])
 

@@ -28,15 +28,21 @@ def digest(model):
     return h.hexdigest()
 
 
-def case(name, env, links, poses, fmt=O.POSE_RT12, pose7=(0, 0, 0, 1, 0, 0, 0)):
+ONLY = sys.argv[1:]  # optional: names of the cases to (re)write
+
+
+def case(name, env, links, poses, fmt=O.POSE_RT12, pose7=(0, 0, 0, 1, 0, 0, 0), self_collision=False):
+    if ONLY and name not in ONLY:
+        return
     models = {}
     om = [models.setdefault(id(m), O.Model(*m)) for m in env]
     ol = [models.setdefault(id(m), O.Model(*m)) for m in links]
     oenv = O.Environment(om, pose7)
     ctr = O.Counters()
-    bits = O.verdicts(oenv, ol, poses, fmt, 8, ctr)
+    bits = (O.verdicts_self if self_collision else O.verdicts)(oenv, ol, poses, fmt, 8, ctr)
     n = poses.shape[0]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), poses=poses, bits=bits, fmt=fmt, pose7=np.asarray(pose7, float),
+                        self_collision=int(self_collision),
                         n_bv_tests=ctr.n_bv_tests, n_leaf_tests=ctr.n_leaf_tests,
                         env_digest=np.array([digest(m) for m in om[:8]]), link_digest=np.array([digest(m) for m in ol[:1]]))
     print("%-28s n=%6d collide=%.3f bv=%d leaf=%d" % (name, n, O.unpack_bits(bits, n).mean(), ctr.n_bv_tests, ctr.n_leaf_tests))
@@ -70,6 +76,10 @@ def main():
     # C4: snake, 11 links of the same box
     poses = np.stack([scenes.random_poses_rt12(rng, 1500, (-4, -4, -1), (4, 4, 1)) for _ in range(11)], axis=1)
     case("c4_snake_11_links", [box], [box] * 11, poses)
+    # N4: checkSelfCollision = true, four independent box links (self-collision OR environment)
+    rng4 = scenes.SplitMix64(0x601E)
+    poses = np.stack([scenes.random_poses_rt12(rng4, 3000, (-2.2,) * 3, (2.2,) * 3) for _ in range(4)], axis=1)
+    case("n4_self_collision_4_links", [box], [box] * 4, poses, self_collision=True)
 
 
 if __name__ == "__main__":
