@@ -607,7 +607,6 @@ __device__ __forceinline__ unsigned rec_at(unsigned cand, unsigned k) { return 4
 
 // Hit bookkeeping of the fused kernel: one bit per pose slot of the warp's chunk, in registers.
 struct FusedTrav {
-	static constexpr bool kStream = false;  // the candidate table is filled once per traverse_all call
 	u64 hitmask, validmask;
 	const double *link_poses;  // pose record of slot s of the current link: link_poses + s * stride
 	size_t stride;
@@ -647,7 +646,6 @@ struct FusedTrav {
 // Hit bookkeeping of the narrowphase kernel (single-link agents): flags in shared memory per pose slot of
 // the batch, verdict bits set with atomicOr (the buffer is zeroed before the pipeline runs).
 struct SplitTrav {
-	static constexpr bool kStream = false;
 	const double *poses;
 	unsigned rec_len;
 	uint32_t *verdict_bits;
@@ -811,7 +809,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 	unsigned top = 0, bot = 0;  // ring buffer: entries [bot, top) = pending right siblings
 	uint2 cur = make_uint2(0u, 0u);
 	bool has = false;           // `cur` is the pair this lane tests next (top of its logical stack)
-	int qhead = 0, qend = ncand, lq = 0;  // unstarted candidates: table slots [qhead, qend)
+	int qhead = 0, lq = 0;
 
 	while (!tv.all_done()) {
 		if (!has && top != bot) {
@@ -820,14 +818,9 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 		}
 		// ---- 1. idle lanes start the next unstarted candidates --------------------------------------
 		unsigned im = __ballot_sync(FULL, !has);
-		if constexpr (Trav::kStream) {
-			// a streaming policy may put more candidates into a drained part of the table (a lane without `cur`
-			// has an empty stack here, so every lane works on at most one candidate: the one of `cur`)
-			if (im && qhead >= qend) tv.refill(p, wm, has ? (cur.y >> 24) : 0xffffffffu, lq, qhead, qend, lane);
-		}
-		if (im && qhead < qend) {
+		if (im && qhead < ncand) {
 			const int c = qhead + __popc(im & lt);
-			if (!has && c < qend) {
+			if (!has && c < ncand) {
 				cur = make_uint2(0u, kPlanSingle | ((unsigned)c << 24));  // root pair
 				has = true;
 			}
@@ -835,7 +828,7 @@ __device__ void traverse_all(const KernelParams &p, const WarpMem &wm, const Dev
 			im = __ballot_sync(FULL, !has);
 		}
 		// ---- 2. ... or steal the bottom entry (largest pending subtree) of a busy lane ------------------
-		if (im && qhead >= qend && !p.no_steal) {
+		if (im && qhead >= ncand && !p.no_steal) {
 			const unsigned dm = __ballot_sync(FULL, has && top != bot);
 			if (dm) {
 				const int n_thieves = __popc(im), n_donors = __popc(dm);

@@ -19,7 +19,6 @@ __host__ __device__ constexpr unsigned self_warp_smem_bytes() { return warp_smem
 // Hit bookkeeping: one bit per pose-set slot of the warp's chunk; a candidate is (slot, link a) against the
 // current link b.
 struct SelfTrav {
-	static constexpr bool kStream = false;
 	u64 hitmask, validmask;
 	const double *chunk_poses;  // record of (slot s, link l): chunk_poses + (s * n_links + l) * rec_len
 	unsigned rec_len, n_links, link_b;

@@ -200,92 +200,6 @@ constexpr int kNpWarpsPerCta = MPTCC_NP_WARPS;
 #define NP_BOUNDS __launch_bounds__(kNpWarpsPerCta * 32, MPTCC_NP_CTAS)
 #endif
 
-#ifdef MPTCC_NP_STREAM
-// Narrowphase without batch boundaries (experimental, -DMPTCC_NP_STREAM): the table is two halves of BATCH/2
-// candidates.  When the unstarted candidates of the half in use are gone and the OTHER half has drained -- no
-// lane's current candidate and no leaf-queue entry belongs to it -- the warp refills that half from the global
-// list, so idle lanes start new candidates while the stragglers of the current half finish.
-template <int BATCH>
-struct SplitStreamTrav {
-	static constexpr bool kStream = true;
-	static constexpr unsigned H = BATCH / 2;
-	uint32_t *verdict_bits;
-	unsigned total;          // candidates in the list
-	unsigned half_first[2];  // list index of slot 0 of each half
-	unsigned fill_half;      // half whose candidates are being started
-	bool exhausted;
-	__device__ __forceinline__ bool dead(unsigned slot, const WarpMem &wm) const { return wm.dead[slot] != 0; }
-	__device__ __forceinline__ bool all_done() const { return false; }
-	__device__ __forceinline__ void mark_hit(unsigned slot, unsigned cand, const WarpMem &wm, const KernelParams &, int lane) {
-		__syncwarp();
-		if (lane == 0) {
-			wm.dead[slot] = 1;
-			const uint32_t pose = wm.cand_pose[cand];
-			atomicOr(verdict_bits + (pose >> 5), 1u << (pose & 31u));
-		}
-		__syncwarp();
-	}
-	__device__ __forceinline__ void mark_hits_per_lane(int slot, unsigned cand, const WarpMem &wm, int) {
-		__syncwarp();
-		if (slot >= 0) {
-			wm.dead[slot] = 1;
-			const uint32_t pose = wm.cand_pose[cand];
-			atomicOr(verdict_bits + (pose >> 5), 1u << (pose & 31u));
-		}
-		__syncwarp();
-	}
-	__device__ __forceinline__ unsigned object(unsigned cand, const WarpMem &wm) const { return wm.cand_ids[cand]; }
-	__device__ __forceinline__ const double *exact_rel(const KernelParams &p, const WarpMem &, const DevObject &, unsigned,
-	                                                   unsigned cand, int) const {
-		return p.cand_rel + 12ull * (half_first[cand / H] + cand % H);
-	}
-	// my_cand: table slot of the candidate this lane is working on, 0xffffffff if none
-	__device__ __forceinline__ bool refill(const KernelParams &p, const WarpMem &wm, unsigned my_cand, int lq, int &qhead,
-	                                       int &qend, int lane) {
-		if (exhausted) return false;
-		const unsigned oh = fill_half ^ 1u;
-		bool busy = my_cand != 0xffffffffu && my_cand / H == oh;
-		for (int i = lane; i < lq; i += 32) busy |= (wm.leafq[i].y >> 24) / H == oh;
-		if (__any_sync(FULL, busy)) return false;
-		unsigned first = 0;
-		if (lane == 0) first = atomicAdd(p.work_counter2, H);
-		first = __shfl_sync(FULL, first, 0);
-		if (first >= total) {
-			exhausted = true;
-			return false;
-		}
-		const int n = (int)(total - first < H ? total - first : H);
-		const unsigned base = oh * H;
-		const float4 *src_rec = p.cand_rec + 4ull * first;
-		for (int i = lane; i < 4 * n; i += 32) wm.cand[rec_at(base + ((unsigned)i >> 2), (unsigned)i & 3u)] = src_rec[i];
-		for (int i = lane; i < n; i += 32) {
-			wm.cand_ids[base + i] = p.cand_obj[first + i];
-			wm.cand_pose[base + i] = p.cand_pose[first + i];
-		}
-		__syncwarp();
-		unsigned carry = base;
-		for (int g = 0; g < (n + 31) / 32; ++g) {
-			const int i = 32 * g + lane;
-			const bool valid = i < n;
-			const uint32_t pose = valid ? wm.cand_pose[base + i] : 0u;
-			const bool start = valid && (i == 0 || wm.cand_pose[base + i - 1] != pose);
-			const unsigned sm = __ballot_sync(FULL, start);
-			const unsigned upto = sm & (0xffffffffu >> (31 - lane));
-			const unsigned slot = upto ? base + (unsigned)(32 * g + 31 - __clz((int)upto)) : carry;
-			if (valid) wm.cand[rec_at(base + (unsigned)i, 3u)].y = __uint_as_float(slot);
-			if (start) wm.dead[base + i] = (unsigned char)((p.verdict_bits[pose >> 5] >> (pose & 31u)) & 1u);
-			if (sm) carry = base + (unsigned)(32 * g + 31 - __clz((int)sm));
-		}
-		__syncwarp();
-		half_first[oh] = first;
-		fill_half = oh;
-		qhead = (int)base;
-		qend = (int)base + n;
-		return true;
-	}
-};
-#endif
-
 template <bool COUNT, int BATCH>
 __global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -312,24 +226,13 @@ __global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParam
 	if (*p.overflow != 0u) return;
 	const unsigned total = *p.cand_total;
 	const DevModel &m2 = p.agent.models[p.link_model[0]];
-	unsigned long long ctr[CTR_N];
-#pragma unroll
-	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
-#ifdef MPTCC_NP_STREAM
-	{
-		SplitStreamTrav<BATCH> st;
-		st.verdict_bits = p.verdict_bits;
-		st.total = total;
-		st.half_first[0] = st.half_first[1] = 0u;
-		st.fill_half = 1u;  // the first refill fills half 0
-		st.exhausted = false;
-		traverse_all<COUNT>(p, wm, m2, 0, st, lane, ctr);
-	}
-#else
 	SplitTrav tv;
 	tv.poses = p.poses;
 	tv.rec_len = p.pose_format == 1u ? 7u : 12u;
 	tv.verdict_bits = p.verdict_bits;
+	unsigned long long ctr[CTR_N];
+#pragma unroll
+	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
 
 	while (true) {
 		unsigned first = 0;
@@ -366,7 +269,6 @@ __global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParam
 		traverse_all<COUNT>(p, wm, m2, n, tv, lane, ctr);
 		__syncwarp();
 	}
-#endif
 	if (COUNT && lane == 0) {
 #pragma unroll
 		for (int i = 0; i < CTR_N; ++i)
