@@ -46,9 +46,18 @@ extern "C" {
  *        /root/reference/agents/omnidirectional.hpp:224-242, agents/snake_trailers.hpp:432,455.
  *  TQ7 : 7 doubles, x y z qw qx qy qz: fcl::Transform3f(fcl::Quaternion3f(w,x,y,z), fcl::Vec3f)
  *        -- fcl_helpers::parseTransform (/root/reference/utilities/fcl_helpers.hpp:16-25) and the
- *        PRMLite samples (/root/reference/discretizations/workspace/prmlite.hpp:246-258). */
+ *        PRMLite samples (/root/reference/discretizations/workspace/prmlite.hpp:246-258).
+ *  T3  : 3 doubles, x y z: fcl::Transform3f(fcl::Vec3f) -- identity rotation AND identity quaternion, i.e. the
+ *        translated tight AABB in the broadphase; what Omnidirectional::getPoses emits
+ *        (/root/reference/agents/omnidirectional.hpp:224-242).  Same verdicts as RT12 with R = I, a quarter of the bytes.
+ *  XYZCS: 5 doubles, x y z c s: fcl::Transform3f(R, T) with the planar rotation the blimp and the snake build,
+ *        R(0,0)=c R(1,0)=-s R(0,1)=s R(1,1)=c R(2,2)=1 (/root/reference/agents/blimp.hpp:345-355,
+ *        agents/snake_trailers.hpp:422-432,445-455); c = cos(theta), s = sin(theta) are evaluated by the CALLER (host
+ *        libm, as the reference does), so the verdicts are those of the RT12 record with the same entries. */
 #define MPTCC_POSE_RT12 0
 #define MPTCC_POSE_TQ7 1
+#define MPTCC_POSE_T3 2
+#define MPTCC_POSE_XYZCS 3
 
 typedef struct mptcc_ctx mptcc_ctx;
 
@@ -141,16 +150,18 @@ int mptcc_reset_counters(mptcc_ctx *ctx);
 /* Device milliseconds of the last host-buffer check call on device slot `slot`: from the first kernel to the end
  * of the last kernel (CUDA events on the launching streams; copies that overlap the kernels are inside). */
 int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
-/* With option "time_phases" = 1: device milliseconds of the three kernels of the last split-pipeline launch
- * on `slot` (CUDA events on the launching stream): ms3 = {broadphase, narrowphase, overflow fall-back}. */
-int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3);
+/* With option "time_phases" = 1: device milliseconds of the four kernels of the last split-pipeline launch
+ * on `slot` (CUDA events on the launching stream): ms4 = {broadphase, narrowphase, exact pass, overflow fall-back}
+ * (the round-1 narrowphase, option "np2" = 0, has no separate exact pass: ms4[2] is then ~0). */
+int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4);
 /* Behaviour: "self_collision" (0/1, default 0) = the checkSelfCollision argument of
  * MeshHandler::isInCollision (/root/reference/utilities/meshhandler.hpp:187-219): every later check also
  * tests the links of each pose-set against each other (pairs with overlapping world AABBs, same mesh-mesh
  * narrowphase) and reports self-collision OR environment collision.
  * Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1),
  * "split_min", "split_cap", "long_batches" (-1 = by launch size), "always_replay", "time_phases", "near_first",
- * "no_steal", "steal_bottom". */
+ * "no_steal", "steal_bottom", "np2" (0 = round-1 narrowphase kernel), "agent_top" (agent tree nodes staged in
+ * shared memory, -1 = auto). */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */

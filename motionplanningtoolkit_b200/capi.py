@@ -10,9 +10,15 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmptcc.so")
+# kernel A/B experiments only (tools/build_variants.sh): another build of the same library
+if os.environ.get("MPTCC_LIB"):
+    LIB_PATH = os.path.abspath(os.environ["MPTCC_LIB"])
 
 POSE_RT12 = 0
 POSE_TQ7 = 1
+POSE_T3 = 2       # x y z: Transform3f(Vec3f)
+POSE_XYZCS = 3    # x y z cos sin: planar rotation of the blimp / snake
+REC_LEN = {0: 12, 1: 7, 2: 3, 3: 5}
 
 OK, ERR_INVALID, ERR_STATE, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM, ERR_LIMIT = range(7)
 _ERR_NAMES = {1: "INVALID", 2: "STATE", 3: "NO_DEVICE", 4: "CUDA", 5: "NOMEM", 6: "LIMIT"}
@@ -216,7 +222,7 @@ class Checker:
         self.n_links = len(link_meshes)
 
     def _rec(self, fmt):
-        return (7 if fmt == POSE_TQ7 else 12) * self.n_links
+        return REC_LEN[fmt] * self.n_links
 
     def check_poses(self, poses, fmt=POSE_RT12, out=None):
         """poses: float64 [n, n_links, 12|7] (host).  Returns uint32 verdict words (bit=1: collides)."""
@@ -281,8 +287,8 @@ class Checker:
         return ms.value
 
     def last_phase_ms(self, slot=0):
-        """(broadphase, narrowphase, fall-back) ms of the last split-pipeline launch (option time_phases)."""
-        ms = (C.c_float * 3)()
+        """(broadphase, narrowphase, exact pass, fall-back) ms of the last split-pipeline launch (option time_phases)."""
+        ms = (C.c_float * 4)()
         self._check(self.lib.mptcc_last_phase_ms(self.h, slot, ms))
         return tuple(ms)
 

@@ -121,10 +121,29 @@ __device__ __forceinline__ void quat_to_rotation(const Quat &q, double *R) {
 	R[8] = dsub(1.0, dadd(twoXX, twoYY));
 }
 
-// Pose record -> R (9), T (3), q.  RT12: Transform3f(R,T) (q = fromRotation(R)); TQ7: Transform3f(q,T).
+// Pose record -> R (9), T (3), q.  RT12: Transform3f(R,T) (q = fromRotation(R)); TQ7: Transform3f(q,T);
+// T3: Transform3f(T) = identity rotation and identity quaternion (Omnidirectional::getPoses,
+// /root/reference/agents/omnidirectional.hpp:224-242); XYZCS: x y z c s -> Transform3f(R,T) with the planar
+// rotation the blimp and the snake fill in, R(0,0)=c R(1,0)=-s R(0,1)=s R(1,1)=c (/root/reference/agents/blimp.hpp:345-355,
+// agents/snake_trailers.hpp:422-432), c and s evaluated by the caller's libm.
 __device__ __forceinline__ void decode_pose(const double *rec, uint32_t fmt, double *R, double *T, Quat &q,
                                             bool want_q) {
-	if (fmt == 1u) {
+	if (fmt == 2u || fmt == 3u) {
+		const double c = fmt == 3u ? rec[3] : 1.0, s = fmt == 3u ? rec[4] : 0.0;
+		R[0] = c;
+		R[1] = s;
+		R[2] = 0.0;
+		R[3] = -s;
+		R[4] = c;
+		R[5] = 0.0;
+		R[6] = 0.0;
+		R[7] = 0.0;
+		R[8] = 1.0;
+		T[0] = rec[0];
+		T[1] = rec[1];
+		T[2] = rec[2];
+		if (want_q) q = quat_from_rotation(R);  // (1,0,0,0) exactly for the identity, as Transform3f(T) stores
+	} else if (fmt == 1u) {
 		T[0] = rec[0];
 		T[1] = rec[1];
 		T[2] = rec[2];
@@ -391,6 +410,23 @@ __device__ __forceinline__ F8 ldg256(const float4 *p) {
 	MPTCC_LD256("");
 	return r;
 }
+// L2 eviction priorities (256-bit accesses only, sm_100): tree nodes are re-read by every warp and should outlive
+// the candidate list, which is written once by the broadphase kernel and read once by the narrowphase kernel.
+__device__ __forceinline__ F8 ldg256_evict_last(const float4 *p) {
+	F8 r;
+	MPTCC_LD256(".L2::evict_last");
+	return r;
+}
+__device__ __forceinline__ F8 ldg256_evict_first(const float4 *p) {
+	F8 r;
+	MPTCC_LD256(".L2::evict_first");
+	return r;
+}
+__device__ __forceinline__ void stg256_evict_first(float4 *p, const float4 a, const float4 b) {
+	asm volatile("st.global.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z),
+	             "f"(a.w), "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
+	             : "memory");
+}
 __device__ __forceinline__ void stg256(float4 *p, const float4 a, const float4 b) {
 	asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w),
 	             "f"(b.x), "f"(b.y), "f"(b.z), "f"(b.w)
@@ -412,8 +448,9 @@ __device__ __forceinline__ void load_pose_record(const double *rec, uint32_t fmt
 #pragma unroll
 		for (int k = 0; k < 12; ++k) out[k] = rec[k];
 	} else {
+		const unsigned len = pose_rec_len(fmt);
 #pragma unroll
-		for (int k = 0; k < 7; ++k) out[k] = rec[k];
+		for (int k = 0; k < 7; ++k) out[k] = (unsigned)k < len ? rec[k] : 0.0;
 #pragma unroll
 		for (int k = 7; k < 12; ++k) out[k] = 0.0;
 	}
@@ -599,6 +636,21 @@ __device__ __forceinline__ double rel_element(const DevObject &ob, const double 
 	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
 }
 
+// fp64 relativeTransform(object, pose) of a candidate, FCL's operation order, into `out` (12 doubles in shared
+// memory): lanes 0..11 compute one element each; all lanes must call.
+__device__ __forceinline__ const double *exact_rel_from_pose(const KernelParams &p, const DevObject &ob, const double *pose_rec,
+                                                             double *out, int lane) {
+	__syncwarp();
+	if (lane < 12) {
+		double R2[9], T2[3];
+		Quat q;
+		decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
+		out[lane] = rel_element(ob, R2, T2, lane);
+	}
+	__syncwarp();
+	return out;
+}
+
 // Candidate records live in shared memory as 4 float4 (64 B).  Lanes fetch the SAME part k of DIFFERENT
 // records at once; with a plain layout all even (odd) candidates would hit the same 4 banks.  Part k of
 // candidate c is therefore stored at position (k + (c >> 1)) & 3 of its record: 8 consecutive candidates
@@ -747,6 +799,52 @@ __device__ __forceinline__ void make_candidate_record(const KernelParams &p, con
 	rec[1] = make_float4((float)rl[4], (float)rl[5], (float)rl[6], (float)rl[7]);
 	rec[2] = make_float4((float)rl[8], tf[0], tf[1], tf[2]);
 	rec[3] = make_float4(S, __uint_as_float(slot), __uint_as_float(m1.node_base), __uint_as_float(m1.tri_base));
+}
+
+// Candidate record of the second-generation narrowphase (np2_kernels.cu): R (9), Tc (3), Tinv (3), S, where
+// x1 - C1 = R (x2 - C2) + Tc is the relative transform in the recentred frames and Tinv = -R^T Tc the translation
+// of its inverse (fp64, rounded once).  `base` = node_base / tri_base of the object's model.  Returns false if R
+// is not a rotation to within 1e-11 (then (R^T, Tinv) is not the inverse and the caller must route the launch to
+// the fused kernel, which makes no such assumption).
+__device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, const double *pose_rec, const DevObject &ob,
+                                                       const DevModel &m2, float4 *rec, double *rel64, uint2 &base) {
+	const DevModel &m1 = p.env.models[ob.model];
+	double R2[9], T2[3], rl[12];
+	Quat q;
+	decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
+#pragma unroll
+	for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
+	if (rel64 != nullptr) {
+#pragma unroll
+		for (int k = 0; k < 12; ++k) rel64[k] = rl[k];  // FCL's R (9), T (3) verbatim, for the exact pass
+	}
+	double tc[3];
+	float tinf = 0.f;
+#pragma unroll
+	for (int r = 0; r < 3; ++r) {
+		tc[r] = rl[3 * r] * m2.ctr[0] + rl[3 * r + 1] * m2.ctr[1] + rl[3 * r + 2] * m2.ctr[2] + rl[9 + r] - m1.ctr[r];
+		tinf = fmaxf(tinf, fabsf((float)tc[r]));
+	}
+	double ti[3], defect = 0.0;
+#pragma unroll
+	for (int c = 0; c < 3; ++c) {
+		ti[c] = -(rl[c] * tc[0] + rl[3 + c] * tc[1] + rl[6 + c] * tc[2]);
+#pragma unroll
+		for (int d = c; d < 3; ++d) {
+			const double g = rl[c] * rl[d] + rl[3 + c] * rl[3 + d] + rl[6 + c] * rl[6 + d] - (c == d ? 1.0 : 0.0);
+			defect = fmax(defect, fabs(g));  // (fmax drops NaN: the finite test below catches those)
+		}
+	}
+	bool finite = true;
+#pragma unroll
+	for (int k = 0; k < 12; ++k) finite = finite && (fabs(rl[k]) <= 1.7e308);
+	const float S = fmaxf(5.01f * m2.r2 + 4.0f * tinf * 1.0000002f, m1.rinf) + m1.rinf;
+	rec[0] = make_float4((float)rl[0], (float)rl[1], (float)rl[2], (float)rl[3]);
+	rec[1] = make_float4((float)rl[4], (float)rl[5], (float)rl[6], (float)rl[7]);
+	rec[2] = make_float4((float)rl[8], (float)tc[0], (float)tc[1], (float)tc[2]);
+	rec[3] = make_float4((float)ti[0], (float)ti[1], (float)ti[2], S);
+	base = make_uint2(m1.node_base, m1.tri_base);
+	return finite && defect <= 1e-11;
 }
 
 // Pose box -> the integer grid of the broadphase tree (device_layout.hpp), rounded outward by one extra cell

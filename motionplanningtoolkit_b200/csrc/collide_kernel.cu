@@ -31,7 +31,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 	if (p.run_if != nullptr && *p.run_if == 0u) return;  // overflow fall-back of the split pipeline: nothing to do
 	const unsigned ppw = 1u << p.ppw_log2;
 	const unsigned long long n_chunks = (p.n_pose_sets + ppw - 1) >> p.ppw_log2;
-	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const unsigned rec_len = pose_rec_len(p.pose_format);
 	const bool aligned32 = (reinterpret_cast<unsigned long long>(p.poses) & 31ull) == 0ull;
 	const unsigned lt = (1u << lane) - 1u;
 	unsigned long long ctr[CTR_N];

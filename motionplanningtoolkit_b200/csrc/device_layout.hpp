@@ -11,6 +11,15 @@
 //              [3] = (extent.xyz rounded up and inflated by 1e-6, int-bits link)
 //            link >= 0: first child (children are link, link+1); link < 0: leaf, primitive = -(link+1).
 //            node_base is odd, so every sibling pair (2k+1, 2k+2) shares one 128-byte line.
+//   nodeq  : uint4[2] per node, 32 B, same numbering as node32: the traversal node of the second-generation
+//            narrowphase (np2_kernels.cu) -- ONE 256-bit load per node, a sibling pair is 64 bytes.
+//              [0].x = axis0.x | axis0.y << 16   [0].y = axis0.z | axis1.x << 16   [0].z = axis1.y | axis1.z << 16
+//                      (binary16, round to nearest; axis2 = axis0 x axis1 is formed in the kernel)
+//              [0].w = extent.x | extent.y << 16  [1].x = extent.z | link[15:0] << 16        (binary16, rounded UP)
+//              [1].y = centre.x (fp32; its low mantissa byte holds link[23:16])   [1].z, [1].w = centre.y, centre.z
+//            link (24 bit): bit 23 = leaf, low 23 bits = first child / primitive.  The extents are widened by the
+//            centre displacement and by (1 + 1e-6); the axis quantisation (<= 2^-12 per component) is covered by an
+//            extra margin in the kernel's SAT.
 //   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.
 //   node64 : double[16] per node: FCL's OBB verbatim -- axis (9), To (3), extent (3), size =
 //            extent.sqrLength() (1).  Only read when a positive leaf pair replays FCL's path.
@@ -35,6 +44,12 @@
 #include <cstdint>
 
 namespace mptcc {
+
+// Doubles per pose record of each format (include/mptcc.h): RT12, TQ7, T3, XYZCS.
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline constexpr unsigned pose_rec_len(unsigned fmt) { return fmt == 1u ? 7u : fmt == 2u ? 3u : fmt == 3u ? 5u : 12u; }
 
 struct DevModel {
 	uint32_t node_base;
@@ -72,6 +87,7 @@ struct ModelPack {
 	const float *mu_chain;  // per triangle: min over its ancestor chain (leaf included) of the sum of the two
 	                        // smallest OBB extents of the node, rounded down (path certificate)
 	const DevModel *models;
+	const uint4 *nodeq;     // 2 x uint4 per node: the quantised fast-pass node of the np2 kernel (see above)
 };
 
 struct KernelParams {
@@ -108,6 +124,13 @@ struct KernelParams {
 	uint32_t steal_bottom;         // 1: thieves take the bottom (largest, most speculative) pending pair
 	uint32_t no_steal;             // 1: lanes never steal pending subtrees (experiment knob)
 	uint32_t always_replay;        // 1: replay FCL's path for every positive pair (ignore the certificate)
+	// second-generation narrowphase (np2_kernels.cu)
+	uint2 *cand_base;              // [cand_cap] node_base, tri_base of the candidate's environment model
+	uint4 *xq;                     // [xq_cap] exact-pass queue: candidate list index, env prim, agent prim, certain-contact flag
+	unsigned int *xq_total;        // [1] entries appended (can exceed xq_cap: then *overflow = 1)
+	unsigned int xq_cap;
+	uint32_t qnode;                // 1: traverse nodeq (32-byte nodes), 0: node32
+	uint32_t agent_top;            // agent nodes [0, agent_top) of link model 0 are staged in shared memory (breadth-first ids)
 };
 
 // index of the counters in KernelParams::counters
@@ -120,6 +143,8 @@ constexpr int kClusterSize = MPTCC_CLUSTER;
 constexpr int kWarpsPerCta = 8;
 constexpr int kLeafQueueCap = 96;   // a node step appends <= 64 pairs; the leaf phase runs at >= 32
 constexpr int kClusterQueueCap = 64;  // (pose, cluster) entries waiting for the exact AABB test
+constexpr unsigned kAgentTopMaxQ = 1023; // the same with 32-byte quantised nodes: 10 full levels, 32 KB
+constexpr unsigned kAgentTopMax = 511;  // top of the (breadth-first numbered) agent tree staged in shared memory: 9 full levels, 32 KB
 constexpr int kLaneStackCap = 64;     // per-lane depth-first stack (local memory); needs depth1 + depth2 + 2 <= 64
 #ifndef MPTCC_CAND_CAP
 #define MPTCC_CAND_CAP 96
@@ -141,11 +166,14 @@ int collide_max_ctas_per_sm(bool count);
 
 // split_kernels.cu: broadphase kernel (poses -> candidate list) and narrowphase kernel (candidate list ->
 // verdict bits); single-link agents.
-int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *stream);
+int launch_broadphase(const KernelParams &p, int sm_count, bool count, bool np2, void *stream);
 // self_kernel.cu: link-vs-link test of every pose-set (checkSelfCollision); p.env = the agent's pack,
 // p.objects = one DevObject per link.  ORs into verdict_bits.
 int launch_self_collide(const KernelParams &p, int grid_ctas, bool count, void *stream);
 int launch_narrowphase(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream);
+// np2_kernels.cu: second-generation narrowphase (TMA-staged agent tree top, child-frame SAT) + its exact-pass kernel
+int launch_narrowphase2(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream);
+int launch_exact(const KernelParams &p, int sm_count, bool count, void *stream);
 
 // edge_kernels.cu
 int launch_expand_omni_edges(const double *d_edges, const unsigned long long *d_offsets, unsigned long long n_edges,

@@ -53,11 +53,10 @@ __global__ void expand_omni_edges_kernel(const double *__restrict__ edges, const
 			y = e[4];
 			z = e[5];
 		}
-		double *o = poses + 12 * t;  // fcl::Transform3f(Vec3f): identity rotation
-		o[0] = 1.0; o[1] = 0.0; o[2] = 0.0;
-		o[3] = 0.0; o[4] = 1.0; o[5] = 0.0;
-		o[6] = 0.0; o[7] = 0.0; o[8] = 1.0;
-		o[9] = x; o[10] = y; o[11] = z;
+		double *o = poses + 3 * t;  // a T3 record: fcl::Transform3f(Vec3f), identity rotation
+		o[0] = x;
+		o[1] = y;
+		o[2] = z;
 	}
 }
 

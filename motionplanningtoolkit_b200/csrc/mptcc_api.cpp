@@ -39,6 +39,38 @@ inline float round_down_f32(double x) {
 	return f;
 }
 
+// IEEE binary16 helpers for the quantised nodes (device_layout.hpp, nodeq): exact half -> float, and float -> half
+// rounded to nearest (ties away from zero are fine here: the error bound is what matters) or upward.
+inline float half_to_float(uint16_t h) {
+	const int e = (h >> 10) & 31, m = h & 1023;
+	float v;
+	if (e == 0) v = std::ldexp((float)m, -24);
+	else if (e == 31) v = m ? NAN : INFINITY;
+	else v = std::ldexp((float)(m + 1024), e - 25);
+	return (h & 0x8000) ? -v : v;
+}
+inline uint16_t float_to_half(float f, bool up) {  // up: smallest half >= f (f >= 0); else nearest
+	if (!(f == f)) return 0x7e00;
+	const uint16_t sign = std::signbit(f) ? 0x8000 : 0;
+	const float a = std::fabs(f);
+	uint16_t h;  // truncation toward zero of |f|
+	if (a >= 65504.0f) h = 0x7bff;
+	else if (a < std::ldexp(1.0f, -24)) h = 0;
+	else {
+		int e;
+		const float m = std::frexp(a, &e);  // a = m * 2^e, m in [0.5, 1)
+		if (e - 1 < -14) h = (uint16_t)std::floor(std::ldexp(a, 24));
+		else h = (uint16_t)(((e - 1 + 15) << 10) | (int)std::floor((m * 2.0f - 1.0f) * 1024.0f));
+	}
+	const float lo = half_to_float(h), hi = half_to_float((uint16_t)(h + 1));
+	if (up) {
+		if (lo < a) ++h;
+	} else if (a - lo >= hi - a && hi != INFINITY) {
+		++h;
+	}
+	return (uint16_t)(sign | h);
+}
+
 // [FCL-recalled] Quaternion3f::operator* / transform
 inline void qmul(const double a[4], const double b[4], double o[4]) {
 	const double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
@@ -65,6 +97,7 @@ inline void quat_rotate(const double q[4], const double v[3], double o[3]) {
 // Host image of one ModelPack.
 struct HostPack {
 	std::vector<float4> node32;
+	std::vector<uint4> nodeq;
 	std::vector<float4> tri32;
 	std::vector<double> node64;
 	std::vector<double> tri64;
@@ -75,12 +108,32 @@ struct HostPack {
 
 	void clear() { *this = HostPack(); }
 
-	// Appends one model; returns its id.
-	uint32_t add(const HostBvh &b) {
+	// Appends one model; returns its id.  bfs: number the device nodes breadth-first (root 0, the two children of a
+	// node adjacent, parents before children level by level) instead of in FCL's allocation order, so that the top
+	// levels of the tree are one contiguous block the narrowphase kernel can stage in shared memory with one bulk
+	// copy.  Only the device ids change (links, ancestor chains); primitives and the fp64 node values do not.
+	uint32_t add(const HostBvh &b, bool bfs = false) {
+		const uint32_t nn0 = b.num_nodes();
+		std::vector<uint32_t> order(nn0), newid(nn0);  // order[new] = FCL id, newid[FCL id] = new
+		if (bfs) {
+			uint32_t head = 0, tail = 0;
+			order[tail++] = 0;
+			while (head < tail) {
+				const uint32_t v = order[head++];
+				if (b.first_child[v] >= 0) {
+					order[tail++] = (uint32_t)b.first_child[v];
+					order[tail++] = (uint32_t)b.first_child[v] + 1u;
+				}
+			}
+		} else {
+			for (uint32_t i = 0; i < nn0; ++i) order[i] = i;
+		}
+		for (uint32_t i = 0; i < nn0; ++i) newid[order[i]] = i;
 		DevModel m;
 		std::memset(&m, 0, sizeof m);
 		if ((node32.size() / 4) % 2 == 0) {  // node_base must be odd: pad one node slot
 			for (int k = 0; k < 4; ++k) node32.push_back(make_float4(0, 0, 0, 0));
+			for (int k = 0; k < 2; ++k) nodeq.push_back(make_uint4(0, 0, 0, 0));
 			for (int k = 0; k < 16; ++k) node64.push_back(0.0);
 		}
 		m.node_base = (uint32_t)(node32.size() / 4);
@@ -122,7 +175,8 @@ struct HostPack {
 			m.cmax1 = std::max(m.cmax1, std::fabs(C[0]) + std::fabs(C[1]) + std::fabs(C[2]));
 			m.esum = std::max(m.esum, E[0] + E[1] + E[2]);
 		}
-		for (uint32_t i = 0; i < nn; ++i) {
+		for (uint32_t ni = 0; ni < nn; ++ni) {
+			const uint32_t i = order[ni];
 			const double *A = &b.axis[9 * (size_t)i];
 			const double *C = &b.center[3 * (size_t)i];
 			const double *E = &b.extent[3 * (size_t)i];
@@ -132,9 +186,35 @@ struct HostPack {
 			last.x = round_up_f32(E[0] * (1.0 + 1e-6));
 			last.y = round_up_f32(E[1] * (1.0 + 1e-6));
 			last.z = round_up_f32(E[2] * (1.0 + 1e-6));
-			const int32_t link = b.first_child[i];
+			const int32_t link = b.first_child[i] >= 0 ? (int32_t)newid[(uint32_t)b.first_child[i]] : b.first_child[i];
 			std::memcpy(&last.w, &link, 4);
 			node32.push_back(last);
+			{
+				// quantised node (32 bytes, layout: device_layout.hpp).  The centre's x carries link bits 16..23 in its
+				// low mantissa byte; the box is widened by that displacement so that it still contains FCL's box.
+				const uint32_t raw = link >= 0 ? (uint32_t)link : (0x800000u | (uint32_t)(-(link + 1)));
+				float cq[3] = {(float)(C[0] - m.ctr[0]), (float)(C[1] - m.ctr[1]), (float)(C[2] - m.ctr[2])};
+				uint32_t cxb;
+				std::memcpy(&cxb, &cq[0], 4);
+				cxb = (cxb & 0xffffff00u) | ((raw >> 16) & 0xffu);
+				std::memcpy(&cq[0], &cxb, 4);
+				const double dc = std::fabs((double)cq[0] - (C[0] - m.ctr[0])) + std::fabs((double)cq[1] - (C[1] - m.ctr[1])) +
+				                  std::fabs((double)cq[2] - (C[2] - m.ctr[2]));
+				uint16_t hx[6], he[3];
+				for (int k = 0; k < 6; ++k) hx[k] = float_to_half((float)A[k], false);  // axis0, axis1; axis2 = axis0 x axis1
+				for (int k = 0; k < 3; ++k) he[k] = float_to_half(round_up_f32((E[k] + dc) * (1.0 + 1e-6)), true);
+				uint4 q0, q1;
+				q0.x = hx[0] | ((uint32_t)hx[1] << 16);
+				q0.y = hx[2] | ((uint32_t)hx[3] << 16);
+				q0.z = hx[4] | ((uint32_t)hx[5] << 16);
+				q0.w = he[0] | ((uint32_t)he[1] << 16);
+				q1.x = he[2] | ((raw & 0xffffu) << 16);
+				std::memcpy(&q1.y, &cq[0], 4);
+				std::memcpy(&q1.z, &cq[1], 4);
+				std::memcpy(&q1.w, &cq[2], 4);
+				nodeq.push_back(q0);
+				nodeq.push_back(q1);
+			}
 
 			for (int k = 0; k < 9; ++k) node64.push_back(A[k]);
 			for (int k = 0; k < 3; ++k) node64.push_back(C[k]);
@@ -162,7 +242,7 @@ struct HostPack {
 				chain.clear();
 				for (int32_t v = (int32_t)i; v >= 0; v = parent[v]) chain.push_back((uint32_t)v);
 				uint32_t *dst = &anc[m.anc_base + (size_t)prim * b.depth];
-				for (size_t l = 0; l < chain.size(); ++l) dst[l] = chain[chain.size() - 1 - l];
+				for (size_t l = 0; l < chain.size(); ++l) dst[l] = newid[chain[chain.size() - 1 - l]];
 				double mu = DBL_MAX;
 				for (uint32_t v : chain) mu = std::min(mu, node_mu[v]);
 				mu_chain[mu_base + prim] = round_down_f32(mu);
@@ -309,6 +389,7 @@ struct DevBuf {
 
 struct DevPack {
 	DevBuf<float4> node32, tri32;
+	DevBuf<uint4> nodeq;
 	DevBuf<double> node64, tri64;
 	DevBuf<uint32_t> anc;
 	DevBuf<float> mu_chain;
@@ -316,6 +397,7 @@ struct DevPack {
 	cudaError_t upload(const HostPack &h, cudaStream_t s) {
 		cudaError_t e;
 		if ((e = node32.upload(h.node32, s)) != cudaSuccess) return e;
+		if ((e = nodeq.upload(h.nodeq, s)) != cudaSuccess) return e;
 		if ((e = tri32.upload(h.tri32, s)) != cudaSuccess) return e;
 		if ((e = node64.upload(h.node64, s)) != cudaSuccess) return e;
 		if ((e = tri64.upload(h.tri64, s)) != cudaSuccess) return e;
@@ -323,9 +405,10 @@ struct DevPack {
 		if ((e = mu_chain.upload(h.mu_chain, s)) != cudaSuccess) return e;
 		return models.upload(h.models, s);
 	}
-	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, tri64.p, anc.p, mu_chain.p, models.p}; }
+	ModelPack view() const { return ModelPack{node32.p, tri32.p, node64.p, tri64.p, anc.p, mu_chain.p, models.p, nodeq.p}; }
 	void release() {
 		node32.release();
+		nodeq.release();
 		tri32.release();
 		node64.release();
 		tri64.release();
@@ -335,7 +418,12 @@ struct DevPack {
 	}
 };
 
-constexpr int kPipe = 2;      // ping-pong staging sets per device
+#ifndef MPTCC_PIPE
+#define MPTCC_PIPE 4
+#endif
+constexpr int kPipe = MPTCC_PIPE;  // staging sets (pose buffer, verdict words, candidate list, stream) per device: the sub-batches
+                                   // of a call rotate over them, so the copies of the next sub-batches are in flight
+                                   // while the kernels of the previous ones run
 constexpr size_t kSmallBytes = 256 << 10;  // pose bytes up to which a blocking call takes the zero-copy path
 constexpr int kInFlight = 4;  // mptcc_submit_poses calls that may be outstanding before submit waits for the oldest
 
@@ -344,12 +432,17 @@ struct SplitBufs {
 	DevBuf<float4> rec;
 	DevBuf<double> rel;
 	DevBuf<uint32_t> obj, pose;
-	DevBuf<unsigned int> ctl;  // [0] cand_total, [1] overflow, [2] narrowphase batch counter
+	DevBuf<uint2> base;        // node_base / tri_base of each candidate's environment model
+	DevBuf<uint4> xq;          // exact-pass queue (np2_kernels.cu)
+	DevBuf<unsigned int> ctl;  // [0] cand_total, [1] overflow flags (1 = list full, 2 = non-rigid pose), [2] narrowphase
+	                           // batch counter, [3] exact-queue length
 	void release() {
 		rec.release();
 		rel.release();
 		obj.release();
 		pose.release();
+		base.release();
+		xq.release();
 		ctl.release();
 	}
 };
@@ -357,8 +450,9 @@ struct SplitBufs {
 struct Device {
 	int id = 0;
 	int sm_count = 0;
-	cudaStream_t stream[kPipe] = {nullptr, nullptr};
-	cudaEvent_t ev0[kPipe] = {nullptr, nullptr}, ev1[kPipe] = {nullptr, nullptr};
+	size_t l2_persist_max = 0, l2_window_max = 0;  // persisting-L2 carve-out / access policy window limits of the device
+	cudaStream_t stream[kPipe] = {};
+	cudaEvent_t ev0[kPipe] = {}, ev1[kPipe] = {};
 	DevPack env, agent;
 	DevBuf<DevObject> objects;
 	DevBuf<double> obj_aabb;
@@ -371,7 +465,7 @@ struct Device {
 	DevBuf<unsigned long long> counters;
 	DevBuf<uint32_t> work_user;  // work counter of the device-buffer entry point
 	SplitBufs split[kPipe + 2];  // staging sets, device-buffer entry point, edge entry point
-	cudaEvent_t phase_ev[4] = {nullptr, nullptr, nullptr, nullptr};  // option time_phases: around the pipeline kernels
+	cudaEvent_t phase_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // option time_phases: around the pipeline kernels
 	// on-device edge interpolation (mptcc_check_omni_edges)
 	DevBuf<double> edge_in;
 	DevBuf<unsigned long long> edge_off;
@@ -387,6 +481,7 @@ struct Device {
 	cudaEvent_t done[kInFlight][kPipe] = {};
 	unsigned int *ctl_h[kInFlight] = {};
 	size_t used[kInFlight] = {};
+	bool split_ran[kPipe] = {};  // the last job enqueued on stream k went through the split pipeline
 };
 
 }  // namespace
@@ -401,6 +496,7 @@ struct mptcc_ctx {
 	std::vector<uint32_t> link_model_h;
 	std::vector<DevObject> self_objects_h;
 	bool env_set = false, agent_set = false;
+	bool env_q_ok = true, agent_q_ok = true;  // every model small enough for the 24-bit links of the quantised nodes
 	std::string err;
 	bool count = false;
 	long opt_ppw = 0;           // 0 = auto
@@ -416,6 +512,10 @@ struct mptcc_ctx {
 	long opt_near_first = 1;
 	long opt_long_batches = -1;      // narrowphase batches of 128 instead of 96 candidates: -1 = by launch size
 	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
+	long opt_np2 = 0;                // 1 = second-generation narrowphase (np2_kernels.cu): same speed on C5, see DESIGN.md section 5
+	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
+	long opt_qnode = 0;              // np2: traverse the 32-byte quantised nodes (0 = the 64-byte fp32 nodes)
+	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
 	mptcc_counters ctr{};
 	uint64_t submitted = 0, completed = 0;  // tickets of mptcc_submit_poses
 	int ctas_per_sm_cached = -1;
@@ -541,6 +641,8 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 	CU(sb.rel.reserve(12 * cap64));
 	CU(sb.obj.reserve(cap64));
 	CU(sb.pose.reserve(cap64));
+	CU(sb.base.reserve(cap64));
+	CU(sb.xq.reserve(cap64));
 	CU(sb.ctl.reserve(4));
 	return MPTCC_OK;
 }
@@ -567,7 +669,9 @@ int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, int grid
 }
 
 int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses, int fmt, uint32_t *d_bits,
-                   uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr, bool whole_words = false) {
+                   uint32_t *d_work, cudaStream_t s, SplitBufs *sb = nullptr, bool whole_words = false,
+                   bool *ran_split = nullptr) {
+	if (ran_split) *ran_split = false;
 	KernelParams kp;
 	fill_params(ctx, d, kp);
 	const int grid = grid_for(ctx, d);
@@ -581,6 +685,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 	const bool split = sb != nullptr && ctx->opt_split && ctx->link_model_h.size() == 1 && n >= (uint64_t)ctx->opt_split_min &&
 	                   n < (1ull << 32) && !ctx->objects_h.empty();
 	if (split) {
+		if (ran_split) *ran_split = true;
 		const uint64_t cap64 = std::min<uint64_t>(n * (uint64_t)ctx->opt_split_cap, 0xfffffff0ull);
 		{
 			const int rrc = reserve_split(ctx, *sb, n);
@@ -594,6 +699,20 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		kp.overflow = sb->ctl.p + 1;
 		kp.work_counter2 = sb->ctl.p + 2;
 		kp.cand_cap = (unsigned int)cap64;
+		const bool np2 = ctx->opt_np2 != 0;
+		kp.cand_base = sb->base.p;
+		kp.xq = sb->xq.p;
+		kp.xq_total = sb->ctl.p + 3;
+		kp.xq_cap = (unsigned int)cap64;
+		{
+			// top of the agent tree staged in shared memory: whole sibling pairs only (odd count)
+			const DevModel &am = ctx->agent_h.models[ctx->link_model_h[0]];
+			uint32_t top = std::min<uint32_t>(2u * am.num_tris - 1u, (ctx->opt_qnode && ctx->env_q_ok) ? kAgentTopMaxQ : kAgentTopMax);
+			kp.qnode = (ctx->opt_qnode && ctx->env_q_ok) ? 1u : 0u;
+			if (ctx->opt_agent_top >= 0) top = std::min<uint32_t>(top, (uint32_t)ctx->opt_agent_top);
+			if (top && top % 2 == 0) --top;
+			kp.agent_top = top;
+		}
 		CU(cudaMemsetAsync(sb->ctl.p, 0, 4 * sizeof(unsigned int), s));
 		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 		CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
@@ -602,23 +721,50 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			for (auto &ev : d.phase_ev)
 				if (!ev) CU(cudaEventCreate(&ev));
 		if (timed) CU(cudaEventRecord(d.phase_ev[0], s));
-		int e = launch_broadphase(kp, d.sm_count, ctx->count, s);
+		int e = launch_broadphase(kp, d.sm_count, ctx->count, np2, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "broadphase_kernel launch");
 		if (timed) CU(cudaEventRecord(d.phase_ev[1], s));
 		// ~1.4 candidates per pose-set on the benchmark scenes: long batches once every resident warp (2 CTAs x 8
 		// warps per SM) can expect at least four of them
 		const bool long_batches = ctx->opt_long_batches == 1 ||
 		                          (ctx->opt_long_batches < 0 && n >= (uint64_t)d.sm_count * 16u * 128u * 3u);
-		e = launch_narrowphase(kp, d.sm_count, ctx->count, long_batches, s);
-		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase_kernel launch");
-		if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
+		if (ctx->opt_l2_persist && d.l2_persist_max > 0) {
+			// keep (a fraction of) the environment's traversal nodes in the persisting part of L2 while the narrowphase runs
+			cudaStreamAttrValue av;
+			std::memset(&av, 0, sizeof av);
+			const size_t bytes = kp.qnode ? d.env.nodeq.n * sizeof(uint4) : d.env.node32.n * sizeof(float4);
+			av.accessPolicyWindow.base_ptr = kp.qnode ? (void *)d.env.nodeq.p : (void *)d.env.node32.p;
+			av.accessPolicyWindow.num_bytes = std::min(bytes, d.l2_window_max);
+			av.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)d.l2_persist_max / (double)std::max<size_t>(1, av.accessPolicyWindow.num_bytes));
+			av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+			av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+			CU(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
+		}
+		if (np2) {
+			e = launch_narrowphase2(kp, d.sm_count, ctx->count, long_batches, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase2_kernel launch");
+			if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
+			e = launch_exact(kp, d.sm_count, ctx->count, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "exact_kernel launch");
+			ctx->ctr.n_kernel_launches++;
+		} else {
+			e = launch_narrowphase(kp, d.sm_count, ctx->count, long_batches, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase_kernel launch");
+			if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
+		}
+		if (timed) CU(cudaEventRecord(d.phase_ev[3], s));
+		if (ctx->opt_l2_persist && d.l2_persist_max > 0) {
+			cudaStreamAttrValue av;
+			std::memset(&av, 0, sizeof av);
+			CU(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));  // num_bytes = 0: window off
+		}
 		// overflow fall-back: the fused kernel returns at once unless the candidate list overflowed
 		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
 		kp.run_if = kp.overflow;
 		kp.ppw_log2 = 4;  // atomicOr into the words the split kernels already wrote
 		e = launch_collide(kp, grid, ctx->count, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel (fall-back) launch");
-		if (timed) CU(cudaEventRecord(d.phase_ev[3], s));
+		if (timed) CU(cudaEventRecord(d.phase_ev[4], s));
 		ctx->ctr.n_kernel_launches += 3;
 		ctx->ctr.n_pose_sets += n;
 		return enqueue_self(ctx, d, kp, grid, s);
@@ -660,7 +806,13 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 		if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) return MPTCC_ERR_NO_DEVICE;
 		if (prop.major != 10) return MPTCC_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
 		d.sm_count = prop.multiProcessorCount;
+		d.l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
+		d.l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
 		if (cudaSetDevice(d.id) != cudaSuccess) return MPTCC_ERR_CUDA;
+		if (d.l2_persist_max > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d.l2_persist_max) != cudaSuccess) {
+			cudaGetLastError();
+			d.l2_persist_max = 0;
+		}
 		for (int k = 0; k < kPipe; ++k) {
 			if (cudaStreamCreateWithFlags(&d.stream[k], cudaStreamNonBlocking) != cudaSuccess) return MPTCC_ERR_CUDA;
 			if (cudaEventCreate(&d.ev0[k]) != cudaSuccess || cudaEventCreate(&d.ev1[k]) != cudaSuccess) return MPTCC_ERR_CUDA;
@@ -673,7 +825,7 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 				return MPTCC_ERR_CUDA;
 		}
 		if (cudaHostAlloc(reinterpret_cast<void **>(&d.small_in), kSmallBytes, cudaHostAllocMapped) != cudaSuccess ||
-		    cudaHostAlloc(reinterpret_cast<void **>(&d.small_out), kSmallBytes / 56 / 8 + 64, cudaHostAllocMapped) != cudaSuccess)
+		    cudaHostAlloc(reinterpret_cast<void **>(&d.small_out), kSmallBytes / 24 / 8 + 64, cudaHostAllocMapped) != cudaSuccess)
 			return MPTCC_ERR_CUDA;
 		if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_in_dev), d.small_in, 0) != cudaSuccess ||
 		    cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_out_dev), d.small_out, 0) != cudaSuccess)
@@ -737,6 +889,7 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 	if (!ctx || n_objects < 0 || (n_objects > 0 && (!meshes || !obj_pose7))) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
 	if (n_objects >= (1 << 26)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
 	ctx->env_h.clear();
+	ctx->env_q_ok = true;
 	ctx->objects_h.clear();
 	ctx->obj_aabb_h.clear();
 	ctx->bp_nodes_h.clear();
@@ -766,6 +919,7 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 			for (auto &t : pool) t.join();
 		}
 		const HostBvh &b = block[(size_t)(i % kBlock)];
+		if (b.num_tris() >= (1u << 22)) ctx->env_q_ok = false;
 		if (!block_ok[(size_t)(i % kBlock)])
 			return fail(ctx, MPTCC_ERR_INVALID, "environment object " + std::to_string(i) + " has an empty mesh");
 		DevObject o;
@@ -862,10 +1016,10 @@ int mptcc_wait(mptcc_ctx *ctx, uint64_t ticket) {
 			CU(cudaSetDevice(d.id));
 			for (size_t k = 0; k < d.used[slot]; ++k) {
 				CU(cudaEventSynchronize(d.done[slot][k]));
-				overflowed = overflowed || d.ctl_h[slot][4 * k + 1] != 0;  // [1] = overflow flag of the last split launch
+				overflowed = overflowed || (d.ctl_h[slot][4 * k + 1] & 1u) != 0;  // [1] = overflow flag of the last split launch
 				if (t == ctx->submitted) {
-					float ms = 0.f;  // device time from the first kernel to the end of the last kernel of this stream
-					if (cudaEventElapsedTime(&ms, d.ev0[k], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
+					float ms = 0.f;  // device time from the first kernel of the call (stream 0) to the end of the last kernel
+					if (cudaEventElapsedTime(&ms, d.ev0[0], d.ev1[k]) == cudaSuccess) d.last_ms = std::max(d.last_ms, ms);
 				}
 			}
 			d.used[slot] = 0;
@@ -882,9 +1036,9 @@ int mptcc_check_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt, 
 	// Planner-sized calls (one edge, a few hundred pose-sets): no copies are enqueued at all -- the poses are put in
 	// pinned host memory the fused kernel reads in place, the verdict words are stored straight into pinned
 	// memory, and the only CUDA calls are one 4-byte memset, the launch and the synchronise.
-	if (ctx && n > 0 && poses && verdict_bits && (fmt == MPTCC_POSE_RT12 || fmt == MPTCC_POSE_TQ7) &&
+	if (ctx && n > 0 && poses && verdict_bits && (fmt >= MPTCC_POSE_RT12 && fmt <= MPTCC_POSE_XYZCS) &&
 	    ctx->submitted == ctx->completed && ctx->opt_ppw == 0 && !ctx->opt_self_collision && !ctx->devs.empty()) {
-		const size_t bytes = n * (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size() * sizeof(double);
+		const size_t bytes = n * pose_rec_len((unsigned)fmt) * ctx->link_model_h.size() * sizeof(double);
 		if (bytes <= kSmallBytes && check_ready(ctx) == MPTCC_OK) {
 			Device &d = ctx->devs[0];
 			CU(cudaSetDevice(d.id));
@@ -907,7 +1061,7 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 	int rc = check_ready(ctx);
 	if (rc != MPTCC_OK) return rc;
 	if (!ticket) return fail(ctx, MPTCC_ERR_INVALID, "null ticket");
-	if (fmt != MPTCC_POSE_RT12 && fmt != MPTCC_POSE_TQ7) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
+	if (fmt < MPTCC_POSE_RT12 || fmt > MPTCC_POSE_XYZCS) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
 	*ticket = ctx->submitted;  // an empty batch completes with whatever is outstanding
 	if (n == 0) return MPTCC_OK;
 	if (!poses || !verdict_bits) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
@@ -916,7 +1070,7 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		if (rc != MPTCC_OK) return rc;
 	}
 	const int tslot = (int)(ctx->submitted % kInFlight);
-	const size_t rec = (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size();  // doubles per pose-set
+	const size_t rec = pose_rec_len((unsigned)fmt) * ctx->link_model_h.size();  // doubles per pose-set
 	const uint64_t n_words = (n + 31) / 32;
 	const size_t nd = ctx->devs.size();
 	// contiguous word-aligned slices per device, cut into sub-batches that ping-pong over two streams
@@ -970,8 +1124,10 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 			CU(cudaSetDevice(d.id));
 			CU(cudaMemcpyAsync(d.poses[k].p, poses + p0 * rec, sizeof(double) * cnt * rec, cudaMemcpyHostToDevice, d.stream[k]));
 			if (ji < (size_t)kPipe) CU(cudaEventRecord(d.ev0[k], d.stream[k]));  // first kernel of this stream
-			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k], &d.split[k]);
+			bool ran_split = false;
+			rc = enqueue_kernel(ctx, d, cnt, d.poses[k].p, fmt, d.bits[k].p, d.work[k].p, d.stream[k], &d.split[k], false, &ran_split);
 			if (rc != MPTCC_OK) return rc;
+			d.split_ran[k] = ran_split;  // (the last job of this stream counts: its flags are the ones read back)
 			CU(cudaEventRecord(d.ev1[k], d.stream[k]));  // re-recorded by every job: the last one counts
 			CU(cudaMemcpyAsync(verdict_bits + jb.w0, d.bits[k].p, sizeof(uint32_t) * (jb.w1 - jb.w0), cudaMemcpyDeviceToHost,
 			                   d.stream[k]));
@@ -986,7 +1142,7 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		const size_t used = std::min<size_t>(jobs[di].size(), kPipe);
 		for (size_t k = 0; k < used; ++k) {
 			d.ctl_h[tslot][4 * k + 1] = 0;
-			if (d.split[k].ctl.p)
+			if (d.split[k].ctl.p && d.split_ran[k])  // (a stale flag of an earlier launch must not grow the list again)
 				CU(cudaMemcpyAsync(d.ctl_h[tslot] + 4 * k, d.split[k].ctl.p, sizeof(unsigned int) * 4, cudaMemcpyDeviceToHost,
 				                   d.stream[k]));
 			CU(cudaEventRecord(d.done[tslot][k], d.stream[k]));
@@ -1006,7 +1162,7 @@ int mptcc_check_segments(mptcc_ctx *ctx, uint64_t n_segments, const uint64_t *se
 	for (uint64_t s = 0; s < n_segments; ++s)
 		if (seg_begin[s + 1] < seg_begin[s]) return fail(ctx, MPTCC_ERR_INVALID, "seg_begin must be non-decreasing");
 	std::vector<uint32_t> bits((n + 31) / 32, 0u);
-	const size_t rec = (fmt == MPTCC_POSE_TQ7 ? 7 : 12) * ctx->link_model_h.size();
+	const size_t rec = pose_rec_len((unsigned)fmt) * ctx->link_model_h.size();
 	const int rc = mptcc_check_poses(ctx, n, poses ? poses + first * rec : nullptr, fmt, bits.data());
 	if (rc != MPTCC_OK) return rc;
 	for (uint64_t s = 0; s < n_segments; ++s) {
@@ -1059,7 +1215,7 @@ int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start
 		CU(cudaStreamSynchronize(s));  // the host vector `off` and the device buffers are reused
 		CU(d.edge_in.reserve(6 * ne));
 		CU(d.edge_off.reserve(ne + 1));
-		CU(d.edge_poses.reserve(12 * np));
+		CU(d.edge_poses.reserve(3 * np));
 		CU(d.edge_bits.reserve((np + 31) / 32));
 		CU(d.edge_safe.reserve(ne));
 		CU(d.edge_work.reserve(1));
@@ -1067,7 +1223,7 @@ int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start
 		CU(cudaMemcpyAsync(d.edge_off.p, off.data(), sizeof(unsigned long long) * (ne + 1), cudaMemcpyHostToDevice, s));
 		int e = launch_expand_omni_edges(d.edge_in.p, d.edge_off.p, ne, np, dt, d.edge_poses.p, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "expand_omni_edges launch");
-		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_RT12, d.edge_bits.p, d.edge_work.p, s, &d.split[kPipe + 1]);
+		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_T3, d.edge_bits.p, d.edge_work.p, s, &d.split[kPipe + 1]);
 		if (rc != MPTCC_OK) return rc;
 		e = launch_reduce_segments(d.edge_bits.p, d.edge_off.p, ne, d.edge_safe.p, s);
 		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "reduce_segments launch");
@@ -1083,7 +1239,7 @@ int mptcc_check_poses_device(mptcc_ctx *ctx, int slot, uint64_t n, const double 
 	int rc = check_ready(ctx);
 	if (rc != MPTCC_OK) return rc;
 	if (slot < 0 || slot >= (int)ctx->devs.size()) return fail(ctx, MPTCC_ERR_INVALID, "bad device slot");
-	if (fmt != MPTCC_POSE_RT12 && fmt != MPTCC_POSE_TQ7) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
+	if (fmt < MPTCC_POSE_RT12 || fmt > MPTCC_POSE_XYZCS) return fail(ctx, MPTCC_ERR_INVALID, "unknown pose format");
 	if (n == 0) return MPTCC_OK;
 	if (!d_poses || !d_bits) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
 	Device &d = ctx->devs[slot];
@@ -1156,13 +1312,13 @@ int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms) {
 	return MPTCC_OK;
 }
 
-int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms3) {
-	if (!ctx || !ms3 || slot < 0 || slot >= (int)ctx->devs.size()) return MPTCC_ERR_INVALID;
+int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4) {
+	if (!ctx || !ms4 || slot < 0 || slot >= (int)ctx->devs.size()) return MPTCC_ERR_INVALID;
 	Device &d = ctx->devs[slot];
 	if (!d.phase_ev[0]) return fail(ctx, MPTCC_ERR_STATE, "no timed split-pipeline launch yet (option time_phases)");
 	CU(cudaSetDevice(d.id));
-	CU(cudaEventSynchronize(d.phase_ev[3]));
-	for (int k = 0; k < 3; ++k) CU(cudaEventElapsedTime(ms3 + k, d.phase_ev[k], d.phase_ev[k + 1]));
+	CU(cudaEventSynchronize(d.phase_ev[4]));
+	for (int k = 0; k < 4; ++k) CU(cudaEventElapsedTime(ms4 + k, d.phase_ev[k], d.phase_ev[k + 1]));
 	return MPTCC_OK;
 }
 
@@ -1179,6 +1335,15 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 		ctx->opt_long_batches = value < 0 ? -1 : (value != 0);
 	} else if (k == "self_collision") {
 		ctx->opt_self_collision = value != 0;
+	} else if (k == "np2") {
+		ctx->opt_np2 = value != 0;
+	} else if (k == "l2_persist") {
+		ctx->opt_l2_persist = value != 0;
+	} else if (k == "qnode") {
+		ctx->opt_qnode = value != 0;
+	} else if (k == "agent_top") {
+		if (value < -1) return fail(ctx, MPTCC_ERR_INVALID, "agent_top: -1 (auto) or a node count");
+		ctx->opt_agent_top = value;
 	} else if (k == "near_first") {
 		ctx->opt_near_first = value != 0;
 	} else if (k == "steal_bottom") {

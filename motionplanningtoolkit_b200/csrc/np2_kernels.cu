@@ -1,0 +1,660 @@
+// np2_kernels.cu -- narrowphase of the split pipeline, second generation (round 2), plus the exact-pass kernel.
+//
+//   narrowphase2_kernel : persistent warps take batches of candidates (pose-set, environment object) from the list
+//                         the broadphase kernel wrote and run the conservative fp32 BVH-vs-BVH traversal.
+//   exact_kernel        : re-decides, in fp64 with FCL's operation order, the few leaf pairs the fp32 triangle
+//                         filter could not settle (and replays FCL's OBB path where the certificate does not hold).
+//
+// What changed against narrowphase_kernel (split_kernels.cu), and why:
+//   * TMA-staged tree top.  The agent's nodes are numbered breadth-first (HostPack::add, bfs = true), so the top
+//     levels are one contiguous block; one elected thread per CTA pulls them into shared memory with
+//     cp.async.bulk (SASS UBLKCP) completing on an mbarrier.  Agent-side node fetches with index < agent_top are
+//     LDS instead of per-lane global gathers (the L1 data pipe, one wavefront per 32-byte sector per lane, is
+//     what the round-1 kernel ran out of).
+//   * Child-frame SAT with a shared half.  A traversal step tests the two children of one tree against one node
+//     of the other.  The test is evaluated in the frame of the CHILD box: W = Ry [S axes], w = Ry cS + Ty are
+//     computed once per step from the stationary node S, then per child G = C^T W, t = C^T (w - cC).  When the
+//     children are agent nodes, (Ry, Ty) is the inverse relative transform (R^T, -R^T T), stored in the candidate
+//     record by the broadphase kernel (fp64, rounded once).  One code path for both descent directions: no
+//     role selects (46 of 302 instructions per test in round 1), 36 instead of 75 set-up FMAs per test.
+//     The inverse is only the inverse for a rigid R; the broadphase kernel measures |R^T R - I| in fp64 and hands
+//     launches with a non-rigid pose to the fused kernel (overflow flag = 2).
+//   * No fp64 in the hot kernel.  Leaf pairs that need FCL's exact arithmetic are appended to a queue and
+//     processed by exact_kernel afterwards, so the traversal kernel carries no fp64 code, no fp64 shared
+//     scratch and fewer registers.
+#include <cuda_fp16.h>
+
+#include "collide_device.cuh"
+#include "launch_cache.hpp"
+
+namespace mptcc {
+namespace {
+
+#ifndef MPTCC_NP2_WARPS
+#define MPTCC_NP2_WARPS 16
+#endif
+#ifndef MPTCC_NP2_CTAS
+#define MPTCC_NP2_CTAS 1
+#endif
+#ifndef MPTCC_NP2_BATCH
+#define MPTCC_NP2_BATCH 96
+#endif
+#ifndef MPTCC_NP2_BATCH_LONG
+#define MPTCC_NP2_BATCH_LONG 128
+#endif
+constexpr int kNp2Warps = MPTCC_NP2_WARPS;
+constexpr int kNp2Batch = MPTCC_NP2_BATCH, kNp2BatchLong = MPTCC_NP2_BATCH_LONG;
+constexpr unsigned kTopBytes = kAgentTopMaxQ * 32u > kAgentTopMax * 64u ? kAgentTopMaxQ * 32u : kAgentTopMax * 64u;  // staged agent nodes
+constexpr unsigned kTopRegion = (kTopBytes + 8u + 127u) & ~127u;  // + the mbarrier, rounded for alignment
+
+struct Np2Mem {
+	uint2 *leafq;             // [kLeafQueueCap] (env prim, agent prim | cand << 24)
+	float4 *cand;             // [BATCH][4] R(9) T(3) Tinv(3) S, swizzled with rec_at
+	uint2 *cand_base;         // [BATCH] node_base, tri_base of the candidate's environment model
+	uint32_t *cand_pose;      // [BATCH] pose-set index
+	unsigned char *cand_slot; // [BATCH] slot = batch index of the first candidate of the same pose-set
+	unsigned char *dead;      // [BATCH] per slot: pose-set already in collision
+	unsigned char *donor;     // [32]
+	double *rel;              // [16] fp64 relative transform of the pair being re-decided exactly
+};
+
+__host__ __device__ constexpr unsigned np2_warp_smem_bytes(unsigned batch) {
+	return kLeafQueueCap * 8u + 16u * 8u + batch * 64u + batch * 8u + batch * 4u + batch + batch + 32u;
+}
+
+struct Node {
+	float4 v0, v1, v2, v3;  // (axis0, c.x) (axis1, c.y) (axis2, c.z) (extent, link)
+};
+__device__ __forceinline__ Node node_global(const float4 *p) {
+#ifdef MPTCC_NODE_EL
+	const F8 a = ldg256_evict_last(p), b = ldg256_evict_last(p + 2);
+#else
+	const F8 a = ldg256(p), b = ldg256(p + 2);
+#endif
+	return Node{a.a, a.b, b.a, b.b};
+}
+__device__ __forceinline__ Node node_shared(const float4 *p) { return Node{p[0], p[1], p[2], p[3]}; }
+
+// Quantised node (device_layout.hpp, nodeq) -> Node.  v3.w carries the link as the int the rest of the code expects.
+__device__ __forceinline__ Node node_decode(const uint4 q0, const uint4 q1) {
+	const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q0.x));  // axis0.x, axis0.y
+	const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&q0.y));  // axis0.z, axis1.x
+	const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&q0.z));  // axis1.y, axis1.z
+	const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&q0.w));  // extent.x, extent.y
+	const float ez = __half2float(__ushort_as_half((unsigned short)(q1.x & 0xffffu)));
+	const uint32_t raw = (q1.x >> 16) | ((q1.y & 0xffu) << 16);
+	const int link = (raw & 0x800000u) ? -(int)(raw & 0x7fffffu) - 1 : (int)raw;
+	Node n;
+	n.v0 = make_float4(a.x, a.y, b.x, __uint_as_float(q1.y));
+	n.v1 = make_float4(b.y, c.x, c.y, __uint_as_float(q1.z));
+	n.v2 = make_float4(a.y * c.y - b.x * c.x, b.x * b.y - a.x * c.y, a.x * c.x - a.y * b.y, __uint_as_float(q1.w));
+	n.v3 = make_float4(e.x, e.y, ez, __int_as_float(link));
+	return n;
+}
+__device__ __forceinline__ Node qnode_global(const uint4 *p) {
+	uint4 q0, q1;
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w)
+	    : "l"(p));
+	return node_decode(q0, q1);
+}
+__device__ __forceinline__ Node qnode_shared(const uint4 *p) { return node_decode(p[0], p[1]); }
+// A sibling pair (64 contiguous bytes) with two 256-bit loads issued back to back.
+
+// The 15-axis SAT in the frame of box a (extents ea) against box b (extents eb): G(i,j) = a_i . b_j, t = centre of
+// b in a's frame.  One-sided: true only if the boxes are certainly disjoint (margins: DESIGN.md section 6).
+__device__ __forceinline__ bool sat15(const float *G, const float t0, const float t1, const float t2, const float4 ea,
+                                      const float4 eb, const float mg) {
+	float F[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) F[k] = fabsf(G[k]) + 3e-6f;
+	bool dj = false;
+	dj |= fabsf(t0) > ea.x + (F[0] * eb.x + F[1] * eb.y + F[2] * eb.z) + mg;
+	dj |= fabsf(t1) > ea.y + (F[3] * eb.x + F[4] * eb.y + F[5] * eb.z) + mg;
+	dj |= fabsf(t2) > ea.z + (F[6] * eb.x + F[7] * eb.y + F[8] * eb.z) + mg;
+	dj |= fabsf(t0 * G[0] + t1 * G[3] + t2 * G[6]) > eb.x + (F[0] * ea.x + F[3] * ea.y + F[6] * ea.z) + mg;
+	dj |= fabsf(t0 * G[1] + t1 * G[4] + t2 * G[7]) > eb.y + (F[1] * ea.x + F[4] * ea.y + F[7] * ea.z) + mg;
+	dj |= fabsf(t0 * G[2] + t1 * G[5] + t2 * G[8]) > eb.z + (F[2] * ea.x + F[5] * ea.y + F[8] * ea.z) + mg;
+	// a0 x b0..2
+	dj |= fabsf(t2 * G[3] - t1 * G[6]) > ea.y * F[6] + ea.z * F[3] + eb.y * F[2] + eb.z * F[1] + mg;
+	dj |= fabsf(t2 * G[4] - t1 * G[7]) > ea.y * F[7] + ea.z * F[4] + eb.x * F[2] + eb.z * F[0] + mg;
+	dj |= fabsf(t2 * G[5] - t1 * G[8]) > ea.y * F[8] + ea.z * F[5] + eb.x * F[1] + eb.y * F[0] + mg;
+	// a1 x b0..2
+	dj |= fabsf(t0 * G[6] - t2 * G[0]) > ea.x * F[6] + ea.z * F[0] + eb.y * F[5] + eb.z * F[4] + mg;
+	dj |= fabsf(t0 * G[7] - t2 * G[1]) > ea.x * F[7] + ea.z * F[1] + eb.x * F[5] + eb.z * F[3] + mg;
+	dj |= fabsf(t0 * G[8] - t2 * G[2]) > ea.x * F[8] + ea.z * F[2] + eb.x * F[4] + eb.y * F[3] + mg;
+	// a2 x b0..2
+	dj |= fabsf(t1 * G[0] - t0 * G[3]) > ea.x * F[3] + ea.y * F[0] + eb.y * F[8] + eb.z * F[7] + mg;
+	dj |= fabsf(t1 * G[1] - t0 * G[4]) > ea.x * F[4] + ea.y * F[1] + eb.x * F[8] + eb.z * F[6] + mg;
+	dj |= fabsf(t1 * G[2] - t0 * G[5]) > ea.x * F[5] + ea.y * F[2] + eb.x * F[7] + eb.y * F[6] + mg;
+	return dj;
+}
+
+// Stationary half of a step: W = Ry [S axes as columns] (W[3r+j] = Ry.row(r) . s_j), w = Ry cS + Ty.
+struct StepFrame {
+	float W[9], w[3];
+	float s1;  // |Ty|_1 + |cS|_1
+};
+
+// Child half: true => child box C and stationary box S are certainly disjoint.  d2 = squared centre distance.
+// Q: the nodes come from the quantised array.  Their axes are off by <= 2^-12 per component (the third, a cross
+// product, by twice that), so every projection radius the SAT forms from them can be short by a few 1e-4 of the
+// box's size; 8e-3 (esum_C + esum_S) added to the margin covers that with a factor > 2.
+template <bool Q>
+__device__ __forceinline__ bool child_disjoint(const StepFrame &f, const Node &C, const float4 es, float &d2) {
+	float G[9];
+#pragma unroll
+	for (int j = 0; j < 3; ++j) {
+		G[0 + j] = C.v0.x * f.W[j] + C.v0.y * f.W[3 + j] + C.v0.z * f.W[6 + j];
+		G[3 + j] = C.v1.x * f.W[j] + C.v1.y * f.W[3 + j] + C.v1.z * f.W[6 + j];
+		G[6 + j] = C.v2.x * f.W[j] + C.v2.y * f.W[3 + j] + C.v2.z * f.W[6 + j];
+	}
+	const float dx = f.w[0] - C.v0.w, dy = f.w[1] - C.v1.w, dz = f.w[2] - C.v2.w;
+	d2 = dx * dx + dy * dy + dz * dz;
+	const float t0 = C.v0.x * dx + C.v0.y * dy + C.v0.z * dz;
+	const float t1 = C.v1.x * dx + C.v1.y * dy + C.v1.z * dz;
+	const float t2 = C.v2.x * dx + C.v2.y * dy + C.v2.z * dz;
+	// margin = 192 u (|Ty|_1 + |cS|_1 + |cC|_1)
+	float mg = (192.0f * kU) * (f.s1 + (fabsf(C.v0.w) + fabsf(C.v1.w) + fabsf(C.v2.w)));
+	if (Q) mg += 8e-3f * ((C.v3.x + C.v3.y + C.v3.z) + (es.x + es.y + es.z));
+	return sat15(G, t0, t1, t2, C.v3, es, mg);
+}
+
+template <bool COUNT, int BATCH, bool Q>
+__device__ void traverse2(const KernelParams &p, const Np2Mem &wm, const float4 *__restrict__ atop, const DevModel &m2,
+                          int ncand, unsigned batch_first, int lane, unsigned long long *ctr) {
+	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
+	const uint4 *__restrict__ qnodes2 = p.agent.nodeq + 2ull * m2.node_base;
+	const uint4 *__restrict__ qtop = reinterpret_cast<const uint4 *>(atop);
+	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
+	const unsigned lt = (1u << lane) - 1u;
+	const unsigned ktop = p.agent_top;
+	constexpr unsigned M = kLaneStackCap - 1;
+
+	uint2 stk[kLaneStackCap];
+	unsigned top = 0, bot = 0;
+	uint2 cur = make_uint2(0u, 0u);
+	bool has = false;
+	int qhead = 0, lq = 0;
+
+	while (true) {
+		if (!has && top != bot) {
+			cur = stk[--top & M];
+			has = true;
+		}
+		// ---- 1. idle lanes start the next unstarted candidates ------------------------------------------------
+		unsigned im = __ballot_sync(FULL, !has);
+		if (im && qhead < ncand) {
+			const int c = qhead + __popc(im & lt);
+			if (!has && c < ncand) {
+				cur = make_uint2(0u, kPlanSingle | ((unsigned)c << 24));
+				has = true;
+			}
+			qhead += __popc(im);
+			im = __ballot_sync(FULL, !has);
+		}
+		// ---- 2. ... or steal the top pending plan of a busy lane ------------------------------------------------
+		if (im && qhead >= ncand && !p.no_steal) {
+			const unsigned dm = __ballot_sync(FULL, has && top != bot);
+			if (dm) {
+				const int n_thieves = __popc(im), n_donors = __popc(dm);
+				const int drank = __popc(dm & lt);
+				const bool donor = (dm >> lane) & 1u;
+				if (donor) wm.donor[drank] = (unsigned char)lane;
+				__syncwarp();
+				const int r = __popc(im & lt);
+				const bool thief = !has && r < n_donors;
+				const int from = thief ? (int)wm.donor[r] : lane;
+				const bool robbed = donor && drank < n_thieves;
+				uint2 e = make_uint2(0u, 0u);
+				if (robbed) e = p.steal_bottom ? stk[bot++ & M] : stk[--top & M];
+				e.x = __shfl_sync(FULL, e.x, from);
+				e.y = __shfl_sync(FULL, e.y, from);
+				if (thief) {
+					cur = e;
+					has = true;
+				}
+			}
+		}
+		const unsigned am = __ballot_sync(FULL, has);
+		if (am == 0u && lq == 0) break;
+
+		if (lq >= 32 || am == 0u) {
+			// ---- 3. leaf phase: up to 32 triangle pairs ---------------------------------------------------------
+			const int k = lq < 32 ? lq : 32;
+			lq -= k;
+			int verdict = TRI_SEPARATED;
+			bool certified = false;
+			uint2 pr = make_uint2(0u, 0u);
+			unsigned lc = 0, slot = 0;
+			if (lane < k) {
+				pr = wm.leafq[lq + lane];
+				lc = pr.y >> 24;
+				slot = wm.cand_slot[lc];
+				if (!wm.dead[slot]) {
+					const float4 r0 = wm.cand[rec_at(lc, 0)], r1 = wm.cand[rec_at(lc, 1)], r2 = wm.cand[rec_at(lc, 2)],
+					             r3 = wm.cand[rec_at(lc, 3)];
+					RelF x;
+					x.R[0] = r0.x; x.R[1] = r0.y; x.R[2] = r0.z; x.R[3] = r0.w;
+					x.R[4] = r1.x; x.R[5] = r1.y; x.R[6] = r1.z; x.R[7] = r1.w;
+					x.R[8] = r2.x; x.T[0] = r2.y; x.T[1] = r2.z; x.T[2] = r2.w;
+					x.S = r3.w;
+					const uint2 base = wm.cand_base[lc];
+					const float4 *t1 = p.env.tri32 + 3ull * (base.y + pr.x);
+					const float4 *t2 = tris2 + 3ull * (pr.y & 0xffffffu);
+					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
+					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
+					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
+					if (verdict == TRI_INTERSECT && !p.always_replay) {
+						// path certificate, evaluated from the fp32 record: a larger magnitude
+						// only makes it stricter
+						const DevModel &m1 = p.env.models[p.objects[p.cand_obj[batch_first + lc]].model];
+						const double t1n = (double)((fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2])) * 1.000001f);
+						const double mag = t1n + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+						                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
+						                   m1.esum + m2.esum;
+						const double mu = fmin((double)p.env.mu_chain[base.y + pr.x],
+						                       (double)p.agent.mu_chain[m2.tri_base + (pr.y & 0xffffffu)]);
+						certified = mu >= 1e-5 * mag;
+					}
+				}
+			}
+			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
+			if (certified) {  // first contact settles the pose-set
+				wm.dead[slot] = 1;
+				const uint32_t pose = wm.cand_pose[lc];
+				atomicOr(p.verdict_bits + (pose >> 5), 1u << (pose & 31u));
+			}
+#ifndef MPTCC_NP2_DEFER_ALL
+			// Pairs inside the fp32 error band: re-decide them now, in fp64 with FCL's operation order (the 17 axes
+			// over 17 lanes), because a contact found here ends the pose-set's traversal.  Measured on C5: leaving
+			// them all to exact_kernel costs 11 % more OBB tests and 35 % more triangle tests.
+			{
+				unsigned um = __ballot_sync(FULL, verdict == TRI_UNCERTAIN);
+				while (um) {
+					const int from = __ffs(um) - 1;
+					um &= um - 1;
+					const unsigned c = __shfl_sync(FULL, lc, from), sl = __shfl_sync(FULL, slot, from);
+					const uint32_t t1 = __shfl_sync(FULL, pr.x, from), t2 = __shfl_sync(FULL, pr.y, from) & 0xffffffu;
+					if (wm.dead[sl]) {  // settled by an earlier pair of this round (warp-uniform: shared memory)
+						if (lane == from) verdict = TRI_SEPARATED;
+						continue;
+					}
+					if (COUNT) ctr[CTR_EXACT] += 1;
+					const uint2 bs = wm.cand_base[c];
+					const double *rel = exact_rel_from_pose(p, p.objects[p.cand_obj[batch_first + c]],
+					                                        p.poses + (size_t)wm.cand_pose[c] * (pose_rec_len(p.pose_format)), wm.rel, lane);
+					const bool hit = exact_tri_intersect_warp(rel, p.env.tri64 + 9ull * (bs.y + t1),
+					                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
+					if (lane == from) verdict = hit ? TRI_INTERSECT : TRI_SEPARATED;
+					if (hit) {  // certificate with the record's magnitudes; uncertified contacts go to exact_kernel (path replay)
+						if (lane == from && !p.always_replay) {
+							const DevModel &m1 = p.env.models[p.objects[p.cand_obj[batch_first + c]].model];
+							const float4 r2 = wm.cand[rec_at(c, 2)];
+							const double t1n = (double)((fabsf(r2.y) + fabsf(r2.z) + fabsf(r2.w)) * 1.000001f);
+							const double mag = t1n + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+							                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
+							                   m1.esum + m2.esum;
+							const double mu = fmin((double)p.env.mu_chain[bs.y + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
+							if (mu >= 1e-5 * mag) {
+								wm.dead[sl] = 1;
+								const uint32_t pose = wm.cand_pose[c];
+								atomicOr(p.verdict_bits + (pose >> 5), 1u << (pose & 31u));
+								verdict = TRI_SEPARATED;  // settled
+							}
+						}
+						__syncwarp();
+					}
+				}
+			}
+#endif
+			// contacts whose path certificate does not hold (and, with MPTCC_NP2_DEFER_ALL, every pair the filter could
+			// not settle) go to the exact pass
+			const bool defer = verdict != TRI_SEPARATED && !certified;
+			const unsigned dmk = __ballot_sync(FULL, defer);
+			if (dmk) {
+				unsigned qb = 0;
+				if (lane == 0) qb = atomicAdd(p.xq_total, (unsigned)__popc(dmk));
+				qb = __shfl_sync(FULL, qb, 0);
+				if (defer) {
+					const unsigned at = qb + __popc(dmk & lt);
+					if (at < p.xq_cap)
+						p.xq[at] = make_uint4(batch_first + lc, pr.x, pr.y & 0xffffffu, verdict == TRI_INTERSECT ? 1u : 0u);
+					else
+						atomicOr(p.overflow, 1u);  // the fused fall-back recomputes the launch
+				}
+			}
+			__syncwarp();
+			continue;
+		}
+		// ---- 4. node step: both children of the descended tree against the stationary node of the other ----------
+		bool leaf0 = false, leaf1 = false;
+		uint2 lf0 = make_uint2(0u, 0u), lf1 = make_uint2(0u, 0u);
+		unsigned n_tests = 0;
+		if (has) {
+			const uint2 pr = cur;
+			has = false;
+			const unsigned tag = pr.y & 0xff000000u;
+			const unsigned nc = pr.y >> 24;
+			if (wm.dead[wm.cand_slot[nc]]) {
+				top = bot;  // this lane's stack holds one candidate only, and its pose-set already collides
+			} else {
+				const float4 r0 = wm.cand[rec_at(nc, 0)], r1 = wm.cand[rec_at(nc, 1)], r2 = wm.cand[rec_at(nc, 2)],
+				             r3 = wm.cand[rec_at(nc, 3)];
+				const bool single = (pr.y & kPlanSingle) != 0u;
+				const bool env_side = single || (pr.y & kPlanEnv) != 0u;  // the children are environment nodes
+				const uint32_t i2base = pr.y & kPlanIdxMask;
+				const unsigned nb1 = wm.cand_base[nc].x;
+				Node S, C0, C1;
+				if (Q) {
+					const uint4 *qnodes1 = p.env.nodeq + 2ull * nb1;
+					if (env_side) {
+						S = i2base < ktop ? qnode_shared(qtop + 2u * i2base) : qnode_global(qnodes2 + 2ull * i2base);
+						C0 = qnode_global(qnodes1 + 2ull * pr.x);
+						C1 = single ? C0 : qnode_global(qnodes1 + 2ull * pr.x + 2);
+					} else {
+						S = qnode_global(qnodes1 + 2ull * pr.x);
+						if (i2base + 1u < ktop) {
+							C0 = qnode_shared(qtop + 2u * i2base);
+							C1 = qnode_shared(qtop + 2u * i2base + 2);
+						} else {
+							C0 = qnode_global(qnodes2 + 2ull * i2base);
+							C1 = qnode_global(qnodes2 + 2ull * i2base + 2);
+						}
+					}
+				} else {
+					const float4 *nodes1 = p.env.node32 + 4ull * nb1;
+					if (env_side) {
+						S = i2base < ktop ? node_shared(atop + 4u * i2base) : node_global(nodes2 + 4ull * i2base);
+						C0 = node_global(nodes1 + 4ull * pr.x);
+						C1 = single ? C0 : node_global(nodes1 + 4ull * pr.x + 4);
+					} else {
+						S = node_global(nodes1 + 4ull * pr.x);
+						if (i2base + 1u < ktop) {
+							C0 = node_shared(atop + 4u * i2base);
+							C1 = node_shared(atop + 4u * i2base + 4);
+						} else {
+							C0 = node_global(nodes2 + 4ull * i2base);
+							C1 = node_global(nodes2 + 4ull * i2base + 4);
+						}
+					}
+				}
+				// (Ry, Ty): the relative transform when the children are environment nodes, its inverse otherwise
+				StepFrame f;
+				{
+					const float y00 = r0.x, y11 = r1.x, y22 = r2.x;
+					const float y01 = env_side ? r0.y : r0.w, y10 = env_side ? r0.w : r0.y;
+					const float y02 = env_side ? r0.z : r1.z, y20 = env_side ? r1.z : r0.z;
+					const float y12 = env_side ? r1.y : r1.w, y21 = env_side ? r1.w : r1.y;
+					const float ty0 = env_side ? r2.y : r3.x, ty1 = env_side ? r2.z : r3.y, ty2 = env_side ? r2.w : r3.z;
+					f.W[0] = y00 * S.v0.x + y01 * S.v0.y + y02 * S.v0.z;
+					f.W[1] = y00 * S.v1.x + y01 * S.v1.y + y02 * S.v1.z;
+					f.W[2] = y00 * S.v2.x + y01 * S.v2.y + y02 * S.v2.z;
+					f.W[3] = y10 * S.v0.x + y11 * S.v0.y + y12 * S.v0.z;
+					f.W[4] = y10 * S.v1.x + y11 * S.v1.y + y12 * S.v1.z;
+					f.W[5] = y10 * S.v2.x + y11 * S.v2.y + y12 * S.v2.z;
+					f.W[6] = y20 * S.v0.x + y21 * S.v0.y + y22 * S.v0.z;
+					f.W[7] = y20 * S.v1.x + y21 * S.v1.y + y22 * S.v1.z;
+					f.W[8] = y20 * S.v2.x + y21 * S.v2.y + y22 * S.v2.z;
+					const float cx = S.v0.w, cy = S.v1.w, cz = S.v2.w;
+					f.w[0] = y00 * cx + y01 * cy + y02 * cz + ty0;
+					f.w[1] = y10 * cx + y11 * cy + y12 * cz + ty1;
+					f.w[2] = y20 * cx + y21 * cy + y22 * cz + ty2;
+					f.s1 = (fabsf(ty0) + fabsf(ty1) + fabsf(ty2)) + (fabsf(cx) + fabsf(cy) + fabsf(cz));
+				}
+				const int linkS = __float_as_int(S.v3.w);
+				const float sS = S.v3.x * S.v3.x + S.v3.y * S.v3.y + S.v3.z * S.v3.z;
+				uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
+				bool ok0 = false, ok1 = false;
+				float d2_0 = 0.f, d2_1 = 0.f;
+#pragma unroll
+				for (int k = 0; k < 2; ++k) {
+					if (k == 1 && single) break;
+					const Node &C = k == 0 ? C0 : C1;
+					++n_tests;
+					float d2;
+					if (child_disjoint<Q>(f, C, S.v3, d2)) continue;
+					if (k == 0) d2_0 = d2; else d2_1 = d2;
+					const int linkC = __float_as_int(C.v3.w);
+					const float sC = C.v3.x * C.v3.x + C.v3.y * C.v3.y + C.v3.z * C.v3.z;
+					// back to (environment, agent) roles
+					const int link1 = env_side ? linkC : linkS, link2 = env_side ? linkS : linkC;
+					const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
+					const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
+					const bool l1 = link1 < 0, l2 = link2 < 0;
+					if (l1 && l2) {
+						const uint2 lf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)) | tag);
+						if (k == 0) { leaf0 = true; lf0 = lf; } else { leaf1 = true; lf1 = lf; }
+						continue;
+					}
+					// firstOverSecond: descend the environment tree iff l2 || (!l1 && size1 > size2)
+					const float s1 = env_side ? sC : sS, s2 = env_side ? sS : sC;
+					const bool first = l2 || (!l1 && s1 > s2);
+					const uint2 pl = first ? make_uint2((uint32_t)link1, i2 | kPlanEnv | tag) : make_uint2(i1, (uint32_t)link2 | tag);
+					if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
+				}
+				if (ok0 && ok1) {
+					const bool swap = p.near_first && d2_1 < d2_0;
+					cur = swap ? plan1 : plan0;
+					has = true;
+					stk[top++ & M] = swap ? plan0 : plan1;
+				} else if (ok0) {
+					cur = plan0;
+					has = true;
+				} else if (ok1) {
+					cur = plan1;
+					has = true;
+				}
+			}
+		}
+		if (COUNT) {
+			unsigned t = n_tests;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+			ctr[CTR_BV] += t;
+		}
+		{
+			const unsigned lm0 = __ballot_sync(FULL, leaf0);
+			if (leaf0) wm.leafq[lq + __popc(lm0 & lt)] = lf0;
+			lq += __popc(lm0);
+		}
+		const unsigned lm = __ballot_sync(FULL, leaf1);
+		if (leaf1) wm.leafq[lq + __popc(lm & lt)] = lf1;
+		lq += __popc(lm);
+		__syncwarp();
+	}
+}
+
+#ifdef MPTCC_NP2_MAXREG
+#define NP2_BOUNDS __maxnreg__(MPTCC_NP2_MAXREG)
+#else
+#define NP2_BOUNDS __launch_bounds__(kNp2Warps * 32, MPTCC_NP2_CTAS)
+#endif
+
+template <bool COUNT, int BATCH, bool Q>
+__global__ void NP2_BOUNDS narrowphase2_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	float4 *atop = reinterpret_cast<float4 *>(smem_raw);
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+
+	// ---- TMA bulk copy of the agent tree's top levels into shared memory (one thread issues, all wait) ---------
+	const unsigned top_bytes = p.agent_top * (Q ? 32u : 64u);
+	const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw + kTopBytes);
+	if (top_bytes != 0u) {
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(mbar), "r"(1u) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			const void *src = Q ? static_cast<const void *>(p.agent.nodeq + 2ull * m2.node_base)
+			                    : static_cast<const void *>(p.agent.node32 + 4ull * m2.node_base);
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(atop);
+			asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(top_bytes) : "memory");
+			asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+			             "l"(src), "r"(top_bytes), "r"(mbar)
+			             : "memory");
+		}
+	}
+
+	unsigned char *base = smem_raw + kTopRegion + (size_t)warp * np2_warp_smem_bytes(BATCH);
+	Np2Mem wm;
+	wm.leafq = reinterpret_cast<uint2 *>(base);
+	base += kLeafQueueCap * 8;
+	wm.rel = reinterpret_cast<double *>(base);
+	base += 16 * 8;
+	wm.cand = reinterpret_cast<float4 *>(base);
+	base += BATCH * 64;
+	wm.cand_base = reinterpret_cast<uint2 *>(base);
+	base += BATCH * 8;
+	wm.cand_pose = reinterpret_cast<uint32_t *>(base);
+	base += BATCH * 4;
+	wm.cand_slot = base;
+	base += BATCH;
+	wm.dead = base;
+	base += BATCH;
+	wm.donor = base;
+
+	// overflowed list / non-rigid pose: the whole launch belongs to the fused fall-back kernel
+	const bool skip = *p.overflow != 0u;
+	if (top_bytes != 0u) {  // wait for the staged block (every thread observes the phase flip)
+		unsigned done = 0;
+		while (!done)
+			asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+			             : "=r"(done)
+			             : "r"(mbar), "r"(0u)
+			             : "memory");
+	}
+	if (skip) return;
+	const unsigned total = *p.cand_total;
+	unsigned long long ctr[CTR_N];
+#pragma unroll
+	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
+
+	while (true) {
+		unsigned first = 0;
+		if (lane == 0) first = atomicAdd(p.work_counter2, (unsigned)BATCH);
+		first = __shfl_sync(FULL, first, 0);
+		if (first >= total) break;
+		const int n = (int)(total - first < (unsigned)BATCH ? total - first : (unsigned)BATCH);
+		// ---- load the batch ---------------------------------------------------------------------------------------
+		const float4 *src_rec = p.cand_rec + 4ull * first;
+#ifdef MPTCC_LIST_EF
+		for (int i = lane; i < 2 * n; i += 32) {
+			const F8 v = ldg256_evict_first(src_rec + 2 * i);
+			wm.cand[rec_at((unsigned)i >> 1, 2u * ((unsigned)i & 1u))] = v.a;
+			wm.cand[rec_at((unsigned)i >> 1, 2u * ((unsigned)i & 1u) + 1u)] = v.b;
+		}
+#else
+		for (int i = lane; i < 4 * n; i += 32) wm.cand[rec_at((unsigned)i >> 2, (unsigned)i & 3u)] = src_rec[i];
+#endif
+		for (int i = lane; i < n; i += 32) {
+			wm.cand_base[i] = p.cand_base[first + i];
+			wm.cand_pose[i] = p.cand_pose[first + i];
+		}
+		__syncwarp();
+		// ---- pose slots: candidates of one pose-set are adjacent; the slot of a run is the index of its first
+		//      candidate; dead[slot] starts from the verdict bit (another batch may have settled the pose-set) ------
+		unsigned carry = 0;
+		for (int g = 0; g < (n + 31) / 32; ++g) {
+			const int i = 32 * g + lane;
+			const bool valid = i < n;
+			const uint32_t pose = valid ? wm.cand_pose[i] : 0u;
+			const bool start = valid && (i == 0 || wm.cand_pose[i - 1] != pose);
+			const unsigned sm = __ballot_sync(FULL, start);
+			const unsigned upto = sm & (0xffffffffu >> (31 - lane));
+			const unsigned slot = upto ? (unsigned)(32 * g + 31 - __clz((int)upto)) : carry;
+			if (valid) wm.cand_slot[i] = (unsigned char)slot;
+			if (start) wm.dead[i] = (unsigned char)((p.verdict_bits[pose >> 5] >> (pose & 31u)) & 1u);
+			if (sm) carry = (unsigned)(32 * g + 31 - __clz((int)sm));
+		}
+		__syncwarp();
+		traverse2<COUNT, BATCH, Q>(p, wm, atop, m2, n, first, lane, ctr);
+		__syncwarp();
+	}
+	if (COUNT && lane == 0) {
+#pragma unroll
+		for (int i = 0; i < CTR_N; ++i)
+			if (ctr[i]) atomicAdd(p.counters + i, ctr[i]);
+	}
+}
+
+// ---- exact pass: one warp per queued leaf pair -----------------------------------------------------------------
+template <bool COUNT>
+__global__ void __launch_bounds__(256) exact_kernel(const __grid_constant__ KernelParams p) {
+	__shared__ double rel_s[8][16];
+	if (*p.overflow != 0u) return;
+	const int lane = threadIdx.x & 31;
+	const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+	const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+	const unsigned total = min(*p.xq_total, p.xq_cap);
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+	unsigned long long n_exact = 0, n_path = 0;
+	for (unsigned i = warp; i < total; i += n_warps) {
+		const uint4 e = p.xq[i];
+		const uint32_t pose = p.cand_pose[e.x];
+		if ((p.verdict_bits[pose >> 5] >> (pose & 31u)) & 1u) continue;  // settled meanwhile
+		const DevObject &ob = p.objects[p.cand_obj[e.x]];
+		const DevModel &m1 = p.env.models[ob.model];
+		const double *rel = exact_rel_from_pose(p, ob, p.poses + (size_t)pose * (pose_rec_len(p.pose_format)),
+		                                        rel_s[threadIdx.x >> 5], lane);
+		const bool sure = e.w != 0u && !p.always_replay;
+		if (COUNT && !sure) ++n_exact;
+		const bool hit = sure ? true
+		                      : exact_tri_intersect_warp(rel, p.env.tri64 + 9ull * (m1.tri_base + e.y),
+		                                                 p.agent.tri64 + 9ull * (m2.tri_base + e.z), lane);
+		if (!hit) continue;
+		const double mag = fabs(rel[9]) + fabs(rel[10]) + fabs(rel[11]) + m1.cmax1 + m2.cmax1 + m1.esum + m2.esum;
+		const double mu = fmin((double)p.env.mu_chain[m1.tri_base + e.y], (double)p.agent.mu_chain[m2.tri_base + e.z]);
+		bool reached = !p.always_replay && mu >= 1e-5 * mag;
+		if (!reached) {
+			if (COUNT) ++n_path;
+			reached = exact_path_reaches(p, m1, m2, rel, e.y, e.z, lane);
+		}
+		if (reached && lane == 0) atomicOr(p.verdict_bits + (pose >> 5), 1u << (pose & 31u));
+	}
+	if (COUNT && lane == 0) {
+		if (n_exact) atomicAdd(p.counters + CTR_EXACT, n_exact);
+		if (n_path) atomicAdd(p.counters + CTR_PATH, n_path);
+	}
+}
+
+template <class K>
+int launch_np2(K kernel, const KernelParams &p, int sm_count, size_t smem, void *stream) {
+	int per_sm = 0;
+	const cudaError_t e = prepare_kernel(reinterpret_cast<const void *>(kernel), kNp2Warps * 32, smem, &per_sm);
+	if (e != cudaSuccess) return (int)e;
+	if (per_sm < 1) per_sm = 1;
+	kernel<<<sm_count * per_sm, kNp2Warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+	return (int)cudaGetLastError();
+}
+
+}  // namespace
+
+int launch_narrowphase2(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream) {
+#define NP2_LAUNCH(B)                                                                                                  \
+	{                                                                                                                  \
+		const size_t smem = kTopRegion + (size_t)kNp2Warps * np2_warp_smem_bytes(B);                                   \
+		if (p.qnode)                                                                                                   \
+			return count ? launch_np2(narrowphase2_kernel<true, B, true>, p, sm_count, smem, stream)                   \
+			             : launch_np2(narrowphase2_kernel<false, B, true>, p, sm_count, smem, stream);                 \
+		return count ? launch_np2(narrowphase2_kernel<true, B, false>, p, sm_count, smem, stream)                      \
+		             : launch_np2(narrowphase2_kernel<false, B, false>, p, sm_count, smem, stream);                    \
+	}
+	if (long_batches && kNp2BatchLong != kNp2Batch) NP2_LAUNCH(kNp2BatchLong)
+	NP2_LAUNCH(kNp2Batch)
+#undef NP2_LAUNCH
+}
+
+int launch_exact(const KernelParams &p, int sm_count, bool count, void *stream) {
+	cudaStream_t s = static_cast<cudaStream_t>(stream);
+	if (count)
+		exact_kernel<true><<<sm_count * 2, 256, 0, s>>>(p);
+	else
+		exact_kernel<false><<<sm_count * 2, 256, 0, s>>>(p);
+	return (int)cudaGetLastError();
+}
+
+}  // namespace mptcc

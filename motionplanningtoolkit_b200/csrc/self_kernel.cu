@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) self_collide_kernel(cons
 	double *box_a = reinterpret_cast<double *>(smem_raw + (size_t)warp * self_warp_smem_bytes() + warp_smem_bytes());
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
-	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const unsigned rec_len = pose_rec_len(p.pose_format);
 	const unsigned lt = (1u << lane) - 1u;
 	unsigned long long ctr[CTR_N];
 #pragma unroll

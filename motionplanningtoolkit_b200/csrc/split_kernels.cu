@@ -40,7 +40,7 @@ __host__ __device__ constexpr unsigned np_warp_smem_bytes(unsigned batch) {
 	return kLeafQueueCap * 8u + batch * 64u + 16u * 8u + batch * 4u + batch * 4u + batch + 32u;
 }
 
-template <bool COUNT>
+template <bool COUNT, bool NP2>
 __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 	unsigned *pfx = reinterpret_cast<unsigned *>(base);  // [32] first list position of each pose slot's run
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
-	const unsigned rec_len = p.pose_format == 1u ? 7u : 12u;
+	const unsigned rec_len = pose_rec_len(p.pose_format);
 	const bool aligned32 = (reinterpret_cast<unsigned long long>(p.poses) & 31ull) == 0ull;
 	const unsigned lt = (1u << lane) - 1u;
 	const DevModel &m2 = p.agent.models[p.link_model[0]];
@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 					gbase = __shfl_sync(FULL, gbase, 0);
 					__syncwarp();
 					if ((unsigned long long)gbase + (unsigned)ncand > (unsigned long long)p.cand_cap) {
-						if (lane == 0) atomicExch(p.overflow, 1u);  // the fused fall-back recomputes this launch
+						if (lane == 0) atomicOr(p.overflow, 1u);  // the fused fall-back recomputes this launch
 					} else {
 						for (int i = lane; i < ncand; i += 32) {
 							const uint32_t id = wm.cand_ids[i];
@@ -163,14 +163,28 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 							float4 rec[4];
 							double pose[12], rel[12];
 							load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
-							make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
 							float4 *out = p.cand_rec + 4ull * dst;
+							if (NP2) {
+								// (the exact pass of the np2 kernels recomputes the fp64 relative transform from the pose
+								// record: 96 bytes per candidate less to write, and less of the L2 taken from the trees)
+								uint2 mbase;
+								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, nullptr, mbase))
+									atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
+								p.cand_base[dst] = mbase;
+							} else {
+								make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
+								double *orel = p.cand_rel + 12ull * dst;
+								stg256(orel, rel[0], rel[1], rel[2], rel[3]);
+								stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
+								stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
+							}
+#ifdef MPTCC_LIST_EF
+							stg256_evict_first(out, rec[0], rec[1]);
+							stg256_evict_first(out + 2, rec[2], rec[3]);
+#else
 							stg256(out, rec[0], rec[1]);
 							stg256(out + 2, rec[2], rec[3]);
-							double *orel = p.cand_rel + 12ull * dst;
-							stg256(orel, rel[0], rel[1], rel[2], rel[3]);
-							stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
-							stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
+#endif
 							p.cand_obj[dst] = e;
 							p.cand_pose[dst] = (uint32_t)(pose0 + sl);
 						}
@@ -228,7 +242,7 @@ __global__ void NP_BOUNDS narrowphase_kernel(const __grid_constant__ KernelParam
 	const DevModel &m2 = p.agent.models[p.link_model[0]];
 	SplitTrav tv;
 	tv.poses = p.poses;
-	tv.rec_len = p.pose_format == 1u ? 7u : 12u;
+	tv.rec_len = pose_rec_len(p.pose_format);
 	tv.verdict_bits = p.verdict_bits;
 	unsigned long long ctr[CTR_N];
 #pragma unroll
@@ -288,10 +302,13 @@ int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads
 
 }  // namespace
 
-int launch_broadphase(const KernelParams &p, int sm_count, bool count, void *stream) {
+int launch_broadphase(const KernelParams &p, int sm_count, bool count, bool np2, void *stream) {
 	const size_t smem = (size_t)kBpWarpsPerCta * bp_warp_smem_bytes();
-	return count ? launch_persistent(broadphase_kernel<true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
-	             : launch_persistent(broadphase_kernel<false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
+	if (np2)
+		return count ? launch_persistent(broadphase_kernel<true, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
+		             : launch_persistent(broadphase_kernel<false, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
+	return count ? launch_persistent(broadphase_kernel<true, false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
+	             : launch_persistent(broadphase_kernel<false, false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
 }
 
 int launch_narrowphase(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream) {

@@ -113,6 +113,31 @@ def omnidirectional_edge_poses(start, end, dt):
     return np.stack(pts)
 
 
+def omnidirectional_edges_poses(starts, ends, dt):
+    """omnidirectional_edge_poses for many edges at once (same arithmetic, vectorised): returns
+    (translations [P,3], seg_begin [n+1])."""
+    starts, ends = np.asarray(starts, float).reshape(-1, 3), np.asarray(ends, float).reshape(-1, 3)
+    d = ends - starts
+    dist = np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        ratio = np.where(dist > 0, dist / dt, 0.0)
+        it = np.where(ratio >= 1.0, np.minimum(ratio, 4294967295.0), 0.0).astype(np.int64)
+        extra = (it.astype(np.float64) * dt < dist) & (it >= 1)
+        cnt = np.where(it < 1, 2, it + extra)
+        seg = np.concatenate([[0], np.cumsum(cnt)]).astype(np.uint64)
+        e = np.repeat(np.arange(len(cnt)), cnt)
+        i = np.arange(int(seg[-1])) - np.repeat(seg[:-1].astype(np.int64), cnt)
+        step = np.where(dist > 0, dt / dist, 0.0)
+        s = (step[e] * i.astype(np.float64))[:, None]
+        pts = starts[e] + s * d[e]
+    short = it[e] < 1
+    pts[short & (i == 0)] = starts[e][short & (i == 0)]
+    pts[short & (i == 1)] = ends[e][short & (i == 1)]
+    last = (~short) & (i >= it[e])
+    pts[last] = ends[e][last]
+    return pts, seg
+
+
 # ---------------------------------------------------------------------------------------------------
 # procedural meshes
 # ---------------------------------------------------------------------------------------------------

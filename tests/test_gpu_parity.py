@@ -315,3 +315,64 @@ def test_device_resident_buffers_any_alignment(box_scene, n, offset_doubles):
     stream.synchronize()
     got = bits.cpu().numpy().view(np.uint32)
     assert_bits_equal(got, want, n, "device buffers, offset %d doubles" % offset_doubles)
+
+
+@pytest.mark.parametrize("opts", [dict(np2=1), dict(np2=1, qnode=1), dict(np2=1, always_replay=1), dict(np2=1, qnode=1, agent_top=0),
+                                  dict(np2=1, split_cap=1), dict(np2=1, long_batches=0), dict(np2=1, l2_persist=1)])
+def test_second_generation_narrowphase_matches_oracle(built, opts):
+    """np2_kernels.cu (TMA-staged agent tree top, child-frame SAT, exact-pass kernel; optionally the 32-byte
+    quantised nodes) gives the oracle's verdicts on deep trees, incl. forced path replay and the overflow fall-back."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(321)
+    poses = scenes.random_poses_near_objects(rng, 40007, env, 2.0)
+    chk = sc.checker(split=1, split_min=32, **opts)
+    assert_bits_equal(chk.check_poses(poses), sc.oracle_bits(poses), len(poses), "np2 %s" % (opts,))
+    tq = scenes.random_poses_near_objects(rng, 20000, env, 2.0, fmt="tq7")
+    assert_bits_equal(chk.check_poses(tq, capi.POSE_TQ7), sc.oracle_bits(tq, O.POSE_TQ7), len(tq), "np2 TQ7 %s" % (opts,))
+
+
+@pytest.mark.parametrize("qnode", [0, 1])
+def test_second_generation_narrowphase_unit_boxes_and_non_rigid_poses(box_scene, qnode):
+    """Exact-contact cases (touching cubes) and poses whose 3x3 block is not a rotation: the np2 kernel evaluates
+    agent-side tests with the inverse transform, which only exists for rigid poses, so such a launch must fall
+    back to the fused kernel and still give FCL's (formula-defined) verdicts."""
+    rng = scenes.SplitMix64(322)
+    chk = box_scene.checker(split=1, split_min=32, np2=1, qnode=qnode)
+    e = 2.0 ** -52
+    T = np.concatenate([np.array([[1, 0, 0], [1 + e, 0, 0], [1 - e, 0, 0], [0, -1, 0], [1, 1, 1], [1, 1, 1 + e]], float),
+                        np.stack([rng.uniform(40000, -1.6, 1.6) for _ in range(3)], 1)])
+    poses = scenes.translation_poses(T)
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "np2 translations")
+    poses = scenes.random_poses_rt12(rng, 40000, (-1.6,) * 3, (1.6,) * 3)
+    poses[::7, :9] *= 1.25                      # scaled "rotations"
+    poses[5::11, 1] += 0.3                      # sheared
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "np2 non-rigid poses")
+
+
+@pytest.mark.parametrize("opts", [dict(split=0), dict(split=1, split_min=32), dict(split=1, split_min=32, np2=1)])
+def test_compact_pose_formats_equal_rt12(built, opts):
+    """MPTCC_POSE_T3 (x y z = Transform3f(Vec3f)) and MPTCC_POSE_XYZCS (x y z cos sin = the planar Transform3f(R,T) of
+    the blimp and the snake) are the RT12 records with the same entries: identical verdicts, 24 / 40 bytes per pose."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(555)
+    lo, hi = env_bbox(env, 2.0)
+    chk = sc.checker(**opts)
+    T = np.stack([rng.uniform(36001, lo[k], hi[k]) for k in range(3)], 1)
+    want = sc.oracle_bits(scenes.translation_poses(T))
+    assert_bits_equal(chk.check_poses(T, capi.POSE_T3), want, len(T), "T3 %s" % (opts,))
+    th = rng.uniform(len(T), -np.pi, np.pi)
+    xyzcs = np.concatenate([T, np.cos(th)[:, None], np.sin(th)[:, None]], axis=1)
+    want = sc.oracle_bits(scenes._rz_convention(th, T))
+    assert_bits_equal(chk.check_poses(xyzcs, capi.POSE_XYZCS), want, len(T), "XYZCS %s" % (opts,))
+    # planner-sized call (zero-copy path) and multi-link pose-sets
+    assert_bits_equal(chk.check_poses(xyzcs[:10], capi.POSE_XYZCS), sc.oracle_bits(scenes._rz_convention(th[:10], T[:10])), 10, "XYZCS small")
+    box = meshio.load_mptm("unit_box")[0]
+    sc2 = Scene([box], [box] * 3)
+    chk2 = sc2.checker(**{k: v for k, v in opts.items() if k != "np2"})
+    T3 = np.stack([rng.uniform(3 * 9000, -1.7, 1.7) for _ in range(3)], 1)
+    want = sc2.oracle_bits(scenes.translation_poses(T3).reshape(-1, 3, 12))
+    assert_bits_equal(chk2.check_poses(T3.reshape(-1, 3, 3), capi.POSE_T3), want, 9000, "T3 3 links")
