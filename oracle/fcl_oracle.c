@@ -1158,3 +1158,141 @@ int orc_verdicts_bruteforce(const orc_env *env, int n_links, orc_model *const *l
 	}
 	return 0;
 }
+
+/* ---- structure-free oracle, fast form ----------------------------------------------------------------------
+ * Same verdict definition as orc_verdicts_bruteforce (exists object, link with overlapping world AABBs and a
+ * triangle pair for which Intersect::intersect_Triangle holds), made fast enough for the deep trees (blimp merged
+ * vs divider, the C5 scene) by two things that have nothing to do with the BVH, the OBB fit or the OBB test:
+ *   - the pose range is split over pthreads;
+ *   - a triangle pair is only handed to intersect_Triangle if the axis-aligned boxes of the two triangles (agent
+ *     triangle moved into the object's frame with the same R, T) overlap after growing them by `pad` (1e-9 of the
+ *     coordinates' magnitude).  Triangles whose boxes are further apart than that are separated along a coordinate
+ *     axis by far more than fp64 round-off; if FCL's 17-axis test nevertheless reported a contact for such a pair,
+ *     this oracle would say "free" where the BVH oracle says "collides" and the equality test would FAIL, i.e. the
+ *     shortcut cannot hide a disagreement. */
+typedef struct {
+	const orc_env *env;
+	int n_links;
+	orc_model *const *links;
+	const double *poses;
+	int fmt;
+	uint32_t *bits;
+	uint64_t p0, p1;
+	double **tri_box; /* per environment object: [nt][6] triangle boxes in the object's model frame */
+} bf_slice;
+
+static void *bf_run(void *arg) {
+	bf_slice *s = (bf_slice *)arg;
+	const int rl = rec_len(s->fmt);
+	for (uint64_t p = s->p0; p < s->p1; ++p) {
+		int hit = 0;
+		for (int l = 0; l < s->n_links && !hit; ++l) {
+			const orc_model *am = s->links[l];
+			xform at;
+			aabb ab;
+			xform_decode(s->poses + (size_t)rl * ((size_t)p * (size_t)s->n_links + (size_t)l), s->fmt, &at);
+			object_world_aabb(am, &at, &ab);
+			for (int e = 0; e < s->env->n && !hit; ++e) {
+				if (!aabb_overlap(&s->env->box[e], &ab)) continue;
+				const orc_model *em = s->env->models[e];
+				const double *tb = s->tri_box[e];
+				mat3 R;
+				double T[3];
+				relative_transform(&s->env->tf[e], &at, &R, T);
+				for (uint32_t k = 0; k < am->nt && !hit; ++k) {
+					const uint32_t *t2 = am->tri + 3 * (size_t)k;
+					double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, mag = 0.0;
+					for (int c = 0; c < 3; ++c) {
+						double q[3];
+						mat_vec(&R, am->xyz + 3 * (size_t)t2[c], q);
+						for (int a = 0; a < 3; ++a) {
+							const double v = q[a] + T[a];
+							if (v < lo[a]) lo[a] = v;
+							if (v > hi[a]) hi[a] = v;
+							if (fabs(v) > mag) mag = fabs(v);
+						}
+					}
+					const double pad = 1e-9 * (mag + 1.0);
+					for (uint32_t i = 0; i < em->nt; ++i) {
+						const double *b = tb + 6 * (size_t)i;
+						if (b[0] > hi[0] + pad || b[1] > hi[1] + pad || b[2] > hi[2] + pad || b[3] < lo[0] - pad ||
+						    b[4] < lo[1] - pad || b[5] < lo[2] - pad)
+							continue;
+						const uint32_t *t1 = em->tri + 3 * (size_t)i;
+						if (tri_intersect(em->xyz + 3 * (size_t)t1[0], em->xyz + 3 * (size_t)t1[1], em->xyz + 3 * (size_t)t1[2],
+						                  am->xyz + 3 * (size_t)t2[0], am->xyz + 3 * (size_t)t2[1], am->xyz + 3 * (size_t)t2[2], &R,
+						                  T)) {
+							hit = 1;
+							break;
+						}
+					}
+				}
+			}
+		}
+		if (hit) s->bits[p >> 5] |= (1u << (p & 31));
+	}
+	return NULL;
+}
+
+int orc_verdicts_bruteforce_fast(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                                 const double *poses, int fmt, uint32_t *verdict_bits, int n_threads) {
+	const size_t n_words = (size_t)((n_pose_sets + 31) / 32);
+	memset(verdict_bits, 0, sizeof(uint32_t) * n_words);
+	double **tri_box = (double **)calloc((size_t)(env->n > 0 ? env->n : 1), sizeof(double *));
+	for (int e = 0; e < env->n; ++e) {
+		const orc_model *em = env->models[e];
+		int shared = -1; /* objects may share a model */
+		for (int f = 0; f < e; ++f)
+			if (env->models[f] == em) {
+				shared = f;
+				break;
+			}
+		if (shared >= 0) {
+			tri_box[e] = tri_box[shared];
+			continue;
+		}
+		tri_box[e] = (double *)malloc(sizeof(double) * 6 * (size_t)em->nt);
+		for (uint32_t i = 0; i < em->nt; ++i) {
+			double *b = tri_box[e] + 6 * (size_t)i;
+			for (int a = 0; a < 3; ++a) {
+				b[a] = DBL_MAX;
+				b[3 + a] = -DBL_MAX;
+			}
+			for (int c = 0; c < 3; ++c) {
+				const double *v = em->xyz + 3 * (size_t)em->tri[3 * (size_t)i + c];
+				for (int a = 0; a < 3; ++a) {
+					if (v[a] < b[a]) b[a] = v[a];
+					if (v[a] > b[3 + a]) b[3 + a] = v[a];
+				}
+			}
+		}
+	}
+	if (n_threads < 1) n_threads = 1;
+	if (n_threads > 64) n_threads = 64;
+	pthread_t th[64];
+	int created[64];
+	bf_slice sl[64];
+	const uint64_t words_per = (n_words + (uint64_t)n_threads - 1) / (uint64_t)n_threads;
+	for (int t = 0; t < n_threads; ++t) {
+		uint64_t p0 = (uint64_t)t * words_per * 32, p1 = ((uint64_t)t + 1) * words_per * 32;
+		if (p0 > n_pose_sets) p0 = n_pose_sets;
+		if (p1 > n_pose_sets) p1 = n_pose_sets;
+		sl[t] = (bf_slice){env, n_links, links, poses, fmt, verdict_bits, p0, p1, tri_box};
+		created[t] = 0;
+		if (p0 == p1) continue;
+		if (t < n_threads - 1 && pthread_create(&th[t], NULL, bf_run, &sl[t]) == 0)
+			created[t] = 1;
+		else
+			bf_run(&sl[t]); /* the last slice (or a failed create) runs on the calling thread */
+	}
+	for (int t = 0; t < n_threads; ++t)
+		if (created[t]) pthread_join(th[t], NULL);
+	for (int e = 0; e < env->n; ++e) {
+		int shared = 0;
+		for (int f = 0; f < e; ++f)
+			if (env->models[f] == env->models[e]) shared = 1;
+		if (!shared) free(tri_box[e]);
+	}
+	free(tri_box);
+	return 0;
+}

@@ -85,6 +85,12 @@ int orc_self_collision(int n_links, orc_model *const *links, const double *pose_
 int orc_verdicts_bruteforce(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
                             const double *poses, int pose_format, uint32_t *verdict_bits);
 
+/* The same verdicts, fast enough for deep trees and large scenes: pose range over n_threads pthreads, and a pair of
+ * triangles is only tested when their axis-aligned boxes (grown by 1e-9 of the coordinate magnitude) overlap.  Still
+ * no BVH, no OBB fit, no OBB test: independent of everything the BVH oracle could get wrong there. */
+int orc_verdicts_bruteforce_fast(const orc_env *env, int n_links, orc_model *const *links, uint64_t n_pose_sets,
+                                 const double *poses, int pose_format, uint32_t *verdict_bits, int n_threads);
+
 /* ---- primitives exposed for unit tests ------------------------------------------------------ */
 /* OBB overlap(R0,T0,b1,b2) -> 1 if NOT disjoint. b = axis[9], To[3], extent[3] */
 int orc_obb_overlap(const double *R0, const double *T0, const double *axis1, const double *To1,

@@ -62,6 +62,8 @@ def lib():
         L.orc_self_collision.argtypes = [C.c_int, C.POINTER(vp), dp, C.c_int, C.POINTER(Counters)]
         L.orc_verdicts_bruteforce.restype = C.c_int
         L.orc_verdicts_bruteforce.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_uint64, dp, C.c_int, u32p]
+        L.orc_verdicts_bruteforce_fast.restype = C.c_int
+        L.orc_verdicts_bruteforce_fast.argtypes = [vp, C.c_int, C.POINTER(vp), C.c_uint64, dp, C.c_int, u32p, C.c_int]
         L.orc_obb_overlap.restype = C.c_int
         L.orc_obb_overlap.argtypes = [dp] * 8
         L.orc_tri_intersect.restype = C.c_int
@@ -199,6 +201,14 @@ def verdicts_bruteforce(env, links, poses, fmt=POSE_RT12):
     p, n = _poses(poses, len(links), fmt)
     bits = np.zeros((n + 31) // 32, np.uint32)
     lib().orc_verdicts_bruteforce(env.h, len(links), _links(links), n, _dp(p), fmt, _u32p(bits))
+    return bits
+
+
+def verdicts_bruteforce_fast(env, links, poses, fmt=POSE_RT12, n_threads=8):
+    """Structure-free oracle with a triangle-box prefilter and threads (see fcl_oracle.h)."""
+    p, n = _poses(poses, len(links), fmt)
+    bits = np.zeros((n + 31) // 32, np.uint32)
+    lib().orc_verdicts_bruteforce_fast(env.h, len(links), _links(links), n, _dp(p), fmt, _u32p(bits), n_threads)
     return bits
 
 

@@ -40,6 +40,9 @@ class Scene:
     def brute_bits(self, poses, fmt=O.POSE_RT12):
         return O.verdicts_bruteforce(self.oenv, self.olinks, poses, fmt)
 
+    def brute_bits_fast(self, poses, fmt=O.POSE_RT12, n_threads=8):
+        return O.verdicts_bruteforce_fast(self.oenv, self.olinks, poses, fmt, n_threads)
+
 
 def unit_box():
     return meshio.load_mptm("unit_box")[0]

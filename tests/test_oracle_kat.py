@@ -150,6 +150,28 @@ def test_golden_vectors(built, path):
     assert ctr.n_bv_tests == int(g["n_bv_tests"]) and ctr.n_leaf_tests == int(g["n_leaf_tests"])
 
 
+def test_golden_pin_status(built, capsys):
+    """Every golden file says whether its verdicts were ever compared with REAL FCL (tools/pin_golden_with_fcl.py
+    through oracle/_ref/fcl_harness).  In this repository's build container FCL does not exist, so the honest state
+    is "unpinned"; the test reports the state and checks that the pinning route is in place."""
+    files = sorted(glob.glob(os.path.join(GOLDEN, "*.npz")))
+    assert files
+    states = {}
+    for path in files:
+        g = np.load(path)
+        assert "pinned_by" in g.files, "%s lacks the pinned_by field (regenerate with tools/make_golden.py)" % path
+        states[os.path.basename(path)] = str(g["pinned_by"])
+    with capsys.disabled():
+        for k, v in states.items():
+            print("\n  golden %-42s %s" % (k, ("PINNED by " + v) if v else "unpinned (oracle only)"), end="")
+        print()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for rel in ("oracle/fcl_pin/fcl_harness.cpp", "oracle/fcl_pin/CMakeLists.txt", "tools/pin_golden_with_fcl.py"):
+        assert os.path.exists(os.path.join(root, rel)), rel
+    src = open(os.path.join(root, "oracle/fcl_pin/fcl_harness.cpp")).read()
+    assert '#include "utilities/meshhandler.hpp"' in src and "MeshHandler::isInCollision(" in src
+
+
 def test_self_collision_known_answers():
     """checkSelfCollision (meshhandler.hpp:205-219): unit cubes as links; closed-interval contact counts."""
     b = unit_box()

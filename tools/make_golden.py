@@ -42,7 +42,8 @@ def case(name, env, links, poses, fmt=O.POSE_RT12, pose7=(0, 0, 0, 1, 0, 0, 0), 
     bits = (O.verdicts_self if self_collision else O.verdicts)(oenv, ol, poses, fmt, 8, ctr)
     n = poses.shape[0]
     np.savez_compressed(os.path.join(OUT, name + ".npz"), poses=poses, bits=bits, fmt=fmt, pose7=np.asarray(pose7, float),
-                        self_collision=int(self_collision),
+                        self_collision=int(self_collision), pinned_by=np.array(""),  # set by tools/pin_golden_with_fcl.py
+
                         n_bv_tests=ctr.n_bv_tests, n_leaf_tests=ctr.n_leaf_tests,
                         env_digest=np.array([digest(m) for m in om[:8]]), link_digest=np.array([digest(m) for m in ol[:1]]))
     print("%-28s n=%6d collide=%.3f bv=%d leaf=%d" % (name, n, O.unpack_bits(bits, n).mean(), ctr.n_bv_tests, ctr.n_leaf_tests))
