@@ -28,6 +28,8 @@ public:
 	}
 
 	const WorkspaceBounds &getBounds() const { return bounds; }
+	// the environment handler, for callers of MeshHandler::isInCollision that bring their own pose-sets
+	const StaticEnvironmentMeshHandler &getEnvironment() const { return mesh; }
 
 	// map3d.hpp:33-37
 	bool safeEdge(const Agent &agent, const Edge &edge, double dt, bool checkSelfCollision = false) const {

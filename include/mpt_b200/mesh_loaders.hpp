@@ -3,7 +3,8 @@
 // The reference loads meshes with Assimp, `importer.ReadFile(pFile, 0)` -- no post-processing flags
 // (/root/reference/utilities/assimp_mesh_loader.hpp:11-18) -- and hands FCL one (vertices, triangles) pair per
 // aiMesh (`get`, :20-60).  These readers reproduce what that yields for the formats of the bundled fixtures:
-//   COLLADA (.dae): one sub-mesh per <triangles> group of every geometry that the visual scene instantiates,
+//   COLLADA (.dae): one sub-mesh per <triangles> group (and per <polylist> / <polygons> group, of which only the
+//                   three-vertex faces count) of every geometry that the visual scene instantiates,
 //                   in Assimp's ColladaLoader::BuildHierarchy order (real child nodes, then <instance_node>s,
 //                   then the node's own <instance_geometry>), each geometry once; vertices un-indexed (three
 //                   fresh vertices per face), raw mesh-local float32 coordinates (node matrices, <unit>,
@@ -44,15 +45,17 @@ inline bool read_file(const std::string &path, std::string &out) {
 	return true;
 }
 
-// three fresh vertices per face, faces (0,1,2), (3,4,5), ...
-inline SubMesh unindex(const std::vector<float> &pos, const std::vector<uint32_t> &faces) {
-	SubMesh m;
+// three fresh vertices per face, faces (0,1,2), (3,4,5), ...  Returns false if a face index points past the
+// vertex array (malformed file): mesh files are untrusted input.
+inline bool unindex(const std::vector<float> &pos, const std::vector<uint32_t> &faces, SubMesh &m) {
+	const size_t nv = pos.size() / 3;
 	for (size_t i = 0; i < faces.size(); ++i) {
 		const size_t v = faces[i];
+		if (v >= nv) return false;
 		for (int k = 0; k < 3; ++k) m.xyz.push_back((double)pos[3 * v + k]);
 		m.tri.push_back((uint32_t)i);
 	}
-	return m;
+	return true;
 }
 
 // ---- a small XML reader: elements, attributes, text; comments / processing instructions skipped ----------
@@ -197,6 +200,7 @@ inline bool load_dae(const std::string &path, std::vector<SubMesh> &out) {
 			const Xml *tc = child(*k, "technique_common");
 			const Xml *acc = tc ? child(*tc, "accessor") : nullptr;
 			if (acc && !acc->get("stride").empty()) stride = atoi(acc->get("stride").c_str());
+			if (stride < 1 || stride > 64) return false;  // (a stride of 0 would never advance)
 			std::vector<float> vals;
 			const char *c = fa->text.c_str();
 			char *end = nullptr;
@@ -207,7 +211,7 @@ inline bool load_dae(const std::string &path, std::vector<SubMesh> &out) {
 				c = end;
 			}
 			std::vector<float> xyz;
-			for (size_t i = 0; i + stride <= vals.size(); i += stride)
+			for (size_t i = 0; i + (size_t)stride <= vals.size(); i += (size_t)stride)
 				for (int a = 0; a < 3; ++a) xyz.push_back(a < stride ? vals[i + a] : 0.f);
 			sources[k->get("id")] = xyz;
 		}
@@ -221,12 +225,17 @@ inline bool load_dae(const std::string &path, std::vector<SubMesh> &out) {
 				}
 		}
 		for (const auto &prim : mesh->kids) {
-			if (prim->name != "triangles") continue;   // <lines> etc.: no triangle faces -> skipped sub-mesh
+			// <triangles>; <polylist> / <polygons> faces with exactly three vertices (Assimp without the triangulate flag
+			// keeps polygons as they are and AssimpMeshLoader::get only takes 3-index faces,
+			// /root/reference/utilities/assimp_mesh_loader.hpp:50-53).  <lines> etc. have no such faces.
+			const bool is_tri = prim->name == "triangles", is_plist = prim->name == "polylist", is_pgons = prim->name == "polygons";
+			if (!is_tri && !is_plist && !is_pgons) continue;
 			int nin = 1, voff = -1;
 			const std::vector<float> *pos = nullptr;
 			for (const auto &in : prim->kids) {
 				if (in->name != "input") continue;
 				const int off = atoi(in->get("offset").c_str());
+				if (off < 0 || off > 255) return false;
 				if (off + 1 > nin) nin = off + 1;
 				if (in->get("semantic") == "VERTEX") {
 					voff = off;
@@ -234,21 +243,55 @@ inline bool load_dae(const std::string &path, std::vector<SubMesh> &out) {
 					if (it != verts.end()) pos = it->second;
 				}
 			}
-			const Xml *p = child(*prim, "p");
-			if (!p || !pos || voff < 0) continue;
+			if (!pos || voff < 0) continue;
+			auto read_indices = [nin, voff](const std::string &text, std::vector<uint32_t> &idx) {
+				const char *c = text.c_str();
+				char *end = nullptr;
+				long col = 0;
+				for (;;) {
+					const long v = strtol(c, &end, 10);
+					if (end == c) break;
+					if (col % nin == voff) idx.push_back(v < 0 ? 0xffffffffu : (uint32_t)v);  // (negative: rejected by unindex)
+					++col;
+					c = end;
+				}
+			};
 			std::vector<uint32_t> idx;
-			const char *c = p->text.c_str();
-			char *end = nullptr;
-			long col = 0;
-			for (;;) {
-				const long v = strtol(c, &end, 10);
-				if (end == c) break;
-				if (col % nin == voff) idx.push_back((uint32_t)v);
-				++col;
-				c = end;
+			if (is_pgons) {
+				for (const auto &pp : prim->kids) {
+					if (pp->name != "p") continue;
+					std::vector<uint32_t> one;
+					read_indices(pp->text, one);
+					if (one.size() == 3) idx.insert(idx.end(), one.begin(), one.end());
+				}
+			} else {
+				const Xml *p = child(*prim, "p");
+				if (!p) continue;
+				std::vector<uint32_t> all;
+				read_indices(p->text, all);
+				if (is_tri) {
+					all.resize(all.size() / 3 * 3);
+					idx.swap(all);
+				} else {
+					const Xml *vc = child(*prim, "vcount");
+					if (!vc) continue;
+					const char *c = vc->text.c_str();
+					char *end = nullptr;
+					size_t at = 0;
+					for (;;) {
+						const long n = strtol(c, &end, 10);
+						if (end == c) break;
+						c = end;
+						if (n < 0 || at + (size_t)n > all.size()) return false;
+						if (n == 3) idx.insert(idx.end(), all.begin() + (long)at, all.begin() + (long)at + 3);
+						at += (size_t)n;
+					}
+				}
 			}
-			idx.resize(idx.size() / 3 * 3);
-			out.push_back(unindex(*pos, idx));
+			if (idx.empty()) continue;
+			SubMesh sm;
+			if (!unindex(*pos, idx, sm)) return false;
+			out.push_back(sm);
 		}
 	}
 	return true;
@@ -268,6 +311,7 @@ inline bool load_3ds(const std::string &path, std::vector<SubMesh> &out) {
 		const std::string &d;
 		std::vector<std::string> &materials;
 		std::vector<Obj> &objects;
+		bool bad;  // a chunk whose payload runs past its own end: the file is rejected
 		uint16_t u16(size_t o) const { uint16_t v; memcpy(&v, d.data() + o, 2); return v; }
 		uint32_t u32(size_t o) const { uint32_t v; memcpy(&v, d.data() + o, 4); return v; }
 		std::string cstr(size_t o, size_t &next) const {
@@ -277,7 +321,7 @@ inline bool load_3ds(const std::string &path, std::vector<SubMesh> &out) {
 			return d.substr(o, e - o);
 		}
 		void walk(size_t off, size_t end, Obj *obj, std::string *matname) {
-			while (off + 6 <= end) {
+			while (off + 6 <= end && !bad) {
 				const uint16_t id = u16(off);
 				const uint32_t len = u32(off + 2);
 				const size_t body = off + 6, cend = off + len;
@@ -299,18 +343,24 @@ inline bool load_3ds(const std::string &path, std::vector<SubMesh> &out) {
 				} else if (id == 0x4100) {
 					walk(body, cend, obj, matname);
 				} else if (id == 0x4110 && obj) {
+					if (body + 2 > cend) { bad = true; return; }
 					const uint16_t n = u16(body);
+					if (body + 2 + sizeof(float) * 3 * (size_t)n > cend) { bad = true; return; }  // payload must fit the chunk
 					obj->verts.resize(3 * (size_t)n);
 					memcpy(obj->verts.data(), d.data() + body + 2, sizeof(float) * 3 * n);
 				} else if (id == 0x4120 && obj) {
+					if (body + 2 > cend) { bad = true; return; }
 					const uint16_t n = u16(body);
+					if (body + 2 + 8 * (size_t)n > cend) { bad = true; return; }
 					for (uint16_t f = 0; f < n; ++f)
 						for (int k = 0; k < 3; ++k) obj->faces.push_back(u16(body + 2 + 8 * (size_t)f + 2 * k));
 					walk(body + 2 + 8 * (size_t)n, cend, obj, matname);
 				} else if (id == 0x4130 && obj) {
 					size_t nx;
 					const std::string m = cstr(body, nx);
+					if (nx + 2 > cend) { bad = true; return; }
 					const uint16_t n = u16(nx);
+					if (nx + 2 + 2 * (size_t)n > cend) { bad = true; return; }
 					std::vector<uint32_t> ids;
 					for (uint16_t f = 0; f < n; ++f) ids.push_back(u16(nx + 2 + 2 * (size_t)f));
 					obj->facemat.push_back(std::make_pair(m, ids));
@@ -318,8 +368,9 @@ inline bool load_3ds(const std::string &path, std::vector<SubMesh> &out) {
 				off = cend;
 			}
 		}
-	} parser{d, materials, objects};
+	} parser{d, materials, objects, false};
 	parser.walk(0, d.size(), nullptr, nullptr);
+	if (parser.bad) return false;
 	for (const Obj &o : objects) {
 		const size_t nf = o.faces.size() / 3;
 		if (nf == 0 || o.verts.empty()) continue;            // Assimp drops empty objects
@@ -337,7 +388,11 @@ inline bool load_3ds(const std::string &path, std::vector<SubMesh> &out) {
 			for (size_t f = 0; f < nf; ++f)
 				if (fm[f] == want)
 					for (int k = 0; k < 3; ++k) idx.push_back(o.faces[3 * f + k]);
-			if (!idx.empty()) out.push_back(unindex(o.verts, idx));
+			if (!idx.empty()) {
+				SubMesh sm;
+				if (!unindex(o.verts, idx, sm)) return false;
+				out.push_back(sm);
+			}
 		}
 	}
 	return true;
@@ -350,16 +405,29 @@ inline bool load_mptm(const std::string &path, std::vector<SubMesh> &out) {
 	if (!f.is_open() || !f.read(magic, 4) || std::memcmp(magic, "MPTM", 4) != 0 ||
 	    !f.read(reinterpret_cast<char *>(&ver), 4) || ver != 1 || !f.read(reinterpret_cast<char *>(&nsub), 4))
 		return false;
+	// the header counts are checked against what is left of the file before anything is allocated
+	f.seekg(0, std::ios::end);
+	const unsigned long long file_size = (unsigned long long)f.tellg();
+	f.seekg(12, std::ios::beg);
+	unsigned long long left = file_size >= 12 ? file_size - 12 : 0;
+	if ((unsigned long long)nsub * 8ull > left) return false;
 	out.resize(nsub);
 	for (auto &m : out) {
 		uint32_t nv = 0, nt = 0;
 		f.read(reinterpret_cast<char *>(&nv), 4);
 		f.read(reinterpret_cast<char *>(&nt), 4);
+		if (!f || left < 8) return false;
+		left -= 8;
+		const unsigned long long need = 24ull * nv + 12ull * nt;
+		if (need > left) return false;
+		left -= need;
 		m.xyz.resize(3 * (size_t)nv);
 		m.tri.resize(3 * (size_t)nt);
 		f.read(reinterpret_cast<char *>(m.xyz.data()), sizeof(double) * m.xyz.size());
 		f.read(reinterpret_cast<char *>(m.tri.data()), sizeof(uint32_t) * m.tri.size());
 		if (!f) return false;
+		for (uint32_t i : m.tri)
+			if (i >= nv) return false;
 	}
 	return true;
 }

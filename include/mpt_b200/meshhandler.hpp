@@ -55,7 +55,7 @@ class SimpleAgentMeshHandler {
 public:
 	// mergeSubMeshes = false reproduces the reference: agentModel is overwritten for every non-empty
 	// sub-mesh, so only the last one collides (meshhandler.hpp:124-134).
-	explicit SimpleAgentMeshHandler(const std::string &filename, bool mergeSubMeshes = false) {
+	explicit SimpleAgentMeshHandler(const std::string &filename, bool mergeSubMeshes = false) : id(nextId()) {
 		mpt_b200::MeshFileLoader loader(filename);
 		if (loader.error) exit(0);
 		for (const auto &m : loader.meshes) {
@@ -70,9 +70,17 @@ public:
 		}
 	}
 	const mpt_b200::SubMesh &getModel() const { return model; }
+	// Identity of this handler's model for the environment's "agent currently installed" cache: unique per
+	// constructed handler, so a handler that is freed and another one allocated at the same address never aliases.
+	unsigned long long getId() const { return id; }
 
 private:
+	static unsigned long long nextId() {
+		static unsigned long long counter = 0;
+		return ++counter;
+	}
 	mpt_b200::SubMesh model;
+	unsigned long long id;
 };
 
 class StaticEnvironmentMeshHandler {
@@ -105,12 +113,16 @@ public:
 	StaticEnvironmentMeshHandler &operator=(const StaticEnvironmentMeshHandler &) = delete;
 
 	// The context bound to this environment, with `agent` installed as the current link models.
+	// (mptcc_set_agent first waits for every outstanding submit of this context, so replacing the agent while
+	// PendingVerdicts / PendingEdges are in flight is safe.)
 	mptcc_ctx *getCollisionChecker(const std::vector<const SimpleAgentMeshHandler *> &agent) const {
-		if (agent != agentKey) {
+		std::vector<unsigned long long> key;
+		for (const auto *a : agent) key.push_back(a->getId());
+		if (key != agentKey) {
 			std::vector<mptcc_mesh> cm;
 			for (const auto *a : agent) cm.push_back(mpt_b200::as_c_mesh(a->getModel()));
 			check(mptcc_set_agent(ctx, (int)cm.size(), cm.data()), "mptcc_set_agent");
-			agentKey = agent;
+			agentKey = key;
 		}
 		return ctx;
 	}
@@ -124,7 +136,7 @@ public:
 private:
 	std::vector<mpt_b200::SubMesh> objects;
 	mptcc_ctx *ctx;
-	mutable std::vector<const SimpleAgentMeshHandler *> agentKey;
+	mutable std::vector<unsigned long long> agentKey;
 };
 
 namespace mpt_b200 {
@@ -199,34 +211,77 @@ private:
 
 class MeshHandler {
 public:
-	// [P][L] transforms -> pose records.  All transforms of a batch built from matrices / translations use
-	// RT12; all built from quaternions use TQ7; a mixed batch is split by the callers below.
+	// Pose record format of one transform: the most compact libmptcc format that carries exactly what FCL would
+	// compute with (fcl_types.hpp): a quaternion-built transform -> TQ7; a matrix-built one -> T3 if the matrix is the
+	// identity (Transform3f(Vec3f), Omnidirectional::getPoses), XYZCS if it is the planar rotation the blimp and the
+	// snake fill in (R00 = R11 = c, R01 = s, R10 = -s, rest of the identity), RT12 otherwise.
+	static int kindOf(const fcl::Transform3f &tf) {
+		if (tf.builtFromQuaternion()) return MPTCC_POSE_TQ7;
+		const fcl::Matrix3f &R = tf.getRotation();
+		if (R(0, 2) == 0 && R(1, 2) == 0 && R(2, 0) == 0 && R(2, 1) == 0 && R(2, 2) == 1 && R(0, 0) == R(1, 1) && R(1, 0) == -R(0, 1))
+			return (R(0, 0) == 1 && R(0, 1) == 0) ? MPTCC_POSE_T3 : MPTCC_POSE_XYZCS;
+		return MPTCC_POSE_RT12;
+	}
+	// Format of a whole pose-set: the most general of its links (T3 < XYZCS < RT12); quaternion- and matrix-built
+	// links cannot share a record format, no agent of the toolkit produces such a set.
+	static int kindOfSet(const std::vector<fcl::Transform3f> &set) {
+		static const int rank[4] = {2 /*RT12*/, 3 /*TQ7*/, 0 /*T3*/, 1 /*XYZCS*/};
+		int kind = MPTCC_POSE_T3;
+		bool any_q = false, any_m = false;
+		for (const auto &tf : set) {
+			const int k = kindOf(tf);
+			(k == MPTCC_POSE_TQ7 ? any_q : any_m) = true;
+			if (rank[k] > rank[kind]) kind = k;
+		}
+		if (any_q && any_m) {
+			fprintf(stderr, "MeshHandler: a pose-set mixes quaternion-built and matrix-built transforms\n");
+			exit(1);
+		}
+		return kind;
+	}
+	static size_t recLen(int kind) { return kind == MPTCC_POSE_TQ7 ? 7 : kind == MPTCC_POSE_T3 ? 3 : kind == MPTCC_POSE_XYZCS ? 5 : 12; }
+
+	// [P][L] transforms -> pose records of format `kind` for the pose-sets listed in `index`.
 	static int packPoses(const std::vector<std::vector<fcl::Transform3f> > &poses, const std::vector<size_t> &index,
-	                     size_t links, bool quat, double *out) {
+	                     size_t links, int kind, double *out) {
 		for (size_t i : index) {
 			const std::vector<fcl::Transform3f> &set = poses[i];
 			if (set.size() != links) return -1;
 			for (const auto &tf : set) {
-				if (quat) {
+				const fcl::Vec3f &T = tf.getTranslation();
+				if (kind == MPTCC_POSE_TQ7) {
 					const fcl::Quaternion3f &q = tf.getQuatRotation();
-					out[0] = tf.getTranslation()[0];
-					out[1] = tf.getTranslation()[1];
-					out[2] = tf.getTranslation()[2];
+					out[0] = T[0];
+					out[1] = T[1];
+					out[2] = T[2];
 					out[3] = q.getW();
 					out[4] = q.getX();
 					out[5] = q.getY();
 					out[6] = q.getZ();
-					out += 7;
+				} else if (kind == MPTCC_POSE_T3 || kind == MPTCC_POSE_XYZCS) {
+					out[0] = T[0];
+					out[1] = T[1];
+					out[2] = T[2];
+					if (kind == MPTCC_POSE_XYZCS) {
+						out[3] = tf.getRotation()(0, 0);
+						out[4] = tf.getRotation()(0, 1);
+					}
 				} else {
 					memcpy(out, tf.getRotation().data(), 9 * sizeof(double));
-					out[9] = tf.getTranslation()[0];
-					out[10] = tf.getTranslation()[1];
-					out[11] = tf.getTranslation()[2];
-					out += 12;
+					out[9] = T[0];
+					out[10] = T[1];
+					out[11] = T[2];
 				}
+				out += recLen(kind);
 			}
 		}
 		return 0;
+	}
+	// pose-set indices per record format; pose-sets without transforms have no agent objects and never collide
+	// (the Blimp::getPoses stub, /root/reference/agents/blimp.hpp:219-223)
+	static void splitByKind(const std::vector<std::vector<fcl::Transform3f> > &poses, std::vector<size_t> index[4]) {
+		for (size_t i = 0; i < poses.size(); ++i)
+			if (!poses[i].empty()) index[kindOfSet(poses[i])].push_back(i);
 	}
 
 	// One verdict per pose-set (true = in collision): what one MeshHandler::isInCollision call per pose-set
@@ -247,20 +302,18 @@ public:
 		mptcc_ctx *ctx = environment.getCollisionChecker(agent);
 		std::vector<double> rec;
 		std::vector<uint32_t> bits;
-		for (int quat = 0; quat < 2; ++quat) {
-			std::vector<size_t> index;
-			for (size_t i = 0; i < poses.size(); ++i)
-				if (!poses[i].empty() && (int)poses[i][0].builtFromQuaternion() == quat) index.push_back(i);
+		std::vector<size_t> byKind[4];
+		splitByKind(poses, byKind);
+		for (int kind = 0; kind < 4; ++kind) {
+			const std::vector<size_t> &index = byKind[kind];
 			if (index.empty()) continue;
-			rec.resize(index.size() * agent.size() * (quat ? 7 : 12));
+			rec.resize(index.size() * agent.size() * recLen(kind));
 			bits.assign((index.size() + 31) / 32, 0u);
-			if (packPoses(poses, index, agent.size(), quat != 0, rec.data()) != 0) {
+			if (packPoses(poses, index, agent.size(), kind, rec.data()) != 0) {
 				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
 				exit(1);
 			}
-			environment.check(mptcc_check_poses(ctx, index.size(), rec.data(), quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12,
-			                                    bits.data()),
-			                  "mptcc_check_poses");
+			environment.check(mptcc_check_poses(ctx, index.size(), rec.data(), kind, bits.data()), "mptcc_check_poses");
 			for (size_t k = 0; k < index.size(); ++k) verdict[index[k]] = (bits[k >> 5] >> (k & 31)) & 1u;
 		}
 		return verdict;
@@ -277,26 +330,24 @@ public:
 		if (poses.empty() || agent.empty()) return out;
 		out->env = &environment;
 		out->ctx = environment.getCollisionChecker(agent);
-		// split by constructor kind (pose-sets whose links mix kinds are not produced by any agent); a pose-set
-		// without transforms has no agent objects and is never in collision (Blimp::getPoses stub)
-		for (int quat = 0; quat < 2; ++quat) {
+		// one submit per record format present in the batch
+		std::vector<size_t> byKind[4];
+		splitByKind(poses, byKind);
+		for (int kind = 0; kind < 4; ++kind) {
+			if (byKind[kind].empty()) continue;
 			PendingVerdicts::Part pt;
-			for (size_t i = 0; i < poses.size(); ++i)
-				if (!poses[i].empty() && (int)poses[i][0].builtFromQuaternion() == quat) pt.index.push_back(i);
-			if (pt.index.empty()) continue;
+			pt.index.swap(byKind[kind]);
 			const size_t n = pt.index.size(), words = (n + 31) / 32;
-			pt.rec = static_cast<double *>(mpt_b200::PinnedPool::take(n * agent.size() * (quat ? 7 : 12) * sizeof(double)));
+			pt.rec = static_cast<double *>(mpt_b200::PinnedPool::take(n * agent.size() * recLen(kind) * sizeof(double)));
 			pt.bits = static_cast<uint32_t *>(mpt_b200::PinnedPool::take(words * sizeof(uint32_t)));
-			if (packPoses(poses, pt.index, agent.size(), quat != 0, pt.rec) != 0) {
+			if (packPoses(poses, pt.index, agent.size(), kind, pt.rec) != 0) {
 				fprintf(stderr, "MeshHandler: every pose-set needs one transform per agent mesh\n");
 				exit(1);
 			}
 			pt.ticket = 0;
 			out->done = false;
 			out->parts.push_back(pt);
-			environment.check(mptcc_submit_poses(out->ctx, n, pt.rec, quat ? MPTCC_POSE_TQ7 : MPTCC_POSE_RT12, pt.bits,
-			                                     &out->parts.back().ticket),
-			                  "mptcc_submit_poses");
+			environment.check(mptcc_submit_poses(out->ctx, n, pt.rec, kind, pt.bits, &out->parts.back().ticket), "mptcc_submit_poses");
 		}
 		return out;
 	}

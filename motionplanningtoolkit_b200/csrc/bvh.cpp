@@ -195,6 +195,8 @@ struct Task {
 
 bool build_bvh(const double *xyz, uint32_t nv, const uint32_t *tri, uint32_t nt, HostBvh &out) {
 	if (nv == 0 || nt == 0 || !xyz || !tri) return false;
+	for (size_t i = 0; i < 3 * (size_t)nt; ++i)
+		if (tri[i] >= nv) return false;  // a face index beyond the vertex array (malformed file / bad mptcc_mesh)
 	out.xyz.assign(xyz, xyz + 3 * (size_t)nv);
 	out.tri.assign(tri, tri + 3 * (size_t)nt);
 	const size_t nn = 2 * (size_t)nt - 1;

@@ -588,6 +588,20 @@ int upload_scene_part(mptcc_ctx *ctx, bool env) {
 	return MPTCC_OK;
 }
 
+// Outstanding submits and device-buffer launches still read the scene arrays: a set_* call (which may overwrite
+// them in place) or an option that changes what later launches do first waits for all of it.
+int drain(mptcc_ctx *ctx) {
+	if (ctx->submitted != ctx->completed) {
+		const int rc = mptcc_wait(ctx, 0);
+		if (rc != MPTCC_OK) return rc;
+	}
+	for (auto &d : ctx->devs) {
+		CU(cudaSetDevice(d.id));
+		CU(cudaDeviceSynchronize());
+	}
+	return MPTCC_OK;
+}
+
 int check_ready(mptcc_ctx *ctx) {
 	if (!ctx) return MPTCC_ERR_INVALID;
 	if (!ctx->env_set) return fail(ctx, MPTCC_ERR_STATE, "environment not set (mptcc_set_environment)");
@@ -798,42 +812,50 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 	}
 	std::unique_ptr<mptcc_ctx> c(new mptcc_ctx);
 	mptcc_ctx *ctx = c.get();
+	ctx->devs.reserve((size_t)n_devices);
+	// Every device is entered in ctx->devs BEFORE its resources are created, so that a failure half way releases
+	// whatever exists (streams, events, pinned blocks, device buffers) through mptcc_destroy.
+	auto bail = [&c](int code) {
+		mptcc_destroy(c.release());
+		return code;
+	};
 	for (int i = 0; i < n_devices; ++i) {
-		Device d;
-		d.id = device_ids ? device_ids[i] : i;
-		if (d.id < 0 || d.id >= avail) return MPTCC_ERR_NO_DEVICE;
+		const int id = device_ids ? device_ids[i] : i;
+		if (id < 0 || id >= avail) return bail(MPTCC_ERR_NO_DEVICE);
 		cudaDeviceProp prop;
-		if (cudaGetDeviceProperties(&prop, d.id) != cudaSuccess) return MPTCC_ERR_NO_DEVICE;
-		if (prop.major != 10) return MPTCC_ERR_NO_DEVICE;  // the kernels are built for sm_100a only
+		if (cudaGetDeviceProperties(&prop, id) != cudaSuccess) return bail(MPTCC_ERR_NO_DEVICE);
+		if (prop.major != 10) return bail(MPTCC_ERR_NO_DEVICE);  // the kernels are built for sm_100a only
+		ctx->devs.emplace_back();
+		Device &d = ctx->devs.back();
+		d.id = id;
 		d.sm_count = prop.multiProcessorCount;
 		d.l2_persist_max = (size_t)std::max(0, prop.persistingL2CacheMaxSize);
 		d.l2_window_max = (size_t)std::max(0, prop.accessPolicyMaxWindowSize);
-		if (cudaSetDevice(d.id) != cudaSuccess) return MPTCC_ERR_CUDA;
+		if (cudaSetDevice(d.id) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
 		if (d.l2_persist_max > 0 && cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, d.l2_persist_max) != cudaSuccess) {
 			cudaGetLastError();
 			d.l2_persist_max = 0;
 		}
 		for (int k = 0; k < kPipe; ++k) {
-			if (cudaStreamCreateWithFlags(&d.stream[k], cudaStreamNonBlocking) != cudaSuccess) return MPTCC_ERR_CUDA;
-			if (cudaEventCreate(&d.ev0[k]) != cudaSuccess || cudaEventCreate(&d.ev1[k]) != cudaSuccess) return MPTCC_ERR_CUDA;
-			if (d.work[k].reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
+			if (cudaStreamCreateWithFlags(&d.stream[k], cudaStreamNonBlocking) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
+			if (cudaEventCreate(&d.ev0[k]) != cudaSuccess || cudaEventCreate(&d.ev1[k]) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
+			if (d.work[k].reserve(1) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
 		}
 		for (int t = 0; t < kInFlight; ++t) {
 			for (int k = 0; k < kPipe; ++k)
-				if (cudaEventCreateWithFlags(&d.done[t][k], cudaEventDisableTiming) != cudaSuccess) return MPTCC_ERR_CUDA;
+				if (cudaEventCreateWithFlags(&d.done[t][k], cudaEventDisableTiming) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
 			if (cudaMallocHost(reinterpret_cast<void **>(&d.ctl_h[t]), sizeof(unsigned int) * 4 * kPipe) != cudaSuccess)
-				return MPTCC_ERR_CUDA;
+				return bail(MPTCC_ERR_CUDA);
 		}
 		if (cudaHostAlloc(reinterpret_cast<void **>(&d.small_in), kSmallBytes, cudaHostAllocMapped) != cudaSuccess ||
 		    cudaHostAlloc(reinterpret_cast<void **>(&d.small_out), kSmallBytes / 24 / 8 + 64, cudaHostAllocMapped) != cudaSuccess)
-			return MPTCC_ERR_CUDA;
+			return bail(MPTCC_ERR_CUDA);
 		if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_in_dev), d.small_in, 0) != cudaSuccess ||
 		    cudaHostGetDevicePointer(reinterpret_cast<void **>(&d.small_out_dev), d.small_out, 0) != cudaSuccess)
-			return MPTCC_ERR_CUDA;
-		if (d.work_user.reserve(1) != cudaSuccess) return MPTCC_ERR_CUDA;
-		if (d.counters.reserve(CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
-		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return MPTCC_ERR_CUDA;
-		ctx->devs.push_back(d);
+			return bail(MPTCC_ERR_CUDA);
+		if (d.work_user.reserve(1) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
+		if (d.counters.reserve(CTR_N) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
+		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
 	}
 	*out = c.release();
 	return MPTCC_OK;
@@ -888,6 +910,10 @@ int mptcc_num_devices(const mptcc_ctx *ctx) { return ctx ? (int)ctx->devs.size()
 int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshes, const double *obj_pose7) {
 	if (!ctx || n_objects < 0 || (n_objects > 0 && (!meshes || !obj_pose7))) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
 	if (n_objects >= (1 << 26)) return fail(ctx, MPTCC_ERR_LIMIT, "too many environment objects");
+	{
+		const int drc = drain(ctx);
+		if (drc != MPTCC_OK) return drc;
+	}
 	ctx->env_h.clear();
 	ctx->env_q_ok = true;
 	ctx->objects_h.clear();
@@ -921,7 +947,7 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 		const HostBvh &b = block[(size_t)(i % kBlock)];
 		if (b.num_tris() >= (1u << 22)) ctx->env_q_ok = false;
 		if (!block_ok[(size_t)(i % kBlock)])
-			return fail(ctx, MPTCC_ERR_INVALID, "environment object " + std::to_string(i) + " has an empty mesh");
+			return fail(ctx, MPTCC_ERR_INVALID, "environment object " + std::to_string(i) + " has an empty mesh or a triangle index beyond its vertices");
 		DevObject o;
 		std::memset(&o, 0, sizeof o);
 		o.model = ctx->env_h.add(b);
@@ -975,6 +1001,10 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 
 int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) {
 	if (!ctx || n_links < 1 || !link_meshes) return fail(ctx, MPTCC_ERR_INVALID, "bad argument");
+	{
+		const int drc = drain(ctx);
+		if (drc != MPTCC_OK) return drc;
+	}
 	ctx->agent_h.clear();
 	ctx->link_model_h.clear();
 	ctx->agent_set = false;
@@ -1334,6 +1364,10 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "long_batches") {
 		ctx->opt_long_batches = value < 0 ? -1 : (value != 0);
 	} else if (k == "self_collision") {
+		if (ctx->opt_self_collision != (value != 0) && ctx->submitted != ctx->completed) {
+			const int drc = mptcc_wait(ctx, 0);  // submits in flight keep the behaviour they were enqueued with
+			if (drc != MPTCC_OK) return drc;
+		}
 		ctx->opt_self_collision = value != 0;
 	} else if (k == "np2") {
 		ctx->opt_np2 = value != 0;

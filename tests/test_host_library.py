@@ -152,7 +152,8 @@ def test_cpp_mesh_loaders_match_the_python_converter(built, tmp_path):
     assert open(out, "rb").read() == open(os.path.join(meshio.DATA_DIR, "blimp.mptm"), "rb").read()
 
 
-@pytest.mark.parametrize("example", ["omnidirectional_demo", "prm_roadmap", "self_collision_check", "mesh_convert"])
+@pytest.mark.parametrize("example", ["omnidirectional_demo", "prm_roadmap", "self_collision_check", "mesh_convert",
+                                     "grid_prmlite_demo", "rrt_speculative"])
 def test_examples_compile_as_cxx11_against_the_shim(built, example, tmp_path):
     """The drop-in headers are C++11 like the reference (CMakeLists.txt: -std=c++11) and link against libmptcc only."""
     libdir = os.path.join(ROOT, "motionplanningtoolkit_b200")
@@ -161,3 +162,95 @@ def test_examples_compile_as_cxx11_against_the_shim(built, example, tmp_path):
                         os.path.join(ROOT, "examples", example + ".cpp"), "-o", exe, "-L", libdir, "-lmptcc",
                         "-Wl,-rpath," + libdir], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-2000:]
+
+
+def test_mesh_loaders_reject_malformed_files_and_read_polylists(built, tmp_path):
+    """Mesh files are untrusted input: out-of-range face indices, chunks / counts that run past the
+    file, a zero accessor stride must fail cleanly; <polylist> / <polygons> contribute their three-vertex faces."""
+    import struct
+    exe = str(tmp_path / "mesh_convert")
+    subprocess.check_call(["g++", "-std=c++11", "-O1", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "mesh_convert.cpp"), "-o", exe])
+    out = str(tmp_path / "o.mptm")
+
+    def run(name, data):
+        p = str(tmp_path / name)
+        open(p, "wb").write(data)
+        return subprocess.run([exe, p, out], capture_output=True, text=True, timeout=20)
+
+    good = open(os.path.join(meshio.DATA_DIR, "unit_box.mptm"), "rb").read()
+    assert run("ok.mptm", good).returncode == 0
+    assert run("huge_counts.mptm", good[:12] + struct.pack("<II", 0x7fffffff, 0x7fffffff) + good[20:]).returncode != 0
+    assert run("truncated.mptm", good[:len(good) // 2]).returncode != 0
+    bad_idx = bytearray(good)
+    bad_idx[-4:] = struct.pack("<I", 1000)                      # last triangle index beyond the 24+ vertices
+    assert run("bad_index.mptm", bytes(bad_idx)).returncode != 0
+    # 3DS: a vertex-list chunk (0x4110) that claims more vertices than the chunk holds
+    verts = struct.pack("<HI", 0x4110, 6 + 2 + 12) + struct.pack("<H", 5000) + struct.pack("<3f", 0, 0, 0)
+    tri = struct.pack("<HI", 0x4100, 6 + len(verts)) + verts
+    obj = struct.pack("<HI", 0x4000, 6 + 2 + len(tri)) + b"a\0" + tri
+    edit = struct.pack("<HI", 0x3D3D, 6 + len(obj)) + obj
+    assert run("overrun.3ds", struct.pack("<HI", 0x4D4D, 6 + len(edit)) + edit).returncode != 0
+
+    def dae(prim, stride="3"):
+        return ("""<?xml version="1.0"?><COLLADA><library_geometries><geometry id="g"><mesh>
+<source id="p"><float_array id="pa" count="15">0 0 0  1 0 0  1 1 0  0 1 0  0 0 1</float_array>
+<technique_common><accessor source="#pa" count="5" stride="%s"/></technique_common></source>
+<vertices id="v"><input semantic="POSITION" source="#p"/></vertices>%s</mesh></geometry></library_geometries>
+<library_visual_scenes><visual_scene id="s"><node id="n"><instance_geometry url="#g"/></node></visual_scene>
+</library_visual_scenes></COLLADA>""" % (stride, prim)).encode()
+
+    r = run("stride0.dae", dae('<triangles count="1"><input semantic="VERTEX" source="#v" offset="0"/><p>0 1 2</p></triangles>', "0"))
+    assert r.returncode != 0
+    assert run("oob.dae", dae('<triangles count="1"><input semantic="VERTEX" source="#v" offset="0"/><p>0 1 9</p></triangles>')).returncode != 0
+    r = run("plist.dae", dae('<polylist count="3"><input semantic="VERTEX" source="#v" offset="0"/><vcount>3 4 3</vcount>'
+                             '<p>0 1 2  0 1 2 3  2 3 4</p></polylist>'))
+    assert r.returncode == 0 and "1 sub-meshes, 2 triangles" in r.stdout, r.stdout + r.stderr
+    r = run("pgons.dae", dae('<polygons count="2"><input semantic="VERTEX" source="#v" offset="0"/><p>0 1 2</p><p>0 1 2 3</p></polygons>'))
+    assert r.returncode == 0 and "1 sub-meshes, 1 triangles" in r.stdout, r.stdout + r.stderr
+    # the C ABI refuses a mesh whose triangle indices point past its vertices
+    v, t = meshio.load_mptm("unit_box")[0]
+    t = t.copy()
+    t[0, 0] = len(v) + 5
+    with pytest.raises(capi.MptccError):
+        capi.HostBvh(v, t)
+
+
+REFERENCE = "/root/reference"
+PATCHES = sorted(f for f in os.listdir(os.path.join(ROOT, "patches")) if f.endswith(".diff"))
+
+
+@pytest.mark.parametrize("patch_file", PATCHES)
+def test_call_site_patches_apply_to_the_reference(patch_file):
+    """the batched call sites are committed as patches against the reference's planners and
+    discretizations (patches/*.diff); they must apply cleanly to the checkout they were made from."""
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("the reference checkout is not present on this box")
+    r = subprocess.run(["patch", "--dry-run", "-p1", "-d", REFERENCE, "-i", os.path.join(ROOT, "patches", patch_file)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "FAILED" not in r.stdout, r.stdout + r.stderr
+
+
+def test_reference_grid_discretization_compiles_unchanged_and_patched(built, tmp_path):
+    """The reference's discretizations/workspace/griddiscretization.hpp, UNMODIFIED, instantiated with Map3D from
+    include/mpt_b200 (its constructor calls safePoses(agent, vector<vector<Transform3f>>), map3d.hpp:39-42), and again
+    with patches/discretizations_workspace_griddiscretization_hpp.diff applied (one safePosesBatch for the grid).
+    The binaries are left under examples/bin/ (git-ignored; they travel with the snapshot) for the GPU test, because
+    the reference checkout does not exist on the GPU box."""
+    if not os.path.isdir(REFERENCE):
+        pytest.skip("the reference checkout is not present on this box")
+    libdir = os.path.join(ROOT, "motionplanningtoolkit_b200")
+    bindir = os.path.join(ROOT, "examples", "bin")
+    os.makedirs(bindir, exist_ok=True)
+    patched = tmp_path / "patched" / "discretizations" / "workspace"
+    patched.mkdir(parents=True)
+    src = os.path.join(REFERENCE, "discretizations", "workspace", "griddiscretization.hpp")
+    open(str(patched / "griddiscretization.hpp"), "w").write(open(src).read())
+    subprocess.check_call(["patch", "-s", "-p1", "-d", str(tmp_path / "patched"), "-i",
+                           os.path.join(ROOT, "patches", "discretizations_workspace_griddiscretization_hpp.diff")])
+    for name, inc in (("grid_prmlite_demo_reference", REFERENCE), ("grid_prmlite_demo_patched", str(tmp_path / "patched"))):
+        r = subprocess.run(["g++", "-std=c++11", "-O1", "-DMPT_HAVE_REFERENCE", "-I", os.path.join(ROOT, "include"), "-I", inc,
+                            os.path.join(ROOT, "examples", "grid_prmlite_demo.cpp"), "-o", os.path.join(bindir, name),
+                            "-L", libdir, "-lmptcc", "-Wl,-rpath,$ORIGIN/../../motionplanningtoolkit_b200"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr[-3000:]
