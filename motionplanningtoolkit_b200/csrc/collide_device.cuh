@@ -636,21 +636,6 @@ __device__ __forceinline__ double rel_element(const DevObject &ob, const double 
 	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
 }
 
-// fp64 relativeTransform(object, pose) of a candidate, FCL's operation order, into `out` (12 doubles in shared
-// memory): lanes 0..11 compute one element each; all lanes must call.
-__device__ __forceinline__ const double *exact_rel_from_pose(const KernelParams &p, const DevObject &ob, const double *pose_rec,
-                                                             double *out, int lane) {
-	__syncwarp();
-	if (lane < 12) {
-		double R2[9], T2[3];
-		Quat q;
-		decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
-		out[lane] = rel_element(ob, R2, T2, lane);
-	}
-	__syncwarp();
-	return out;
-}
-
 // Candidate records live in shared memory as 4 float4 (64 B).  Lanes fetch the SAME part k of DIFFERENT
 // records at once; with a plain layout all even (odd) candidates would hit the same 4 banks.  Part k of
 // candidate c is therefore stored at position (k + (c >> 1)) & 3 of its record: 8 consecutive candidates

@@ -38,10 +38,19 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32, 2) collide_kernel(const __g
 #pragma unroll
 	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
 
+	bool first_turn = true;
 	while (true) {
 		unsigned chunk = 0;
-		if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
-		chunk = __shfl_sync(FULL, chunk, 0);
+		if (p.work_counter != nullptr) {
+			if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
+			chunk = __shfl_sync(FULL, chunk, 0);
+		} else {
+			// planner-sized launches: one chunk per warp, the grid is sized to fit -- no work counter, hence no memset
+			// in front of the launch (a CUDA call less on a path that is all launch latency)
+			if (!first_turn) break;
+			first_turn = false;
+			chunk = blockIdx.x * kWarpsPerCta + warp;
+		}
 		if (chunk >= n_chunks) break;
 		const unsigned long long pose0 = (unsigned long long)chunk << p.ppw_log2;
 		const unsigned long long left = p.n_pose_sets - pose0;

@@ -129,6 +129,7 @@ struct KernelParams {
 	uint4 *xq;                     // [xq_cap] exact-pass queue: candidate list index, env prim, agent prim, certain-contact flag
 	unsigned int *xq_total;        // [1] entries appended (can exceed xq_cap: then *overflow = 1)
 	unsigned int xq_cap;
+	uint32_t expand4;              // 1: a narrowphase step expands both trees (four tests), 0: FCL's one-tree descent (two)
 	uint32_t qnode;                // 1: traverse nodeq (32-byte nodes), 0: node32
 	uint32_t agent_top;            // agent nodes [0, agent_top) of link model 0 are staged in shared memory (breadth-first ids)
 };

@@ -513,6 +513,7 @@ struct mptcc_ctx {
 	long opt_long_batches = -1;      // narrowphase batches of 128 instead of 96 candidates: -1 = by launch size
 	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
 	long opt_np2 = 0;                // 1 = second-generation narrowphase (np2_kernels.cu): same speed on C5, see DESIGN.md section 5
+	long opt_expand4 = 0;            // np2: 1 = expand both trees per step (four tests); measured 37 % slower on C5
 	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
 	long opt_qnode = 0;              // np2: traverse the 32-byte quantised nodes (0 = the 64-byte fp32 nodes)
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
@@ -665,7 +666,7 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 // split pipeline (broadphase kernel -> candidate list -> narrowphase kernel, then the fused kernel as a
 // conditional overflow fall-back); everything else the fused kernel.
 // checkSelfCollision: after the environment kernels of a launch, OR the link-vs-link verdicts into its words.
-int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, int grid, cudaStream_t s) {
+int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, uint32_t *d_work, int grid, cudaStream_t s) {
 	if (!ctx->opt_self_collision || ctx->link_model_h.size() < 2) return MPTCC_OK;
 	KernelParams kp = kp_env;
 	kp.env = kp.agent;
@@ -673,6 +674,7 @@ int enqueue_self(mptcc_ctx *ctx, Device &d, const KernelParams &kp_env, int grid
 	kp.n_objects = (uint32_t)ctx->link_model_h.size();
 	kp.run_if = nullptr;
 	kp.ppw_log2 = 5;
+	kp.work_counter = d_work;  // (the environment launch may have run without a counter)
 	CU(cudaMemsetAsync(kp.work_counter, 0, sizeof(uint32_t), s));
 	const uint64_t need = ((kp.n_pose_sets + 31) / 32 + kWarpsPerCta - 1) / kWarpsPerCta;
 	const int g = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)grid, need));
@@ -723,6 +725,8 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			const DevModel &am = ctx->agent_h.models[ctx->link_model_h[0]];
 			uint32_t top = std::min<uint32_t>(2u * am.num_tris - 1u, (ctx->opt_qnode && ctx->env_q_ok) ? kAgentTopMaxQ : kAgentTopMax);
 			kp.qnode = (ctx->opt_qnode && ctx->env_q_ok) ? 1u : 0u;
+			// (both trees expanded per step: up to three pending pairs per level, 128 stack entries per lane)
+			kp.expand4 = (ctx->opt_expand4 && 3u * std::max(ctx->env_h.max_depth, ctx->agent_h.max_depth) + 4u <= 2u * kLaneStackCap) ? 1u : 0u;
 			if (ctx->opt_agent_top >= 0) top = std::min<uint32_t>(top, (uint32_t)ctx->opt_agent_top);
 			if (top && top % 2 == 0) --top;
 			kp.agent_top = top;
@@ -781,19 +785,23 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		if (timed) CU(cudaEventRecord(d.phase_ev[4], s));
 		ctx->ctr.n_kernel_launches += 3;
 		ctx->ctr.n_pose_sets += n;
-		return enqueue_self(ctx, d, kp, grid, s);
+		return enqueue_self(ctx, d, kp, d_work, grid, s);
 	}
-	CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
-	if (kp.ppw_log2 < 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
 	const uint64_t chunks = (n + (1ull << kp.ppw_log2) - 1) >> kp.ppw_log2;
 	int g = grid;
 	const uint64_t need = (chunks + kWarpsPerCta - 1) / kWarpsPerCta;
-	if ((uint64_t)g > need) g = (int)std::max<uint64_t>(need, 1);
+	if ((uint64_t)g >= need) {
+		g = (int)std::max<uint64_t>(need, 1);
+		kp.work_counter = nullptr;  // every warp gets (at most) one chunk: no counter to reset
+	} else {
+		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
+	}
+	if (kp.ppw_log2 < 5) CU(cudaMemsetAsync(d_bits, 0, sizeof(uint32_t) * ((n + 31) / 32), s));
 	const int e = launch_collide(kp, g, ctx->count, s);
 	if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "collide_kernel launch");
 	ctx->ctr.n_kernel_launches++;
 	ctx->ctr.n_pose_sets += n;
-	return enqueue_self(ctx, d, kp, grid, s);
+	return enqueue_self(ctx, d, kp, d_work, grid, s);
 }
 
 }  // namespace
@@ -1371,6 +1379,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 		ctx->opt_self_collision = value != 0;
 	} else if (k == "np2") {
 		ctx->opt_np2 = value != 0;
+	} else if (k == "expand4") {
+		ctx->opt_expand4 = value != 0;
 	} else if (k == "l2_persist") {
 		ctx->opt_l2_persist = value != 0;
 	} else if (k == "qnode") {

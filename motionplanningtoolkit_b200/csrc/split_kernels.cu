@@ -165,19 +165,20 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 							load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
 							float4 *out = p.cand_rec + 4ull * dst;
 							if (NP2) {
-								// (the exact pass of the np2 kernels recomputes the fp64 relative transform from the pose
-								// record: 96 bytes per candidate less to write, and less of the L2 taken from the trees)
 								uint2 mbase;
-								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, nullptr, mbase))
+								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase))
 									atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
 								p.cand_base[dst] = mbase;
 							} else {
 								make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
-								double *orel = p.cand_rel + 12ull * dst;
-								stg256(orel, rel[0], rel[1], rel[2], rel[3]);
-								stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
-								stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
 							}
+							// FCL's fp64 relative transform goes along for the exact pass.  (Recomputing it there from the pose
+							// record instead was measured: the broadphase kernel is not faster without these 96 bytes per
+							// candidate, and the narrowphase kernel is 3 % slower.)
+							double *orel = p.cand_rel + 12ull * dst;
+							stg256(orel, rel[0], rel[1], rel[2], rel[3]);
+							stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
+							stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
 #ifdef MPTCC_LIST_EF
 							stg256_evict_first(out, rec[0], rec[1]);
 							stg256_evict_first(out + 2, rec[2], rec[3]);
