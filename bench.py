@@ -344,8 +344,16 @@ def run_ours(args):
             numa_bound = os.sched_getaffinity(0) != cpus_before
         except Exception:
             numa_bound = False
+    cpu_group = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # a CPU-side group: a rank that waits in an NCCL barrier keeps a spinning kernel on its GPU, which must not
+        # happen while rank 0 drives ALL the GPUs from one context (the e2e_one_context leg below)
+        cpu_group = dist.new_group(backend="gloo")
+
+    def cpu_barrier():
+        if world > 1:
+            dist.barrier(group=cpu_group)
 
     def barrier():
         if world > 1:
@@ -487,7 +495,8 @@ def run_ours(args):
                 words_rank0.append(np.array(chk.check_poses(host_poses[b].array, fmt)))
         else:
             chk.close()                             # free this rank's device memory and staging buffers
-        barrier()
+        torch.cuda.synchronize()
+        cpu_barrier()
         if rank == 0:
             big = capi.PinnedArray((per_gpu * world, rec), np.float64)
             for r in range(world):
@@ -509,7 +518,7 @@ def run_ours(args):
                                        "note": "ONE process, ONE mptcc context over all %d GPUs (mptcc_create(n_devices)), "
                                                "one blocking mptcc_check_poses per step on pinned host buffers" % world}
             one.close()
-        barrier()
+        cpu_barrier()
 
     if rank == 0:
         # ---- parity on the whole batch + CPU baseline + roofline (rank 0, N = 1 only for the CPU timing) -----

@@ -45,7 +45,7 @@ def launches():
         agg[k][1] += ms
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(P, "%s_launch_summary.txt" % tag), "w") as f:
-        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 200 ; command: python bench.py --steps 5 --warmup 3\n")
+        f.write("ncu --metrics gpu__time_duration.sum --clock-control none -c 200 ; command: python bench.py --steps 5 --warmup 3 --no-other-configs\n")
         f.write("(cold-cache, serialised launch times: compare SHARES, not absolutes)\n\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
             f.write("%6.2f%%  %9.3f ms  n=%3d  avg %8.3f ms  %s\n" % (100 * v[1] / tot, v[1], v[0], v[1] / v[0], k))
@@ -59,7 +59,7 @@ def kernel(rep, name, cubin):
     hdr, units, vals = rows[0], rows[1], rows[2]
     got = {}
     with open(os.path.join(P, "%s_%s_metrics.txt" % (tag, name)), "w") as f:
-        f.write("ncu --set full --clock-control none --import-source on -k regex:%s -s 3 -c 1 ; command: python bench.py --steps 2 --warmup 3\n" % name)
+        f.write("ncu --set full --clock-control none --import-source on -k regex:%s -s 3 -c 1 ; command: python bench.py --steps 2 --warmup 3 --no-other-configs\n" % name)
         f.write("C5 workload, 2^20 pose-sets per launch (profiled launch: serialised, NOT a bench number)\n\n")
         for i, h in enumerate(hdr):
             if h in KEEP:
