@@ -91,7 +91,9 @@ int mptcc_num_devices(const mptcc_ctx *ctx);
 /* StaticEnvironmentMeshHandler(file, pose) (/root/reference/utilities/meshhandler.hpp:18-55): one
  * collision object per non-empty sub-mesh.  obj_pose7: [n_objects][7] x y z qw qx qy qz (the
  * reference gives every object the same "Environment Location").  Builds the FCL-identical OBB
- * trees on the host, flattens them and replicates them on every device of the context. */
+ * trees on the host, flattens them and replicates them on every device of the context.
+ * Both set_* calls first wait for everything outstanding on the context (submits, device-buffer launches): the
+ * scene arrays are replaced in place.  A mesh with a triangle index >= nv is refused (MPTCC_ERR_INVALID). */
 int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshes, const double *obj_pose7);
 
 /* Agent::getMeshes() (/root/reference/agents/omnidirectional.hpp:186-189,
@@ -133,7 +135,9 @@ int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start
 
 /* ---- queries: device buffers (inputs already resident in HBM) -------------------------------- */
 /* d_poses / d_verdict_bits are device pointers on device slot `slot` (0..n_devices-1); the launch is
- * enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's stream) and NOT synchronised. */
+ * enqueued on `cuda_stream` (a cudaStream_t, NULL = the context's stream) and NOT synchronised.
+ * Every launch of a slot shares that slot's candidate list and work counters: keep at most ONE launch in flight per
+ * slot (chain launches on one stream, or synchronise in between); launches on different slots are independent. */
 int mptcc_check_poses_device(mptcc_ctx *ctx, int slot, uint64_t n_pose_sets, const double *d_poses,
                              int pose_format, uint32_t *d_verdict_bits, void *cuda_stream);
 int mptcc_synchronize(mptcc_ctx *ctx);
