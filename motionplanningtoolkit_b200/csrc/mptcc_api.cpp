@@ -662,6 +662,21 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 	return MPTCC_OK;
 }
 
+// Entry points that do not go through mptcc_wait (device buffers, on-device edges) look at the overflow flag of their
+// candidate list after a synchronise, so that a dense scene gets a longer list from the next launch on there too.
+// The stream the list was used on must be idle.
+void note_overflow(mptcc_ctx *ctx, Device &d, SplitBufs &sb) {
+	(void)d;
+	if (!sb.ctl.p) return;
+	unsigned int h[4] = {0, 0, 0, 0};
+	if (cudaMemcpy(h, sb.ctl.p, sizeof h, cudaMemcpyDeviceToHost) != cudaSuccess) {
+		cudaGetLastError();
+		return;
+	}
+	if ((h[1] & 1u) && ctx->opt_split_cap < 64) ctx->opt_split_cap = std::min<long>(64, ctx->opt_split_cap * 2);
+	if (h[1]) cudaMemset(sb.ctl.p + 1, 0, sizeof(unsigned int));  // seen: a stale flag must not grow the list again
+}
+
 // Enqueue (memsets +) kernels for n pose-sets already on the device.  Large single-link batches take the
 // split pipeline (broadphase kernel -> candidate list -> narrowphase kernel, then the fused kernel as a
 // conditional overflow fall-back); everything else the fused kernel.
@@ -1232,42 +1247,49 @@ int mptcc_check_omni_edges(mptcc_ctx *ctx, uint64_t n_edges, const double *start
 	if (!(dt > 0.0)) return fail(ctx, MPTCC_ERR_INVALID, "dt must be positive");
 	if (n_edges == 0) return MPTCC_OK;
 	if (!start_end || !edge_safe) return fail(ctx, MPTCC_ERR_INVALID, "null buffer");
-	// sub-batches of edges whose poses fit the device-side pose buffer, round-robin over the devices
+	// sub-batches of edges whose poses fit the device-side pose buffer, one per device and round: every device of the
+	// context gets its sub-batch enqueued before any of them is waited for, so the devices work concurrently
 	const uint64_t max_poses = 1ull << 21;
 	const size_t nd = ctx->devs.size();
-	std::vector<unsigned long long> off;
+	std::vector<std::vector<unsigned long long> > offs(nd);  // per device: must stay alive until its stream is done
 	uint64_t e0 = 0;
-	size_t turn = 0;
 	while (e0 < n_edges) {
-		off.assign(1, 0ull);
-		uint64_t e1 = e0;
-		while (e1 < n_edges && (off.back() < max_poses || e1 == e0)) {
-			off.push_back(off.back() + omni_pose_count(start_end + 6 * e1, dt));
-			++e1;
+		size_t used = 0;
+		for (size_t di = 0; di < nd && e0 < n_edges; ++di, ++used) {
+			std::vector<unsigned long long> &off = offs[di];
+			off.assign(1, 0ull);
+			uint64_t e1 = e0;
+			while (e1 < n_edges && (off.back() < max_poses || e1 == e0)) {
+				off.push_back(off.back() + omni_pose_count(start_end + 6 * e1, dt));
+				++e1;
+			}
+			const uint64_t ne = e1 - e0, np = off.back();
+			Device &d = ctx->devs[di];
+			CU(cudaSetDevice(d.id));
+			cudaStream_t s = d.stream[0];
+			CU(d.edge_in.reserve(6 * ne));
+			CU(d.edge_off.reserve(ne + 1));
+			CU(d.edge_poses.reserve(3 * np));
+			CU(d.edge_bits.reserve((np + 31) / 32));
+			CU(d.edge_safe.reserve(ne));
+			CU(d.edge_work.reserve(1));
+			CU(cudaMemcpyAsync(d.edge_in.p, start_end + 6 * e0, sizeof(double) * 6 * ne, cudaMemcpyHostToDevice, s));
+			CU(cudaMemcpyAsync(d.edge_off.p, off.data(), sizeof(unsigned long long) * (ne + 1), cudaMemcpyHostToDevice, s));
+			int e = launch_expand_omni_edges(d.edge_in.p, d.edge_off.p, ne, np, dt, d.edge_poses.p, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "expand_omni_edges launch");
+			rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_T3, d.edge_bits.p, d.edge_work.p, s, &d.split[kPipe + 1]);
+			if (rc != MPTCC_OK) return rc;
+			e = launch_reduce_segments(d.edge_bits.p, d.edge_off.p, ne, d.edge_safe.p, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "reduce_segments launch");
+			CU(cudaMemcpyAsync(edge_safe + e0, d.edge_safe.p, ne, cudaMemcpyDeviceToHost, s));
+			e0 = e1;
 		}
-		const uint64_t ne = e1 - e0, np = off.back();
-		Device &d = ctx->devs[turn % nd];
-		++turn;
-		CU(cudaSetDevice(d.id));
-		cudaStream_t s = d.stream[0];
-		CU(cudaStreamSynchronize(s));  // the host vector `off` and the device buffers are reused
-		CU(d.edge_in.reserve(6 * ne));
-		CU(d.edge_off.reserve(ne + 1));
-		CU(d.edge_poses.reserve(3 * np));
-		CU(d.edge_bits.reserve((np + 31) / 32));
-		CU(d.edge_safe.reserve(ne));
-		CU(d.edge_work.reserve(1));
-		CU(cudaMemcpyAsync(d.edge_in.p, start_end + 6 * e0, sizeof(double) * 6 * ne, cudaMemcpyHostToDevice, s));
-		CU(cudaMemcpyAsync(d.edge_off.p, off.data(), sizeof(unsigned long long) * (ne + 1), cudaMemcpyHostToDevice, s));
-		int e = launch_expand_omni_edges(d.edge_in.p, d.edge_off.p, ne, np, dt, d.edge_poses.p, s);
-		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "expand_omni_edges launch");
-		rc = enqueue_kernel(ctx, d, np, d.edge_poses.p, MPTCC_POSE_T3, d.edge_bits.p, d.edge_work.p, s, &d.split[kPipe + 1]);
-		if (rc != MPTCC_OK) return rc;
-		e = launch_reduce_segments(d.edge_bits.p, d.edge_off.p, ne, d.edge_safe.p, s);
-		if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "reduce_segments launch");
-		CU(cudaMemcpyAsync(edge_safe + e0, d.edge_safe.p, ne, cudaMemcpyDeviceToHost, s));
-		CU(cudaStreamSynchronize(s));  // `off` goes out of scope / is rewritten next round
-		e0 = e1;
+		for (size_t di = 0; di < used; ++di) {  // the round's buffers (host `offs`, device edge_*) are reused by the next one
+			Device &d = ctx->devs[di];
+			CU(cudaSetDevice(d.id));
+			CU(cudaStreamSynchronize(d.stream[0]));
+			note_overflow(ctx, d, d.split[kPipe + 1]);
+		}
 	}
 	return MPTCC_OK;
 }
@@ -1291,6 +1313,7 @@ int mptcc_synchronize(mptcc_ctx *ctx) {
 	for (auto &d : ctx->devs) {
 		CU(cudaSetDevice(d.id));
 		CU(cudaDeviceSynchronize());
+		note_overflow(ctx, d, d.split[kPipe]);  // candidate list of mptcc_check_poses_device
 	}
 	return MPTCC_OK;
 }

@@ -376,3 +376,32 @@ def test_compact_pose_formats_equal_rt12(built, opts):
     T3 = np.stack([rng.uniform(3 * 9000, -1.7, 1.7) for _ in range(3)], 1)
     want = sc2.oracle_bits(scenes.translation_poses(T3).reshape(-1, 3, 12))
     assert_bits_equal(chk2.check_poses(T3.reshape(-1, 3, 3), capi.POSE_T3), want, 9000, "T3 3 links")
+
+
+def test_multi_device_edges_and_device_buffer_overflow(box_scene):
+    """mptcc_check_omni_edges on a 2-device context (every device gets its sub-batch before any is waited for) equals
+    the single-device result; the device-buffer entry point with a candidate list that is too small falls back and
+    still gives the oracle's words, and mptcc_synchronize notes the overflow so the next launch has a longer list."""
+    import torch
+    rng = scenes.SplitMix64(777)
+    n = 300000                                            # > 2^21 poses in total: several sub-batches per device
+    start = np.stack([rng.uniform(n, -3, 3) for _ in range(3)], 1)
+    d = np.stack([rng.uniform(n, -1, 1) for _ in range(3)], 1)
+    end = start + d / np.linalg.norm(d, axis=1, keepdims=True) * rng.uniform(n, 0.0, 2.5)[:, None]
+    edges = np.concatenate([start, end], axis=1)
+    one = box_scene.checker().check_omni_edges(edges, 0.1)
+    assert 0 < one.sum() < n
+    if torch.cuda.device_count() >= 2:
+        assert np.array_equal(box_scene.checker(2).check_omni_edges(edges, 0.1), one)
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    sc = Scene(env, [meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")])
+    poses = scenes.random_poses_near_objects(rng, 40000, env, 2.0)
+    want = sc.oracle_bits(poses)
+    chk = sc.checker(split=1, split_min=32, split_cap=1)
+    buf = torch.from_numpy(poses).cuda()
+    bits = torch.zeros((len(poses) + 31) // 32, dtype=torch.int32, device="cuda")
+    for _ in range(3):                                    # 1st: overflow + fall-back; later: longer list, no overflow
+        bits.zero_()
+        chk.check_poses_device(len(poses), buf.data_ptr(), bits.data_ptr(), capi.POSE_RT12, 0, None)
+        chk.synchronize()
+        assert_bits_equal(bits.cpu().numpy().view(np.uint32), want, len(poses), "device buffers, small candidate list")
