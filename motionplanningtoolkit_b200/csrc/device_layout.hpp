@@ -132,6 +132,8 @@ struct KernelParams {
 	uint32_t expand4;              // 1: a narrowphase step expands both trees (four tests), 0: FCL's one-tree descent (two)
 	uint32_t qnode;                // 1: traverse nodeq (32-byte nodes), 0: node32
 	uint32_t agent_top;            // agent nodes [0, agent_top) of link model 0 are staged in shared memory (breadth-first ids)
+	// third-generation narrowphase (np3_kernels.cu)
+	const float4 *agent_swz;       // link model 0's node32 records in the bank-swizzled order the np3 kernel stages with TMA
 };
 
 // index of the counters in KernelParams::counters
@@ -175,6 +177,10 @@ int launch_narrowphase(const KernelParams &p, int sm_count, bool count, bool lon
 // np2_kernels.cu: second-generation narrowphase (TMA-staged agent tree top, child-frame SAT) + its exact-pass kernel
 int launch_narrowphase2(const KernelParams &p, int sm_count, bool count, bool long_batches, void *stream);
 int launch_exact(const KernelParams &p, int sm_count, bool count, void *stream);
+// np3_kernels.cu: third-generation narrowphase (streaming lanes, whole agent tree in shared memory); uses the np2
+// broadphase records and exact-pass kernel
+int launch_narrowphase3(const KernelParams &p, int sm_count, bool count, void *stream);
+unsigned np3_agent_top_max();
 
 // edge_kernels.cu
 int launch_expand_omni_edges(const double *d_edges, const unsigned long long *d_offsets, unsigned long long n_edges,

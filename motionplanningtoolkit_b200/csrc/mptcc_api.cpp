@@ -11,6 +11,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -459,6 +460,7 @@ struct Device {
 	DevBuf<uint4> bp_nodes;
 	DevBuf<uint32_t> link_model;
 	DevBuf<DevObject> self_objects;  // one per link (model id only): the "objects" of the self-collision kernel
+	DevBuf<float4> agent_swz;        // link model 0's traversal nodes, bank-swizzled for the np3 kernel's shared-memory copy
 	DevBuf<double> poses[kPipe];
 	DevBuf<uint32_t> bits[kPipe];
 	DevBuf<uint32_t> work[kPipe];
@@ -495,6 +497,7 @@ struct mptcc_ctx {
 	float bp_origin[3] = {0.f, 0.f, 0.f}, bp_inv_cell[3] = {1.f, 1.f, 1.f};
 	std::vector<uint32_t> link_model_h;
 	std::vector<DevObject> self_objects_h;
+	std::vector<float4> agent_swz_h;
 	bool env_set = false, agent_set = false;
 	bool env_q_ok = true, agent_q_ok = true;  // every model small enough for the 24-bit links of the quantised nodes
 	std::string err;
@@ -517,6 +520,8 @@ struct mptcc_ctx {
 	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
 	long opt_qnode = 0;              // np2: traverse the 32-byte quantised nodes (0 = the 64-byte fp32 nodes)
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
+	long opt_np3 = 1;                // third-generation narrowphase (np3_kernels.cu, streaming lanes): the default; 0 = the round-1 kernel
+	                                 // (split_kernels.cu), or np2_kernels.cu with np2 = 1
 	mptcc_counters ctr{};
 	uint64_t submitted = 0, completed = 0;  // tickets of mptcc_submit_poses
 	int ctas_per_sm_cached = -1;
@@ -583,6 +588,7 @@ int upload_scene_part(mptcc_ctx *ctx, bool env) {
 			CU(d.agent.upload(ctx->agent_h, d.stream[0]));
 			CU(d.link_model.upload(ctx->link_model_h, d.stream[0]));
 			CU(d.self_objects.upload(ctx->self_objects_h, d.stream[0]));
+			CU(d.agent_swz.upload(ctx->agent_swz_h, d.stream[0]));
 		}
 		CU(cudaStreamSynchronize(d.stream[0]));
 	}
@@ -730,7 +736,8 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		kp.overflow = sb->ctl.p + 1;
 		kp.work_counter2 = sb->ctl.p + 2;
 		kp.cand_cap = (unsigned int)cap64;
-		const bool np2 = ctx->opt_np2 != 0;
+		const bool np3 = ctx->opt_np3 != 0;
+		const bool np2 = ctx->opt_np2 != 0 || np3;
 		kp.cand_base = sb->base.p;
 		kp.xq = sb->xq.p;
 		kp.xq_total = sb->ctl.p + 3;
@@ -743,8 +750,16 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			// (both trees expanded per step: up to three pending pairs per level, 128 stack entries per lane)
 			kp.expand4 = (ctx->opt_expand4 && 3u * std::max(ctx->env_h.max_depth, ctx->agent_h.max_depth) + 4u <= 2u * kLaneStackCap) ? 1u : 0u;
 			if (ctx->opt_agent_top >= 0) top = std::min<uint32_t>(top, (uint32_t)ctx->opt_agent_top);
+			if (np3) {
+				// np3 stages agent nodes only on request (agent_top = n): measured on C5, the shared memory they take away
+				// from L1 costs more than the LDS gathers save
+				top = ctx->opt_agent_top > 0 ? std::min<uint32_t>(std::min<uint32_t>(2u * am.num_tris - 1u, np3_agent_top_max()), (uint32_t)ctx->opt_agent_top) : 0u;
+				kp.qnode = 0u;
+				kp.expand4 = 0u;
+			}
 			if (top && top % 2 == 0) --top;
 			kp.agent_top = top;
+			kp.agent_swz = d.agent_swz.p;
 		}
 		CU(cudaMemsetAsync(sb->ctl.p, 0, 4 * sizeof(unsigned int), s));
 		CU(cudaMemsetAsync(d_work, 0, sizeof(uint32_t), s));
@@ -774,8 +789,8 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			CU(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));
 		}
 		if (np2) {
-			e = launch_narrowphase2(kp, d.sm_count, ctx->count, long_batches, s);
-			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "narrowphase2_kernel launch");
+			e = np3 ? launch_narrowphase3(kp, d.sm_count, ctx->count, s) : launch_narrowphase2(kp, d.sm_count, ctx->count, long_batches, s);
+			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, np3 ? "narrowphase3_kernel launch" : "narrowphase2_kernel launch");
 			if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
 			e = launch_exact(kp, d.sm_count, ctx->count, s);
 			if (e != 0) return cuda_fail(ctx, (cudaError_t)e, "exact_kernel launch");
@@ -881,6 +896,21 @@ int mptcc_create(mptcc_ctx **out, int n_devices, const int *device_ids) {
 		if (cudaMemset(d.counters.p, 0, sizeof(unsigned long long) * CTR_N) != cudaSuccess) return bail(MPTCC_ERR_CUDA);
 	}
 	*out = c.release();
+	// MPTCC_OPTIONS="name=value,name=value": options applied to every new context (A/B runs of the test-suite and the
+	// bench against a kernel option without touching their code); unknown names are ignored here
+	if (const char *envo = std::getenv("MPTCC_OPTIONS")) {
+		std::string all(envo);
+		size_t pos = 0;
+		while (pos < all.size()) {
+			size_t end = all.find(',', pos);
+			if (end == std::string::npos) end = all.size();
+			const std::string kv = all.substr(pos, end - pos);
+			const size_t eq = kv.find('=');
+			if (eq != std::string::npos) mptcc_set_option(*out, kv.substr(0, eq).c_str(), std::atol(kv.c_str() + eq + 1));
+			pos = end + 1;
+		}
+		(*out)->err.clear();
+	}
 	return MPTCC_OK;
 }
 
@@ -896,6 +926,7 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.bp_nodes.release();
 		d.link_model.release();
 		d.self_objects.release();
+		d.agent_swz.release();
 		d.counters.release();
 		d.work_user.release();
 		for (auto &sb : d.split) sb.release();
@@ -1044,9 +1075,19 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 		HostBvh b;
 		if (!build_bvh(m.xyz, m.nv, m.tri, m.nt, b))
 			return fail(ctx, MPTCC_ERR_INVALID, "agent link " + std::to_string(j) + " has an empty mesh");
-		const uint32_t id = ctx->agent_h.add(b);
+		const uint32_t id = ctx->agent_h.add(b, true);  // breadth-first device ids: the top of the tree is one contiguous block
 		seen[key] = id;
 		ctx->link_model_h.push_back(id);
+	}
+	{
+		// link model 0's traversal nodes in the order the np3 kernel keeps them in shared memory: part k (16 bytes) of
+		// node i at position (k + (i >> 1)) & 3 of the node's 64 bytes (np3_kernels.cu, node_shared_swz)
+		const DevModel &am = ctx->agent_h.models[ctx->link_model_h[0]];
+		const uint32_t nn = 2u * am.num_tris - 1u;
+		ctx->agent_swz_h.assign(4 * (size_t)nn, make_float4(0.f, 0.f, 0.f, 0.f));
+		for (uint32_t i = 0; i < nn; ++i)
+			for (uint32_t k = 0; k < 4; ++k)
+				ctx->agent_swz_h[4 * (size_t)i + ((k + (i >> 1)) & 3u)] = ctx->agent_h.node32[4 * ((size_t)am.node_base + i) + k];
 	}
 	ctx->self_objects_h.assign(ctx->link_model_h.size(), DevObject{});
 	for (size_t j = 0; j < ctx->link_model_h.size(); ++j) ctx->self_objects_h[j].model = ctx->link_model_h[j];
@@ -1400,8 +1441,11 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 			if (drc != MPTCC_OK) return drc;
 		}
 		ctx->opt_self_collision = value != 0;
+	} else if (k == "np3") {
+		ctx->opt_np3 = value != 0;
 	} else if (k == "np2") {
 		ctx->opt_np2 = value != 0;
+		if (value != 0) ctx->opt_np3 = 0;  // (np3 is the default; asking for np2 selects np2)
 	} else if (k == "expand4") {
 		ctx->opt_expand4 = value != 0;
 	} else if (k == "l2_persist") {

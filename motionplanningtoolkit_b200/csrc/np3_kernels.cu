@@ -1,0 +1,570 @@
+// np3_kernels.cu -- narrowphase of the split pipeline, third generation: STREAMING lanes.
+//
+// The first two generations hand a warp a batch of 96/128 candidates and let its lanes steal pending sub-trees from
+// each other once the batch has no unstarted candidate left.  A simulation of that schedule on the real geometry
+// (tools/research/warp_sim.c) shows what it costs on the benchmark scene: every batch ends in a tail in which the
+// lanes explore, speculatively and in parallel, the sub-trees of the few long candidates -- 57-61 OBB tests per
+// pose-set instead of the 50 of a schedule without batch ends, and 26-29 busy lanes per step instead of 31.
+// Here a lane that runs out of work simply starts the next candidate of the global list:
+//
+//   * every lane owns a ring of three shared-memory slots: the record of its CURRENT candidate (read back with four
+//     conflict-free LDS.128 per step -- keeping it in registers was measured: the kernel then needs 164 registers and
+//     spills at 128) and the records of its next TWO candidates, prefetched with cp.async while the lane is still
+//     busy, so starting a candidate costs no round trip to the list; no shared candidate table, no batch;
+//   * list indices are reserved in chunks of 64 with one atomicAdd per chunk;
+//   * lanes only steal from each other once the list is exhausted (the tail of the launch);
+//   * a contact is published with atomicOr and broadcast inside the warp by pose-set id (lanes working on the same
+//     pose-set drop their work; a small ring of recently settled pose-sets stops prefetched candidates and queued
+//     leaf pairs of that pose-set);
+//   * the whole agent tree (breadth-first numbering, as many nodes as fit beside the per-warp state: 2 590 of the
+//     blimp's 2 709) is staged in shared memory with TMA bulk copies, in a bank-swizzled layout prepared on the host,
+//     so that only environment nodes are gathered from L1/L2.
+// The SAT (child-frame, shared stationary half), the triangle filter, the inline fp64 re-decide of uncertain pairs and
+// the exact-pass queue are those of np2_kernels.cu.
+#include "collide_device.cuh"
+#include "np_sat.cuh"
+#include "launch_cache.hpp"
+
+namespace mptcc {
+namespace {
+
+#ifndef MPTCC_NP3_WARPS
+#define MPTCC_NP3_WARPS 16
+#endif
+#ifndef MPTCC_NP3_CHUNK
+#define MPTCC_NP3_CHUNK 64
+#endif
+#ifndef MPTCC_NP3_LEAF_AT
+#define MPTCC_NP3_LEAF_AT 32
+#endif
+constexpr int kNp3Warps = MPTCC_NP3_WARPS;
+constexpr unsigned kNp3Chunk = MPTCC_NP3_CHUNK;
+constexpr int kNp3LeafAt = MPTCC_NP3_LEAF_AT;  // queued leaf pairs that trigger a leaf phase
+constexpr int kNp3LeafCap = kNp3LeafAt + 64;   // a node step appends at most 64
+constexpr unsigned kNp3SlotBytes = 80u;        // 4 float4 record + (node_base, tri_base, pose-set, -)
+constexpr unsigned kNp3Depth = 2u;             // candidates prefetched per lane, consumed in order
+constexpr unsigned kNp3Ring = kNp3Depth + 1u;  // slots per lane: the current candidate + the prefetched ones
+constexpr unsigned kNp3WarpBytes = 32u * kNp3Ring * kNp3SlotBytes + (unsigned)kNp3LeafCap * 16u + 32u + 32u;
+constexpr unsigned kNp3TopOffset = 128u;       // the mbarrier lives in front of the staged tree
+constexpr unsigned kPlan3Env = 1u << 31, kPlan3Single = 1u << 30, kPlan3Idx = (1u << 30) - 1u;
+
+// Node i of the staged agent tree: part k (of 4 float4) sits at position (k + (i >> 1)) & 3 of its 64 bytes, so that
+// lanes fetching the same part of different nodes spread over all eight 16-byte bank groups.
+__device__ __forceinline__ Node node_shared_swz(const float4 *top, unsigned i) {
+	const float4 *b = top + 4u * i;
+	const unsigned r = i >> 1;
+	return Node{b[r & 3u], b[(r + 1u) & 3u], b[(r + 2u) & 3u], b[(r + 3u) & 3u]};
+}
+
+__device__ __forceinline__ void cp_async16(void *dst, const void *src) {
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void *dst, const void *src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst, const void *src) {
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// every group but the most recent one has landed
+__device__ __forceinline__ void cp_async_wait_but_one() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+__device__ __forceinline__ bool pose_settled(const uint32_t *hits, uint32_t pose) {
+	const uint4 a = *reinterpret_cast<const uint4 *>(hits), b = *reinterpret_cast<const uint4 *>(hits + 4);
+	return a.x == pose || a.y == pose || a.z == pose || a.w == pose || b.x == pose || b.y == pose || b.z == pose || b.w == pose;
+}
+
+#ifdef MPTCC_NP3_MAXREG
+#define NP3_BOUNDS __maxnreg__(MPTCC_NP3_MAXREG)
+#else
+#define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, 1)
+#endif
+
+template <bool COUNT, bool TOP>
+__global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	const unsigned lt = (1u << lane) - 1u;
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+	const unsigned ktop = TOP ? p.agent_top : 0u;
+	const unsigned top_bytes = ktop * 64u;
+	const float4 *atop = reinterpret_cast<const float4 *>(smem_raw + kNp3TopOffset);
+
+	// ---- TMA bulk copies of the (swizzled) agent tree into shared memory: one thread issues, all wait ------------
+	const unsigned mbar = (unsigned)__cvta_generic_to_shared(smem_raw);
+	if (top_bytes != 0u) {
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.init.shared.b64 [%0], %1;" ::"r"(mbar), "r"(1u) : "memory");
+			asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			asm volatile("mbarrier.arrive.expect_tx.relaxed.cta.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(top_bytes) : "memory");
+			const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_raw + kNp3TopOffset);
+			const char *src = reinterpret_cast<const char *>(p.agent_swz);
+			for (unsigned off = 0; off < top_bytes; off += 32768u) {
+				const unsigned len = top_bytes - off < 32768u ? top_bytes - off : 32768u;
+				asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst + off),
+				             "l"(src + off), "r"(len), "r"(mbar)
+				             : "memory");
+			}
+		}
+	}
+
+	unsigned char *wbase = smem_raw + kNp3TopOffset + ((top_bytes + 127u) & ~127u) + (size_t)warp * kNp3WarpBytes;
+	float4 *slots = reinterpret_cast<float4 *>(wbase) + 5u * kNp3Ring * (unsigned)lane;  // this lane's ring: [kNp3Ring][5]
+	uint4 *leafq = reinterpret_cast<uint4 *>(wbase + 32u * kNp3Ring * kNp3SlotBytes);  // [kNp3LeafCap] env prim, agent prim, list index, pose-set
+	uint32_t *hits = reinterpret_cast<uint32_t *>(wbase + 32u * kNp3Ring * kNp3SlotBytes + (unsigned)kNp3LeafCap * 16u);  // [8]
+	unsigned char *donor = reinterpret_cast<unsigned char *>(hits + 8);       // [32]
+
+	const bool skip = *p.overflow != 0u;  // overflowed list / non-rigid pose: the launch belongs to the fused fall-back
+	if (top_bytes != 0u) {
+		unsigned done = 0;
+		while (!done)
+			asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+			             : "=r"(done)
+			             : "r"(mbar), "r"(0u)
+			             : "memory");
+	}
+	if (skip) return;
+	const unsigned total = *p.cand_total;
+	if (lane < 8) hits[lane] = 0xffffffffu;
+	__syncwarp();
+
+	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
+	const float4 *__restrict__ tris2 = p.agent.tri32 + 3ull * m2.tri_base;
+	unsigned long long ctr[CTR_N];
+#pragma unroll
+	for (int i = 0; i < CTR_N; ++i) ctr[i] = 0;
+
+	// ---- lane state ----------------------------------------------------------------------------------------------
+	unsigned nb1 = 0, ci = 0, pose = 0xffffffffu;  // env node_base, list index, pose-set of the current candidate
+	unsigned rd = 0;                     // ring slot of the current candidate; the prefetched ones follow it
+	unsigned pf = 0, young = 0;          // prefetched candidates, how many of them were issued in the most recent
+	                                     // cp.async group (not consumable yet)
+	uint2 stk[kLaneStackCap];
+	unsigned top = 0;
+	uint2 cur = make_uint2(0u, 0u);
+	bool has = false;
+	unsigned qhead = 0, qend = 0, hit_w = 0;
+	bool exhausted = false;
+	int lq = 0;
+
+	while (true) {
+		if (!has && top != 0u) {
+			cur = stk[--top];
+			has = true;
+		}
+		unsigned im = __ballot_sync(FULL, !has);
+		if (im) {
+			const unsigned cm = __ballot_sync(FULL, pf > young);  // lanes holding a prefetched candidate that has landed
+			if (cm) {
+				cp_async_wait_but_one();
+				__syncwarp();
+				if (exhausted) {
+					// tail of the launch: prefetched candidates of busy lanes go to idle lanes that have none
+					const unsigned want = im & __ballot_sync(FULL, pf == 0u), give = cm & ~im;
+					if (want && give) {
+						const int grank = __popc(give & lt);
+						if ((give >> lane) & 1u) donor[grank] = (unsigned char)lane;
+						__syncwarp();
+						const int r = __popc(want & lt);
+						const bool taker = ((want >> lane) & 1u) && r < __popc(give);
+						const int src = taker ? (int)donor[r] : lane;
+						const unsigned srd = __shfl_sync(FULL, rd, src);
+						const bool given = ((give >> lane) & 1u) && grank < __popc(want);
+						if (taker) {
+							// copy the donor's oldest prefetched record into my next slot, as if I had prefetched it
+							const float4 *from = reinterpret_cast<const float4 *>(wbase) + 5u * (kNp3Ring * (unsigned)src + (srd + 1u) % kNp3Ring);
+							float4 *to = slots + 5u * ((rd + 1u) % kNp3Ring);
+#pragma unroll
+							for (int k = 0; k < 5; ++k) to[k] = from[k];
+							pf = 1u;
+						}
+						__syncwarp();
+						if (given) {
+							// the donor's remaining prefetched record (if any) moves up: rotate by making the given slot the
+							// "current" one is not possible while the lane is busy, so swap the two prefetched slots instead
+							if (pf == 2u) {
+								float4 *a = slots + 5u * ((rd + 1u) % kNp3Ring);
+								const float4 *bsl = slots + 5u * ((rd + 2u) % kNp3Ring);
+#pragma unroll
+								for (int k = 0; k < 5; ++k) a[k] = bsl[k];
+							}
+							--pf;
+						}
+						__syncwarp();
+					}
+				}
+				if (!has && pf > young) {
+					rd = (rd + 1u) % kNp3Ring;
+					--pf;
+					const float4 s4 = slots[5u * rd + 4u];
+					ci = __float_as_uint(s4.w);
+					pose = __float_as_uint(s4.z);
+					nb1 = __float_as_uint(s4.x);
+					if (!pose_settled(hits, pose)) {
+						cur = make_uint2(0u, kPlan3Single);
+						has = true;
+					}
+				}
+				im = __ballot_sync(FULL, !has);
+			}
+		}
+		// ---- prefetch: every lane keeps kNp3Depth candidates in flight ---------------------------------------------
+		young = 0u;
+		if (im && !exhausted) {
+			unsigned need = __ballot_sync(FULL, pf < kNp3Depth);
+			while (need) {
+				if (qhead == qend) {
+					unsigned first = 0;
+					if (lane == 0) first = atomicAdd(p.work_counter2, kNp3Chunk);
+					first = __shfl_sync(FULL, first, 0);
+					if (first >= total) {
+						exhausted = true;
+						break;
+					}
+					qhead = first;
+					qend = total - first < kNp3Chunk ? total : first + kNp3Chunk;
+				}
+				const unsigned avail = qend - qhead;
+				const unsigned rank = (unsigned)__popc(need & lt);
+				if (((need >> lane) & 1u) && rank < avail) {
+					const unsigned idx = qhead + rank;
+					float4 *s = slots + 5u * ((rd + pf + 1u) % kNp3Ring);
+					const float4 *g = p.cand_rec + 4ull * idx;
+					cp_async16(s, g);
+					cp_async16(s + 1, g + 1);
+					cp_async16(s + 2, g + 2);
+					cp_async16(s + 3, g + 3);
+					cp_async8(s + 4, p.cand_base + idx);
+					cp_async4(reinterpret_cast<char *>(s + 4) + 8, p.cand_pose + idx);
+					reinterpret_cast<unsigned *>(s + 4)[3] = idx;
+					++pf;
+					++young;
+				}
+				const unsigned nneed = (unsigned)__popc(need);
+				qhead += nneed < avail ? nneed : avail;
+				need = __ballot_sync(FULL, pf < kNp3Depth);
+			}
+		}
+		cp_async_commit();
+		if (im) {
+			// ---- tail: idle lanes steal the top pending plan of a busy lane (with its candidate) ---------------------
+			if (exhausted && !p.no_steal) {
+				const unsigned dm = __ballot_sync(FULL, has && top != 0u);
+				const unsigned tm = im & ~__ballot_sync(FULL, pf != 0u);  // idle lanes without a prefetched candidate of their own
+				if (dm && tm) {
+					const int n_thieves = __popc(tm), n_donors = __popc(dm);
+					const int drank = __popc(dm & lt);
+					const bool is_donor = (dm >> lane) & 1u;
+					if (is_donor) donor[drank] = (unsigned char)lane;
+					__syncwarp();
+					const int r = __popc(tm & lt);
+					const bool thief = ((tm >> lane) & 1u) && r < n_donors;
+					const int from = thief ? (int)donor[r] : lane;
+					uint2 e = make_uint2(0u, 0u);
+					if (is_donor && drank < n_thieves) e = stk[--top];
+					e.x = __shfl_sync(FULL, e.x, from);
+					e.y = __shfl_sync(FULL, e.y, from);
+					const unsigned frd = __shfl_sync(FULL, rd, from);
+					const unsigned fnb1 = __shfl_sync(FULL, nb1, from), fci = __shfl_sync(FULL, ci, from), fpose = __shfl_sync(FULL, pose, from);
+					if (thief) {
+						const float4 *src = reinterpret_cast<const float4 *>(wbase) + 5u * (kNp3Ring * (unsigned)from + frd);
+						float4 *to = slots + 5u * rd;
+#pragma unroll
+						for (int k = 0; k < 4; ++k) to[k] = src[k];
+						nb1 = fnb1;
+						ci = fci;
+						pose = fpose;
+					}
+					if (thief) {
+						cur = e;
+						has = true;
+					}
+					__syncwarp();
+				}
+			}
+		}
+		const unsigned am = __ballot_sync(FULL, has);
+		if (am == 0u && lq == 0) {
+			if (exhausted && __ballot_sync(FULL, pf != 0u) == 0u) break;
+			continue;
+		}
+
+		if (lq >= kNp3LeafAt || am == 0u) {
+			// ---- leaf phase: up to 32 triangle pairs ------------------------------------------------------------------
+			const int k = lq < 32 ? lq : 32;
+			lq -= k;
+			int verdict = TRI_SEPARATED;
+			bool certified = false;
+			uint4 e = make_uint4(0u, 0u, 0u, 0xfffffffeu);
+			uint2 base = make_uint2(0u, 0u);
+			float tn1 = 0.f;
+			if (lane < k) {
+				e = leafq[lq + lane];
+				if (!pose_settled(hits, e.w)) {
+					const float4 *rp = p.cand_rec + 4ull * e.z;
+					const F8 ra = ldg256(rp), rb = ldg256(rp + 2);
+					RelF x;
+					x.R[0] = ra.a.x; x.R[1] = ra.a.y; x.R[2] = ra.a.z; x.R[3] = ra.a.w;
+					x.R[4] = ra.b.x; x.R[5] = ra.b.y; x.R[6] = ra.b.z; x.R[7] = ra.b.w;
+					x.R[8] = rb.a.x; x.T[0] = rb.a.y; x.T[1] = rb.a.z; x.T[2] = rb.a.w;
+					x.S = rb.b.w;
+					tn1 = (fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2])) * 1.000001f;
+					base = p.cand_base[e.z];
+					const float4 *t1 = p.env.tri32 + 3ull * (base.y + e.x);
+					const float4 *t2 = tris2 + 3ull * e.y;
+					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
+					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
+					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
+					if (verdict == TRI_INTERSECT && !p.always_replay) {
+						// path certificate, evaluated from the fp32 record: a larger magnitude
+						// only makes it stricter
+						const DevModel &m1 = p.env.models[p.objects[p.cand_obj[e.z]].model];
+						const double mag = (double)tn1 + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+						                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
+						                   m1.esum + m2.esum;
+						const double mu = fmin((double)p.env.mu_chain[base.y + e.x], (double)p.agent.mu_chain[m2.tri_base + e.y]);
+						certified = mu >= 1e-5 * mag;
+					}
+				}
+			}
+			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
+			if (certified) atomicOr(p.verdict_bits + (e.w >> 5), 1u << (e.w & 31u));  // first contact settles the pose-set
+			unsigned hm = __ballot_sync(FULL, certified);
+#ifndef MPTCC_NP3_DEFER_ALL
+			// Pairs inside the fp32 error band: re-decide them now, in fp64 with FCL's operation order (the 17 axes over
+			// 17 lanes), because a contact found here ends the pose-set's traversal.
+			{
+				unsigned um = __ballot_sync(FULL, verdict == TRI_UNCERTAIN);
+				while (um) {
+					const int from = __ffs(um) - 1;
+					um &= um - 1;
+					const uint32_t c = __shfl_sync(FULL, e.z, from), ps = __shfl_sync(FULL, e.w, from);
+					const uint32_t t1 = __shfl_sync(FULL, e.x, from), t2 = __shfl_sync(FULL, e.y, from);
+					const uint32_t tb = __shfl_sync(FULL, base.y, from);
+					// settled by an earlier pair of this round?  (warp-uniform)
+					unsigned same = __ballot_sync(FULL, ((hm >> lane) & 1u) && e.w == ps);
+					if (same) {
+						if (lane == from) verdict = TRI_SEPARATED;
+						continue;
+					}
+					if (COUNT) ctr[CTR_EXACT] += 1;
+					const bool hit = exact_tri_intersect_warp(p.cand_rel + 12ull * c, p.env.tri64 + 9ull * (tb + t1),
+					                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
+					if (lane == from) verdict = hit ? TRI_INTERSECT : TRI_SEPARATED;
+					if (hit) {  // certificate with the record's magnitudes; uncertified contacts go to exact_kernel (path replay)
+						bool cert2 = false;
+						if (lane == from && !p.always_replay) {
+							const DevModel &m1 = p.env.models[p.objects[p.cand_obj[c]].model];
+							const double mag = (double)tn1 + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+							                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
+							                   m1.esum + m2.esum;
+							const double mu = fmin((double)p.env.mu_chain[tb + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
+							if (mu >= 1e-5 * mag) {
+								atomicOr(p.verdict_bits + (ps >> 5), 1u << (ps & 31u));
+								verdict = TRI_SEPARATED;  // settled
+								cert2 = true;
+							}
+						}
+						if (__ballot_sync(FULL, cert2)) hm |= 1u << from;
+					}
+				}
+			}
+#endif
+			// contacts whose path certificate does not hold (and, with MPTCC_NP3_DEFER_ALL, every pair the filter could
+			// not settle) go to the exact pass
+			const bool defer = verdict != TRI_SEPARATED && !certified;
+			const unsigned dmk = __ballot_sync(FULL, defer);
+			if (dmk) {
+				unsigned qb = 0;
+				if (lane == 0) qb = atomicAdd(p.xq_total, (unsigned)__popc(dmk));
+				qb = __shfl_sync(FULL, qb, 0);
+				if (defer) {
+					const unsigned at = qb + __popc(dmk & lt);
+					if (at < p.xq_cap)
+						p.xq[at] = make_uint4(e.z, e.x, e.y, verdict == TRI_INTERSECT ? 1u : 0u);
+					else
+						atomicOr(p.overflow, 1u);  // the fused fall-back recomputes the launch
+				}
+			}
+			// settled pose-sets: lanes working on them drop their work; remember them for prefetched candidates and
+			// queued leaf pairs
+			while (hm) {
+				const int from = __ffs(hm) - 1;
+				hm &= hm - 1;
+				const uint32_t hp = __shfl_sync(FULL, e.w, from);
+				if (pose == hp) {
+					has = false;
+					top = 0u;
+				}
+				if (lane == 0) hits[hit_w & 7u] = hp;
+				++hit_w;
+			}
+			__syncwarp();
+			continue;
+		}
+
+		// ---- node step: both children of the descended tree against the stationary node of the other ----------------
+		bool leaf0 = false, leaf1 = false;
+		uint2 lf0 = make_uint2(0u, 0u), lf1 = make_uint2(0u, 0u);
+		unsigned n_tests = 0;
+		if (has) {
+			const uint2 pr = cur;
+			has = false;
+			const bool single = (pr.y & kPlan3Single) != 0u;
+			const bool env_side = single || (pr.y & kPlan3Env) != 0u;  // the children are environment nodes
+			const uint32_t i2base = pr.y & kPlan3Idx;
+			const float4 *rs = slots + 5u * rd;
+			const float4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3];  // R (9), Tc (3), Tinv (3), S
+			const float ti0 = r3.x, ti1 = r3.y, ti2 = r3.z;
+			// Loads only: nothing below consumes a loaded value before every load of the step has been issued, so the
+			// two kinds of step (children = environment nodes / agent nodes) do not wait for memory one after the other.
+			const float4 *ep = p.env.node32 + 4ull * ((unsigned long long)nb1 + pr.x);
+			const unsigned second = single ? 0u : 4u;  // (the root pair is one test: its "second child" repeats the first)
+			Node S, C0, C1;
+			if (TOP) {
+				if (env_side) {
+					C0 = node_global(ep);
+					C1 = node_global(ep + second);
+					if (i2base < ktop) S = node_shared_swz(atop, i2base);
+					else S = node_global(nodes2 + 4ull * i2base);
+				} else {
+					S = node_global(ep);
+					if (i2base + 1u < ktop) {
+						C0 = node_shared_swz(atop, i2base);
+						C1 = node_shared_swz(atop, i2base + 1u);
+					} else {
+						C0 = node_global(nodes2 + 4ull * i2base);
+						C1 = node_global(nodes2 + 4ull * i2base + 4);
+					}
+				}
+			} else {
+				const float4 *ap = nodes2 + 4ull * i2base;
+				const float4 *op = env_side ? ap : ep, *cp = env_side ? ep : ap;
+				S = node_global(op);
+				C0 = node_global(cp);
+				C1 = node_global(cp + second);
+			}
+			// (Ry, Ty): the relative transform when the children are environment nodes, its inverse otherwise
+			StepFrame f;
+			{
+				const float y00 = r0.x, y11 = r1.x, y22 = r2.x;
+				const float y01 = env_side ? r0.y : r0.w, y10 = env_side ? r0.w : r0.y;
+				const float y02 = env_side ? r0.z : r1.z, y20 = env_side ? r1.z : r0.z;
+				const float y12 = env_side ? r1.y : r1.w, y21 = env_side ? r1.w : r1.y;
+				const float ty0 = env_side ? r2.y : ti0, ty1 = env_side ? r2.z : ti1, ty2 = env_side ? r2.w : ti2;
+				f.W[0] = y00 * S.v0.x + y01 * S.v0.y + y02 * S.v0.z;
+				f.W[1] = y00 * S.v1.x + y01 * S.v1.y + y02 * S.v1.z;
+				f.W[2] = y00 * S.v2.x + y01 * S.v2.y + y02 * S.v2.z;
+				f.W[3] = y10 * S.v0.x + y11 * S.v0.y + y12 * S.v0.z;
+				f.W[4] = y10 * S.v1.x + y11 * S.v1.y + y12 * S.v1.z;
+				f.W[5] = y10 * S.v2.x + y11 * S.v2.y + y12 * S.v2.z;
+				f.W[6] = y20 * S.v0.x + y21 * S.v0.y + y22 * S.v0.z;
+				f.W[7] = y20 * S.v1.x + y21 * S.v1.y + y22 * S.v1.z;
+				f.W[8] = y20 * S.v2.x + y21 * S.v2.y + y22 * S.v2.z;
+				const float cx = S.v0.w, cy = S.v1.w, cz = S.v2.w;
+				f.w[0] = y00 * cx + y01 * cy + y02 * cz + ty0;
+				f.w[1] = y10 * cx + y11 * cy + y12 * cz + ty1;
+				f.w[2] = y20 * cx + y21 * cy + y22 * cz + ty2;
+				f.s1 = (fabsf(ty0) + fabsf(ty1) + fabsf(ty2)) + (fabsf(cx) + fabsf(cy) + fabsf(cz));
+			}
+			const int linkS = __float_as_int(S.v3.w);
+			const float sS = S.v3.x * S.v3.x + S.v3.y * S.v3.y + S.v3.z * S.v3.z;
+			uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
+			bool ok0 = false, ok1 = false;
+			float d2_0 = 0.f, d2_1 = 0.f;
+#pragma unroll
+			for (int k = 0; k < 2; ++k) {
+				if (k == 1 && single) break;
+				const Node &C = k == 0 ? C0 : C1;
+				++n_tests;
+				float d2;
+				if (child_disjoint<false>(f, C, S.v3, d2)) continue;
+				if (k == 0) d2_0 = d2; else d2_1 = d2;
+				const int linkC = __float_as_int(C.v3.w);
+				const float sC = C.v3.x * C.v3.x + C.v3.y * C.v3.y + C.v3.z * C.v3.z;
+				// back to (environment, agent) roles
+				const int link1 = env_side ? linkC : linkS, link2 = env_side ? linkS : linkC;
+				const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
+				const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
+				const bool l1 = link1 < 0, l2 = link2 < 0;
+				if (l1 && l2) {
+					const uint2 lf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)));
+					if (k == 0) { leaf0 = true; lf0 = lf; } else { leaf1 = true; lf1 = lf; }
+					continue;
+				}
+				// firstOverSecond: descend the environment tree iff l2 || (!l1 && size1 > size2)
+				const float s1 = env_side ? sC : sS, s2 = env_side ? sS : sC;
+				const bool first = l2 || (!l1 && s1 > s2);
+				const uint2 pl = first ? make_uint2((uint32_t)link1, i2 | kPlan3Env) : make_uint2(i1, (uint32_t)link2);
+				if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
+			}
+			if (ok0 && ok1) {
+				const bool swap = p.near_first && d2_1 < d2_0;
+				cur = swap ? plan1 : plan0;
+				has = true;
+				stk[top++] = swap ? plan0 : plan1;
+			} else if (ok0) {
+				cur = plan0;
+				has = true;
+			} else if (ok1) {
+				cur = plan1;
+				has = true;
+			}
+		}
+		if (COUNT) {
+			unsigned t = n_tests;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+			ctr[CTR_BV] += t;
+		}
+		{
+			const unsigned lm0 = __ballot_sync(FULL, leaf0);
+			if (leaf0) leafq[lq + __popc(lm0 & lt)] = make_uint4(lf0.x, lf0.y, ci, pose);
+			lq += __popc(lm0);
+		}
+		const unsigned lm = __ballot_sync(FULL, leaf1);
+		if (leaf1) leafq[lq + __popc(lm & lt)] = make_uint4(lf1.x, lf1.y, ci, pose);
+		lq += __popc(lm);
+		__syncwarp();
+	}
+	if (COUNT && lane == 0) {
+#pragma unroll
+		for (int i = 0; i < CTR_N; ++i)
+			if (ctr[i]) atomicAdd(p.counters + i, ctr[i]);
+	}
+}
+
+}  // namespace
+
+unsigned np3_agent_top_max();
+
+// Agent nodes the kernel can stage beside its per-warp state (whole sibling pairs: an odd count).
+unsigned np3_agent_top_max() {
+	const unsigned budget = 227u * 1024u - kNp3TopOffset - (unsigned)kNp3Warps * kNp3WarpBytes - 256u;
+	unsigned n = budget / 64u;
+	if (n % 2u == 0u) --n;
+	return n;
+}
+
+int launch_narrowphase3(const KernelParams &p, int sm_count, bool count, void *stream) {
+	const bool top = p.agent_top != 0u;
+	const size_t smem = kNp3TopOffset + (((size_t)p.agent_top * 64u + 127u) & ~(size_t)127u) + (size_t)kNp3Warps * kNp3WarpBytes;
+	// (the opt-in is made once for the largest block the kernel can ask for: prepare_kernel caches per size, and a
+	// later opt-in to a smaller size would lower the kernel's limit again)
+	const size_t smem_max = kNp3TopOffset + (((size_t)np3_agent_top_max() * 64u + 127u) & ~(size_t)127u) + (size_t)kNp3Warps * kNp3WarpBytes;
+	if (smem > smem_max) return (int)cudaErrorInvalidValue;
+	void (*k)(KernelParams) = top ? (count ? narrowphase3_kernel<true, true> : narrowphase3_kernel<false, true>)
+	                              : (count ? narrowphase3_kernel<true, false> : narrowphase3_kernel<false, false>);
+	int per_sm = 0;
+	const cudaError_t e = prepare_kernel(reinterpret_cast<const void *>(k), kNp3Warps * 32, top ? smem_max : smem, &per_sm);
+	if (e != cudaSuccess) return (int)e;
+	if (per_sm < 1) per_sm = 1;
+	k<<<sm_count * per_sm, kNp3Warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+	return (int)cudaGetLastError();
+}
+
+}  // namespace mptcc

@@ -37,5 +37,14 @@ chk.check_poses_device(n, batches[0].data_ptr(), bits.data_ptr(), capi.POSE_RT12
 torch.cuda.synchronize()
 h = hashlib.sha256(bits.cpu().numpy().tobytes()).hexdigest()[:12]
 acc /= reps
+# one more launch with the counters on: OBB / leaf tests per pose-set (not timed)
+chk.enable_counters(True)
+chk.reset_counters()
+chk.check_poses_device(n, batches[0].data_ptr(), bits.data_ptr(), capi.POSE_RT12, 0, stream.cuda_stream)
+torch.cuda.synchronize()
+cd = chk.counters()
+h2 = hashlib.sha256(bits.cpu().numpy().tobytes()).hexdigest()[:12]
+tests = " bv/pose %.1f leaf/pose %.2f exact/pose %.3f%s" % (cd.get("n_bv_tests", 0) / n, cd.get("n_leaf_tests", 0) / n,
+                                                          cd.get("n_exact_tri", 0) / n, "" if h2 == h else " COUNT-BUILD BITS DIFFER " + h2)
 print("%-28s %s bp %.3f np %.3f exact %.3f fb %.3f total %.3f ms  bits %s" % (
-    os.path.basename(os.environ.get("MPTCC_LIB", "libmptcc.so")), " ".join(opts), acc[0], acc[1], acc[2], acc[3], acc.sum(), h))
+    os.path.basename(os.environ.get("MPTCC_LIB", "libmptcc.so")), " ".join(opts), acc[0], acc[1], acc[2], acc[3], acc.sum(), h) + tests)
