@@ -11,15 +11,16 @@
 //              [3] = (extent.xyz rounded up and inflated by 1e-6, int-bits link)
 //            link >= 0: first child (children are link, link+1); link < 0: leaf, primitive = -(link+1).
 //            node_base is odd, so every sibling pair (2k+1, 2k+2) shares one 128-byte line.
-//   nodeq  : uint4[2] per node, 32 B, same numbering as node32: the traversal node of the second-generation
-//            narrowphase (np2_kernels.cu) -- ONE 256-bit load per node, a sibling pair is 64 bytes.
-//              [0].x = axis0.x | axis0.y << 16   [0].y = axis0.z | axis1.x << 16   [0].z = axis1.y | axis1.z << 16
-//                      (binary16, round to nearest; axis2 = axis0 x axis1 is formed in the kernel)
-//              [0].w = extent.x | extent.y << 16  [1].x = extent.z | link[15:0] << 16        (binary16, rounded UP)
-//              [1].y = centre.x (fp32; its low mantissa byte holds link[23:16])   [1].z, [1].w = centre.y, centre.z
-//            link (24 bit): bit 23 = leaf, low 23 bits = first child / primitive.  The extents are widened by the
-//            centre displacement and by (1 + 1e-6); the axis quantisation (<= 2^-12 per component) is covered by an
-//            extra margin in the kernel's SAT.
+//   nodeq  : uint4[2] per node, 32 B, same numbering as node32: the optional traversal node of the np2/np3 kernels
+//            (qnode = 1) -- ONE 256-bit load per node, a sibling pair is 64 bytes.
+//              [0].x, .y, .z = centre (fp32)      [0].w = extent.x | extent.y << 16      [1].x = extent.z | link[15:0] << 16
+//                      (extents binary16, rounded UP after the widening below)
+//              [1].y, .z, .w = 96 bits: the orientation as a unit quaternion (w, x, y, z), four 22-bit fixed-point
+//                      components Q (value Q * 2^-21 - 1) in bits [0,22) [22,44) [44,66) [66,88), then link[23:16]
+//            The rows of the quaternion's rotation matrix are the box axes (a left-handed triple is stored with axis 2
+//            negated: the same box).  link (24 bit): bit 23 = leaf, low 23 bits = first child / primitive.  A decoded
+//            axis component is within 4e-6 of the true one; the extents are widened by sqrt(3) * 4e-6 * (sum of
+//            extents) and (1 + 1e-6) so that the decoded box contains FCL's box.
 //   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.
 //   node64 : double[16] per node: FCL's OBB verbatim -- axis (9), To (3), extent (3), size =
 //            extent.sqrLength() (1).  Only read when a positive leaf pair replays FCL's path.

@@ -95,6 +95,10 @@ inline void quat_rotate(const double q[4], const double v[3], double o[3]) {
 	o[2] = r[3];
 }
 
+// Quantised nodes (device_layout.hpp, nodeq): each component of a decoded axis is within kQAxisDelta of the true one
+// (kQAxisCheck is what the host verifies in exact arithmetic; the rest is the kernel's fp32 evaluation).
+constexpr double kQAxisDelta = 4e-6, kQAxisCheck = 2e-6;
+
 // Host image of one ModelPack.
 struct HostPack {
 	std::vector<float4> node32;
@@ -106,6 +110,7 @@ struct HostPack {
 	std::vector<float> mu_chain;
 	std::vector<DevModel> models;
 	uint32_t max_depth = 0;
+	bool q_ok = true;  // every node could be written as a quantised node (nodeq)
 
 	void clear() { *this = HostPack(); }
 
@@ -191,28 +196,74 @@ struct HostPack {
 			std::memcpy(&last.w, &link, 4);
 			node32.push_back(last);
 			{
-				// quantised node (32 bytes, layout: device_layout.hpp).  The centre's x carries link bits 16..23 in its
-				// low mantissa byte; the box is widened by that displacement so that it still contains FCL's box.
+				// quantised node (32 bytes, layout: device_layout.hpp): centre fp32, extents binary16 (rounded up), the
+				// orientation as a unit quaternion with four 22-bit fixed-point components, 24-bit link.
+				// The rows of the rotation matrix of the quaternion are the box axes; an OBB does not change when an axis
+				// is negated, so a left-handed axis triple is stored with axis 2 flipped.
+				double M[9];
+				for (int k = 0; k < 9; ++k) M[k] = A[k];
+				const double det = M[0] * (M[4] * M[8] - M[5] * M[7]) - M[1] * (M[3] * M[8] - M[5] * M[6]) + M[2] * (M[3] * M[7] - M[4] * M[6]);
+				if (det < 0.0)
+					for (int k = 6; k < 9; ++k) M[k] = -M[k];
+				double q[4];  // w x y z
+				{
+					const double tr = M[0] + M[4] + M[8];
+					if (tr > 0.0) {
+						const double r = std::sqrt(tr + 1.0), f = 0.5 / r;
+						q[0] = 0.5 * r;
+						q[1] = (M[7] - M[5]) * f;
+						q[2] = (M[2] - M[6]) * f;
+						q[3] = (M[3] - M[1]) * f;
+					} else {
+						int i = 0;
+						if (M[4] > M[0]) i = 1;
+						if (M[8] > M[4 * i]) i = 2;
+						const int j = (i + 1) % 3, k2 = (i + 2) % 3;
+						const double r = std::sqrt(M[4 * i] - M[4 * j] - M[4 * k2] + 1.0), f = 0.5 / r;
+						q[1 + i] = 0.5 * r;
+						q[0] = (M[3 * k2 + j] - M[3 * j + k2]) * f;
+						q[1 + j] = (M[3 * i + j] + M[3 * j + i]) * f;
+						q[1 + k2] = (M[3 * i + k2] + M[3 * k2 + i]) * f;
+					}
+					const double nq = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+					for (int k = 0; k < 4; ++k) q[k] = nq > 0.0 && std::isfinite(nq) ? q[k] / nq : (k == 0 ? 1.0 : 0.0);
+				}
+				uint32_t Q[4];
+				double qd[4];  // the components the kernel decodes: Q * 2^-21 - 1
+				for (int k = 0; k < 4; ++k) {
+					const double v = std::floor((q[k] + 1.0) * 2097152.0 + 0.5);
+					Q[k] = (uint32_t)std::min(4194303.0, std::max(0.0, v));
+					qd[k] = (double)Q[k] / 2097152.0 - 1.0;
+				}
+				{
+					// the axes as the kernel reconstructs them (exact arithmetic here; its fp32 evaluation is within 1e-6 of
+					// this) must be within kQAxisCheck of the true ones, or the pack cannot use quantised nodes
+					const double w = qd[0], x = qd[1], y = qd[2], z = qd[3];
+					const double Rq[9] = {1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y),
+					                      2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x),
+					                      2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)};
+					for (int k = 0; k < 9; ++k)
+						if (!(std::fabs(Rq[k] - M[k]) <= kQAxisCheck)) q_ok = false;
+				}
+				const double esum = E[0] + E[1] + E[2];
+				uint16_t he[3];
+				for (int k = 0; k < 3; ++k) {
+					// widened so that the box spanned by the decoded axes contains FCL's box
+					const double e = (E[k] + 1.7320508075688772 * kQAxisDelta * esum) * (1.0 + 1e-6);
+					if (!(e <= 65000.0)) q_ok = false;
+					he[k] = float_to_half(round_up_f32(e), true);
+				}
 				const uint32_t raw = link >= 0 ? (uint32_t)link : (0x800000u | (uint32_t)(-(link + 1)));
-				float cq[3] = {(float)(C[0] - m.ctr[0]), (float)(C[1] - m.ctr[1]), (float)(C[2] - m.ctr[2])};
-				uint32_t cxb;
-				std::memcpy(&cxb, &cq[0], 4);
-				cxb = (cxb & 0xffffff00u) | ((raw >> 16) & 0xffu);
-				std::memcpy(&cq[0], &cxb, 4);
-				const double dc = std::fabs((double)cq[0] - (C[0] - m.ctr[0])) + std::fabs((double)cq[1] - (C[1] - m.ctr[1])) +
-				                  std::fabs((double)cq[2] - (C[2] - m.ctr[2]));
-				uint16_t hx[6], he[3];
-				for (int k = 0; k < 6; ++k) hx[k] = float_to_half((float)A[k], false);  // axis0, axis1; axis2 = axis0 x axis1
-				for (int k = 0; k < 3; ++k) he[k] = float_to_half(round_up_f32((E[k] + dc) * (1.0 + 1e-6)), true);
+				const float cq[3] = {(float)(C[0] - m.ctr[0]), (float)(C[1] - m.ctr[1]), (float)(C[2] - m.ctr[2])};
 				uint4 q0, q1;
-				q0.x = hx[0] | ((uint32_t)hx[1] << 16);
-				q0.y = hx[2] | ((uint32_t)hx[3] << 16);
-				q0.z = hx[4] | ((uint32_t)hx[5] << 16);
+				std::memcpy(&q0.x, &cq[0], 4);
+				std::memcpy(&q0.y, &cq[1], 4);
+				std::memcpy(&q0.z, &cq[2], 4);
 				q0.w = he[0] | ((uint32_t)he[1] << 16);
 				q1.x = he[2] | ((raw & 0xffffu) << 16);
-				std::memcpy(&q1.y, &cq[0], 4);
-				std::memcpy(&q1.z, &cq[1], 4);
-				std::memcpy(&q1.w, &cq[2], 4);
+				q1.y = Q[0] | (Q[1] << 22);
+				q1.z = (Q[1] >> 10) | (Q[2] << 12);
+				q1.w = (Q[2] >> 20) | (Q[3] << 2) | (((raw >> 16) & 0xffu) << 24);
 				nodeq.push_back(q0);
 				nodeq.push_back(q1);
 			}
@@ -518,7 +569,7 @@ struct mptcc_ctx {
 	long opt_np2 = 0;                // 1 = second-generation narrowphase (np2_kernels.cu): same speed on C5, see DESIGN.md section 5
 	long opt_expand4 = 0;            // np2: 1 = expand both trees per step (four tests); measured 37 % slower on C5
 	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
-	long opt_qnode = 0;              // np2: traverse the 32-byte quantised nodes (0 = the 64-byte fp32 nodes)
+	long opt_qnode = 1;              // np2/np3 traverse the 32-byte quantised nodes (one 256-bit load per node); 0 = the 64-byte fp32 nodes
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
 	long opt_np3 = 1;                // third-generation narrowphase (np3_kernels.cu, streaming lanes): the default; 0 = the round-1 kernel
 	                                 // (split_kernels.cu), or np2_kernels.cu with np2 = 1
@@ -745,8 +796,8 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		{
 			// top of the agent tree staged in shared memory: whole sibling pairs only (odd count)
 			const DevModel &am = ctx->agent_h.models[ctx->link_model_h[0]];
-			uint32_t top = std::min<uint32_t>(2u * am.num_tris - 1u, (ctx->opt_qnode && ctx->env_q_ok) ? kAgentTopMaxQ : kAgentTopMax);
-			kp.qnode = (ctx->opt_qnode && ctx->env_q_ok) ? 1u : 0u;
+			uint32_t top = std::min<uint32_t>(2u * am.num_tris - 1u, (ctx->opt_qnode && ctx->env_q_ok && ctx->env_h.q_ok && ctx->agent_h.q_ok) ? kAgentTopMaxQ : kAgentTopMax);
+			kp.qnode = (ctx->opt_qnode && ctx->env_q_ok && ctx->env_h.q_ok && ctx->agent_h.q_ok) ? 1u : 0u;
 			// (both trees expanded per step: up to three pending pairs per level, 128 stack entries per lane)
 			kp.expand4 = (ctx->opt_expand4 && 3u * std::max(ctx->env_h.max_depth, ctx->agent_h.max_depth) + 4u <= 2u * kLaneStackCap) ? 1u : 0u;
 			if (ctx->opt_agent_top >= 0) top = std::min<uint32_t>(top, (uint32_t)ctx->opt_agent_top);
@@ -754,7 +805,6 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 				// np3 stages agent nodes only on request (agent_top = n): measured on C5, the shared memory they take away
 				// from L1 costs more than the LDS gathers save
 				top = ctx->opt_agent_top > 0 ? std::min<uint32_t>(std::min<uint32_t>(2u * am.num_tris - 1u, np3_agent_top_max()), (uint32_t)ctx->opt_agent_top) : 0u;
-				kp.qnode = 0u;
 				kp.expand4 = 0u;
 			}
 			if (top && top % 2 == 0) --top;

@@ -44,7 +44,11 @@ constexpr int kNp3LeafCap = kNp3LeafAt + 64;   // a node step appends at most 64
 constexpr unsigned kNp3SlotBytes = 80u;        // 4 float4 record + (node_base, tri_base, pose-set, -)
 constexpr unsigned kNp3Depth = 2u;             // candidates prefetched per lane, consumed in order
 constexpr unsigned kNp3Ring = kNp3Depth + 1u;  // slots per lane: the current candidate + the prefetched ones
-constexpr unsigned kNp3WarpBytes = 32u * kNp3Ring * kNp3SlotBytes + (unsigned)kNp3LeafCap * 16u + 32u + 32u;
+#ifndef MPTCC_NP3_STACK_S
+#define MPTCC_NP3_STACK_S 12
+#endif
+constexpr unsigned kNp3StackS = MPTCC_NP3_STACK_S;  // per-lane stack entries kept in shared memory (deeper ones: local memory)
+constexpr unsigned kNp3WarpBytes = 32u * kNp3Ring * kNp3SlotBytes + (unsigned)kNp3LeafCap * 16u + 32u + 32u + kNp3StackS * 256u;
 constexpr unsigned kNp3TopOffset = 128u;       // the mbarrier lives in front of the staged tree
 constexpr unsigned kPlan3Env = 1u << 31, kPlan3Single = 1u << 30, kPlan3Idx = (1u << 30) - 1u;
 
@@ -80,7 +84,7 @@ __device__ __forceinline__ bool pose_settled(const uint32_t *hits, uint32_t pose
 #define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, 1)
 #endif
 
-template <bool COUNT, bool TOP>
+template <bool COUNT, bool TOP, bool Q>
 __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
@@ -113,10 +117,34 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 	}
 
 	unsigned char *wbase = smem_raw + kNp3TopOffset + ((top_bytes + 127u) & ~127u) + (size_t)warp * kNp3WarpBytes;
-	float4 *slots = reinterpret_cast<float4 *>(wbase) + 5u * kNp3Ring * (unsigned)lane;  // this lane's ring: [kNp3Ring][5]
+	// record slots of the warp, [kNp3Ring][32 lanes][5 float4]: slot r of lane l starts 5 (32 r + l) float4 in; 80-byte
+	// stride over the lanes and a multiple of 128 bytes between ring positions, so lanes reading part k of their
+	// current slot hit eight different 16-byte bank groups per quarter-warp whatever their ring positions are
+	float4 *wslots = reinterpret_cast<float4 *>(wbase);
+#define NP3_SLOT(l, r) (wslots + 5u * (32u * (r) + (unsigned)(l)))
 	uint4 *leafq = reinterpret_cast<uint4 *>(wbase + 32u * kNp3Ring * kNp3SlotBytes);  // [kNp3LeafCap] env prim, agent prim, list index, pose-set
 	uint32_t *hits = reinterpret_cast<uint32_t *>(wbase + 32u * kNp3Ring * kNp3SlotBytes + (unsigned)kNp3LeafCap * 16u);  // [8]
 	unsigned char *donor = reinterpret_cast<unsigned char *>(hits + 8);       // [32]
+	// The pending plans of a lane: the node gathers keep evicting a local-memory stack from L1 (87 % of its loads
+	// missed), so the entries every descent uses live in shared memory, word-interleaved over the lanes.
+	uint32_t *sstk = reinterpret_cast<uint32_t *>(donor + 32) + lane;         // [kNp3StackS][2][32]
+#define NP3_PUSH(v)                                                  \
+	{                                                                \
+		const uint2 v_ = (v);                                        \
+		if (top < kNp3StackS) {                                      \
+			sstk[64u * top] = v_.x;                                  \
+			sstk[64u * top + 32u] = v_.y;                            \
+		} else {                                                     \
+			stk[top - kNp3StackS] = v_;                              \
+		}                                                            \
+		++top;                                                       \
+	}
+#define NP3_POP(dst)                                                 \
+	{                                                                \
+		--top;                                                       \
+		if (top < kNp3StackS) dst = make_uint2(sstk[64u * top], sstk[64u * top + 32u]); \
+		else dst = stk[top - kNp3StackS];                            \
+	}
 
 	const bool skip = *p.overflow != 0u;  // overflowed list / non-rigid pose: the launch belongs to the fused fall-back
 	if (top_bytes != 0u) {
@@ -153,7 +181,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 
 	while (true) {
 		if (!has && top != 0u) {
-			cur = stk[--top];
+			NP3_POP(cur)
 			has = true;
 		}
 		unsigned im = __ballot_sync(FULL, !has);
@@ -176,8 +204,8 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 						const bool given = ((give >> lane) & 1u) && grank < __popc(want);
 						if (taker) {
 							// copy the donor's oldest prefetched record into my next slot, as if I had prefetched it
-							const float4 *from = reinterpret_cast<const float4 *>(wbase) + 5u * (kNp3Ring * (unsigned)src + (srd + 1u) % kNp3Ring);
-							float4 *to = slots + 5u * ((rd + 1u) % kNp3Ring);
+							const float4 *from = NP3_SLOT(src, (srd + 1u) % kNp3Ring);
+							float4 *to = NP3_SLOT(lane, (rd + 1u) % kNp3Ring);
 #pragma unroll
 							for (int k = 0; k < 5; ++k) to[k] = from[k];
 							pf = 1u;
@@ -187,8 +215,8 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 							// the donor's remaining prefetched record (if any) moves up: rotate by making the given slot the
 							// "current" one is not possible while the lane is busy, so swap the two prefetched slots instead
 							if (pf == 2u) {
-								float4 *a = slots + 5u * ((rd + 1u) % kNp3Ring);
-								const float4 *bsl = slots + 5u * ((rd + 2u) % kNp3Ring);
+								float4 *a = NP3_SLOT(lane, (rd + 1u) % kNp3Ring);
+								const float4 *bsl = NP3_SLOT(lane, (rd + 2u) % kNp3Ring);
 #pragma unroll
 								for (int k = 0; k < 5; ++k) a[k] = bsl[k];
 							}
@@ -200,7 +228,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				if (!has && pf > young) {
 					rd = (rd + 1u) % kNp3Ring;
 					--pf;
-					const float4 s4 = slots[5u * rd + 4u];
+					const float4 s4 = NP3_SLOT(lane, rd)[4];
 					ci = __float_as_uint(s4.w);
 					pose = __float_as_uint(s4.z);
 					nb1 = __float_as_uint(s4.x);
@@ -232,7 +260,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				const unsigned rank = (unsigned)__popc(need & lt);
 				if (((need >> lane) & 1u) && rank < avail) {
 					const unsigned idx = qhead + rank;
-					float4 *s = slots + 5u * ((rd + pf + 1u) % kNp3Ring);
+					float4 *s = NP3_SLOT(lane, (rd + pf + 1u) % kNp3Ring);
 					const float4 *g = p.cand_rec + 4ull * idx;
 					cp_async16(s, g);
 					cp_async16(s + 1, g + 1);
@@ -265,14 +293,14 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					const bool thief = ((tm >> lane) & 1u) && r < n_donors;
 					const int from = thief ? (int)donor[r] : lane;
 					uint2 e = make_uint2(0u, 0u);
-					if (is_donor && drank < n_thieves) e = stk[--top];
+					if (is_donor && drank < n_thieves) NP3_POP(e)
 					e.x = __shfl_sync(FULL, e.x, from);
 					e.y = __shfl_sync(FULL, e.y, from);
 					const unsigned frd = __shfl_sync(FULL, rd, from);
 					const unsigned fnb1 = __shfl_sync(FULL, nb1, from), fci = __shfl_sync(FULL, ci, from), fpose = __shfl_sync(FULL, pose, from);
 					if (thief) {
-						const float4 *src = reinterpret_cast<const float4 *>(wbase) + 5u * (kNp3Ring * (unsigned)from + frd);
-						float4 *to = slots + 5u * rd;
+						const float4 *src = NP3_SLOT(from, frd);
+						float4 *to = NP3_SLOT(lane, rd);
 #pragma unroll
 						for (int k = 0; k < 4; ++k) to[k] = src[k];
 						nb1 = fnb1;
@@ -417,15 +445,17 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			const bool single = (pr.y & kPlan3Single) != 0u;
 			const bool env_side = single || (pr.y & kPlan3Env) != 0u;  // the children are environment nodes
 			const uint32_t i2base = pr.y & kPlan3Idx;
-			const float4 *rs = slots + 5u * rd;
+			const float4 *rs = NP3_SLOT(lane, rd);
 			const float4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3];  // R (9), Tc (3), Tinv (3), S
 			const float ti0 = r3.x, ti1 = r3.y, ti2 = r3.z;
 			// Loads only: nothing below consumes a loaded value before every load of the step has been issued, so the
 			// two kinds of step (children = environment nodes / agent nodes) do not wait for memory one after the other.
 			const float4 *ep = p.env.node32 + 4ull * ((unsigned long long)nb1 + pr.x);
 			const unsigned second = single ? 0u : 4u;  // (the root pair is one test: its "second child" repeats the first)
-			Node S, C0, C1;
+			Node S;
+			Node2 C2;  // both children, side by side (np_sat.cuh)
 			if (TOP) {
+				Node C0, C1;
 				if (env_side) {
 					C0 = node_global(ep);
 					C1 = node_global(ep + second);
@@ -441,12 +471,24 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 						C1 = node_global(nodes2 + 4ull * i2base + 4);
 					}
 				}
+				C2 = pack_nodes(C0, C1);
+			} else if (Q) {
+				// 32-byte quantised nodes (device_layout.hpp, nodeq): one 256-bit load per node
+				const uint4 *eq = p.env.nodeq + 2ull * ((unsigned long long)nb1 + pr.x);
+				const uint4 *aq = p.agent.nodeq + 2ull * ((unsigned long long)m2.node_base + i2base);
+				const uint4 *op = env_side ? aq : eq, *cp = env_side ? eq : aq;
+				uint4 s0, s1, a0, a1, b0, b1;
+				ldg256u(op, s0, s1);
+				ldg256u(cp, a0, a1);
+				ldg256u(cp + (second >> 1), b0, b1);
+				S = node_decode(s0, s1);
+				C2 = node2_decode(a0, a1, b0, b1);
 			} else {
 				const float4 *ap = nodes2 + 4ull * i2base;
 				const float4 *op = env_side ? ap : ep, *cp = env_side ? ep : ap;
 				S = node_global(op);
-				C0 = node_global(cp);
-				C1 = node_global(cp + second);
+				const Node C0 = node_global(cp), C1 = node_global(cp + second);
+				C2 = pack_nodes(C0, C1);
 			}
 			// (Ry, Ty): the relative transform when the children are environment nodes, its inverse otherwise
 			StepFrame f;
@@ -476,16 +518,17 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
 			bool ok0 = false, ok1 = false;
 			float d2_0 = 0.f, d2_1 = 0.f;
+			float2 d2p;
+			const unsigned djm = pair_disjoint<Q>(f, C2, S.v3, d2p);
+			const float2 sC2 = MPTCC_FMA2(C2.e[2], C2.e[2], MPTCC_FMA2(C2.e[1], C2.e[1], MPTCC_MUL2(C2.e[0], C2.e[0])));
+			n_tests = single ? 1u : 2u;
 #pragma unroll
 			for (int k = 0; k < 2; ++k) {
 				if (k == 1 && single) break;
-				const Node &C = k == 0 ? C0 : C1;
-				++n_tests;
-				float d2;
-				if (child_disjoint<false>(f, C, S.v3, d2)) continue;
-				if (k == 0) d2_0 = d2; else d2_1 = d2;
-				const int linkC = __float_as_int(C.v3.w);
-				const float sC = C.v3.x * C.v3.x + C.v3.y * C.v3.y + C.v3.z * C.v3.z;
+				if ((djm >> k) & 1u) continue;
+				if (k == 0) d2_0 = d2p.x; else d2_1 = d2p.y;
+				const int linkC = k == 0 ? C2.link0 : C2.link1;
+				const float sC = k == 0 ? sC2.x : sC2.y;
 				// back to (environment, agent) roles
 				const int link1 = env_side ? linkC : linkS, link2 = env_side ? linkS : linkC;
 				const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
@@ -506,7 +549,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				const bool swap = p.near_first && d2_1 < d2_0;
 				cur = swap ? plan1 : plan0;
 				has = true;
-				stk[top++] = swap ? plan0 : plan1;
+				NP3_PUSH(swap ? plan0 : plan1)
 			} else if (ok0) {
 				cur = plan0;
 				has = true;
@@ -551,14 +594,15 @@ unsigned np3_agent_top_max() {
 }
 
 int launch_narrowphase3(const KernelParams &p, int sm_count, bool count, void *stream) {
-	const bool top = p.agent_top != 0u;
-	const size_t smem = kNp3TopOffset + (((size_t)p.agent_top * 64u + 127u) & ~(size_t)127u) + (size_t)kNp3Warps * kNp3WarpBytes;
+	const bool top = p.agent_top != 0u && !p.qnode;
+	const size_t smem = kNp3TopOffset + (((size_t)(top ? p.agent_top : 0u) * 64u + 127u) & ~(size_t)127u) + (size_t)kNp3Warps * kNp3WarpBytes;
 	// (the opt-in is made once for the largest block the kernel can ask for: prepare_kernel caches per size, and a
 	// later opt-in to a smaller size would lower the kernel's limit again)
 	const size_t smem_max = kNp3TopOffset + (((size_t)np3_agent_top_max() * 64u + 127u) & ~(size_t)127u) + (size_t)kNp3Warps * kNp3WarpBytes;
 	if (smem > smem_max) return (int)cudaErrorInvalidValue;
-	void (*k)(KernelParams) = top ? (count ? narrowphase3_kernel<true, true> : narrowphase3_kernel<false, true>)
-	                              : (count ? narrowphase3_kernel<true, false> : narrowphase3_kernel<false, false>);
+	void (*k)(KernelParams) = p.qnode ? (count ? narrowphase3_kernel<true, false, true> : narrowphase3_kernel<false, false, true>)
+	                          : top   ? (count ? narrowphase3_kernel<true, true, false> : narrowphase3_kernel<false, true, false>)
+	                                  : (count ? narrowphase3_kernel<true, false, false> : narrowphase3_kernel<false, false, false>);
 	int per_sm = 0;
 	const cudaError_t e = prepare_kernel(reinterpret_cast<const void *>(k), kNp3Warps * 32, top ? smem_max : smem, &per_sm);
 	if (e != cudaSuccess) return (int)e;

@@ -23,18 +23,25 @@ __device__ __forceinline__ Node node_global(const float4 *p) {
 __device__ __forceinline__ Node node_shared(const float4 *p) { return Node{p[0], p[1], p[2], p[3]}; }
 
 // Quantised node (device_layout.hpp, nodeq) -> Node.  v3.w carries the link as the int the rest of the code expects.
+// A 22-bit fixed-point component Q stands for Q * 2^-21 - 1: OR-ing Q << 1 into the mantissa of 1.0f gives
+// 1 + Q * 2^-22 exactly, and 2 f - 3 is exact too (no integer-to-float conversion).
+__device__ __forceinline__ float qcomp(uint32_t Q) { return fmaf(__uint_as_float(0x3f800000u | (Q << 1)), 2.0f, -3.0f); }
 __device__ __forceinline__ Node node_decode(const uint4 q0, const uint4 q1) {
-	const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&q0.x));  // axis0.x, axis0.y
-	const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&q0.y));  // axis0.z, axis1.x
-	const float2 c = __half22float2(*reinterpret_cast<const __half2 *>(&q0.z));  // axis1.y, axis1.z
+	constexpr uint32_t M22 = 0x3fffffu;
+	const float w = qcomp(q1.y & M22), x = qcomp(__funnelshift_r(q1.y, q1.z, 22) & M22);
+	const float y = qcomp(__funnelshift_r(q1.z, q1.w, 12) & M22), z = qcomp((q1.w >> 2) & M22);
 	const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&q0.w));  // extent.x, extent.y
 	const float ez = __half2float(__ushort_as_half((unsigned short)(q1.x & 0xffffu)));
-	const uint32_t raw = (q1.x >> 16) | ((q1.y & 0xffu) << 16);
+	const uint32_t raw = (q1.x >> 16) | ((q1.w >> 24) << 16);
 	const int link = (raw & 0x800000u) ? -(int)(raw & 0x7fffffu) - 1 : (int)raw;
+	const float tx = x + x, ty = y + y, tz = z + z;
+	const float twx = tx * w, twy = ty * w, twz = tz * w;
+	const float txx = tx * x, txy = ty * x, txz = tz * x;
+	const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
 	Node n;
-	n.v0 = make_float4(a.x, a.y, b.x, __uint_as_float(q1.y));
-	n.v1 = make_float4(b.y, c.x, c.y, __uint_as_float(q1.z));
-	n.v2 = make_float4(a.y * c.y - b.x * c.x, b.x * b.y - a.x * c.y, a.x * c.x - a.y * b.y, __uint_as_float(q1.w));
+	n.v0 = make_float4(1.0f - (tyy + tzz), txy - twz, txz + twy, __uint_as_float(q0.x));
+	n.v1 = make_float4(txy + twz, 1.0f - (txx + tzz), tyz - twx, __uint_as_float(q0.y));
+	n.v2 = make_float4(txz - twy, tyz + twx, 1.0f - (txx + tyy), __uint_as_float(q0.z));
 	n.v3 = make_float4(e.x, e.y, ez, __int_as_float(link));
 	return n;
 }
@@ -83,10 +90,12 @@ struct StepFrame {
 	float s1;  // |Ty|_1 + |cS|_1
 };
 
+// Q: the decoded axes of a quantised node are within 4e-6 per component of the true ones; the stored extents are
+// widened so that the box they span contains FCL's box, and this term covers what the SAT's algebra loses because the
+// decoded frames are orthonormal only to ~1e-5.
+constexpr float kQFrameMargin = 6.4e-5f;
+
 // Child half: true => child box C and stationary box S are certainly disjoint.  d2 = squared centre distance.
-// Q: the nodes come from the quantised array.  Their axes are off by <= 2^-12 per component (the third, a cross
-// product, by twice that), so every projection radius the SAT forms from them can be short by a few 1e-4 of the
-// box's size; 8e-3 (esum_C + esum_S) added to the margin covers that with a factor > 2.
 template <bool Q>
 __device__ __forceinline__ bool child_disjoint(const StepFrame &f, const Node &C, const float4 es, float &d2) {
 	float G[9];
@@ -103,8 +112,140 @@ __device__ __forceinline__ bool child_disjoint(const StepFrame &f, const Node &C
 	const float t2 = C.v2.x * dx + C.v2.y * dy + C.v2.z * dz;
 	// margin = 192 u (|Ty|_1 + |cS|_1 + |cC|_1)
 	float mg = (192.0f * kU) * (f.s1 + (fabsf(C.v0.w) + fabsf(C.v1.w) + fabsf(C.v2.w)));
-	if (Q) mg += 8e-3f * ((C.v3.x + C.v3.y + C.v3.z) + (es.x + es.y + es.z));
+	if (Q) mg += kQFrameMargin * ((C.v3.x + C.v3.y + C.v3.z) + (es.x + es.y + es.z));
 	return sat15(G, t0, t1, t2, C.v3, es, mg);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Two-wide evaluation: a traversal step tests the two children of one node against the same stationary box, so the
+// two SATs are the same arithmetic on two data sets.  sm_100 has two-wide fp32 instructions (FFMA2 / FMUL2 / FADD2 on
+// 64-bit register pairs, scalar operands broadcast for free); child 0 lives in the .x halves and child 1 in the .y
+// halves.  Same formulas and margins as child_disjoint / sat15 above.
+// ------------------------------------------------------------------------------------------------------------------
+struct Node2 {
+	float2 a[9];  // a[3 i + k] = component k of axis i
+	float2 c[3];  // centre
+	float2 e[3];  // extents
+	int link0, link1;
+};
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 abs2(float2 v) { return make_float2(fabsf(v.x), fabsf(v.y)); }
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+#define MPTCC_MUL2 __fmul2_rn
+#define MPTCC_FMA2 __ffma2_rn
+#define MPTCC_ADD2 __fadd2_rn
+
+__device__ __forceinline__ Node2 pack_nodes(const Node &A, const Node &B) {
+	Node2 n;
+	n.a[0] = make_float2(A.v0.x, B.v0.x); n.a[1] = make_float2(A.v0.y, B.v0.y); n.a[2] = make_float2(A.v0.z, B.v0.z);
+	n.a[3] = make_float2(A.v1.x, B.v1.x); n.a[4] = make_float2(A.v1.y, B.v1.y); n.a[5] = make_float2(A.v1.z, B.v1.z);
+	n.a[6] = make_float2(A.v2.x, B.v2.x); n.a[7] = make_float2(A.v2.y, B.v2.y); n.a[8] = make_float2(A.v2.z, B.v2.z);
+	n.c[0] = make_float2(A.v0.w, B.v0.w); n.c[1] = make_float2(A.v1.w, B.v1.w); n.c[2] = make_float2(A.v2.w, B.v2.w);
+	n.e[0] = make_float2(A.v3.x, B.v3.x); n.e[1] = make_float2(A.v3.y, B.v3.y); n.e[2] = make_float2(A.v3.z, B.v3.z);
+	n.link0 = __float_as_int(A.v3.w);
+	n.link1 = __float_as_int(B.v3.w);
+	return n;
+}
+
+// Two quantised nodes (device_layout.hpp, nodeq) decoded side by side.
+__device__ __forceinline__ int qlink(const uint4 q1) {
+	const uint32_t raw = (q1.x >> 16) | ((q1.w >> 24) << 16);
+	return (raw & 0x800000u) ? -(int)(raw & 0x7fffffu) - 1 : (int)raw;
+}
+__device__ __forceinline__ float2 qcomp2(uint32_t Qa, uint32_t Qb) {
+	return MPTCC_FMA2(make_float2(__uint_as_float(0x3f800000u | (Qa << 1)), __uint_as_float(0x3f800000u | (Qb << 1))), bc2(2.0f), bc2(-3.0f));
+}
+__device__ __forceinline__ Node2 node2_decode(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
+	constexpr uint32_t M22 = 0x3fffffu;
+	const float2 w = qcomp2(a1.y & M22, b1.y & M22);
+	const float2 x = qcomp2(__funnelshift_r(a1.y, a1.z, 22) & M22, __funnelshift_r(b1.y, b1.z, 22) & M22);
+	const float2 y = qcomp2(__funnelshift_r(a1.z, a1.w, 12) & M22, __funnelshift_r(b1.z, b1.w, 12) & M22);
+	const float2 z = qcomp2((a1.w >> 2) & M22, (b1.w >> 2) & M22);
+	const float2 tx = MPTCC_ADD2(x, x), ty = MPTCC_ADD2(y, y), tz = MPTCC_ADD2(z, z);
+	const float2 twx = MPTCC_MUL2(tx, w), twy = MPTCC_MUL2(ty, w), twz = MPTCC_MUL2(tz, w);
+	const float2 txx = MPTCC_MUL2(tx, x), tyy = MPTCC_MUL2(ty, y), tzz = MPTCC_MUL2(tz, z);
+	const float2 one = bc2(1.0f), m1 = bc2(-1.0f);
+	Node2 n;
+	n.a[0] = MPTCC_FMA2(MPTCC_ADD2(tyy, tzz), m1, one);
+	n.a[1] = MPTCC_FMA2(ty, x, neg2(twz));
+	n.a[2] = MPTCC_FMA2(tz, x, twy);
+	n.a[3] = MPTCC_FMA2(ty, x, twz);
+	n.a[4] = MPTCC_FMA2(MPTCC_ADD2(txx, tzz), m1, one);
+	n.a[5] = MPTCC_FMA2(tz, y, neg2(twx));
+	n.a[6] = MPTCC_FMA2(tz, x, neg2(twy));
+	n.a[7] = MPTCC_FMA2(tz, y, twx);
+	n.a[8] = MPTCC_FMA2(MPTCC_ADD2(txx, tyy), m1, one);
+	n.c[0] = make_float2(__uint_as_float(a0.x), __uint_as_float(b0.x));
+	n.c[1] = make_float2(__uint_as_float(a0.y), __uint_as_float(b0.y));
+	n.c[2] = make_float2(__uint_as_float(a0.z), __uint_as_float(b0.z));
+	const float2 ea = __half22float2(*reinterpret_cast<const __half2 *>(&a0.w)), eb = __half22float2(*reinterpret_cast<const __half2 *>(&b0.w));
+	n.e[0] = make_float2(ea.x, eb.x);
+	n.e[1] = make_float2(ea.y, eb.y);
+	n.e[2] = make_float2(__half2float(__ushort_as_half((unsigned short)(a1.x & 0xffffu))), __half2float(__ushort_as_half((unsigned short)(b1.x & 0xffffu))));
+	n.link0 = qlink(a1);
+	n.link1 = qlink(b1);
+	return n;
+}
+__device__ __forceinline__ void ldg256u(const uint4 *p, uint4 &q0, uint4 &q1) {
+	asm("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+	    : "=r"(q0.x), "=r"(q0.y), "=r"(q0.z), "=r"(q0.w), "=r"(q1.x), "=r"(q1.y), "=r"(q1.z), "=r"(q1.w)
+	    : "l"(p));
+}
+
+// Both children against the stationary box: bit 0 / bit 1 set = child 0 / child 1 certainly disjoint from S.
+template <bool Q>
+__device__ __forceinline__ unsigned pair_disjoint(const StepFrame &f, const Node2 &C, const float4 es, float2 &d2) {
+	float2 G[9];
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+#pragma unroll
+		for (int j = 0; j < 3; ++j)
+			G[3 * i + j] = MPTCC_FMA2(C.a[3 * i + 2], bc2(f.W[6 + j]), MPTCC_FMA2(C.a[3 * i + 1], bc2(f.W[3 + j]), MPTCC_MUL2(C.a[3 * i], bc2(f.W[j]))));
+	const float2 m1 = bc2(-1.0f);
+	const float2 dx = MPTCC_FMA2(C.c[0], m1, bc2(f.w[0])), dy = MPTCC_FMA2(C.c[1], m1, bc2(f.w[1])), dz = MPTCC_FMA2(C.c[2], m1, bc2(f.w[2]));
+	d2 = MPTCC_FMA2(dz, dz, MPTCC_FMA2(dy, dy, MPTCC_MUL2(dx, dx)));
+	float2 t[3], nt[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		t[i] = MPTCC_FMA2(C.a[3 * i + 2], dz, MPTCC_FMA2(C.a[3 * i + 1], dy, MPTCC_MUL2(C.a[3 * i], dx)));
+		nt[i] = neg2(t[i]);
+	}
+	// margin = 192 u (|Ty|_1 + |cS|_1 + |cC|_1)
+	float2 mg = MPTCC_MUL2(bc2(192.0f * kU), MPTCC_ADD2(bc2(f.s1), MPTCC_ADD2(MPTCC_ADD2(abs2(C.c[0]), abs2(C.c[1])), abs2(C.c[2]))));
+	if (Q) mg = MPTCC_FMA2(bc2(kQFrameMargin), MPTCC_ADD2(MPTCC_ADD2(MPTCC_ADD2(C.e[0], C.e[1]), C.e[2]), bc2(es.x + es.y + es.z)), mg);
+	float2 F[9];
+#pragma unroll
+	for (int k = 0; k < 9; ++k) F[k] = MPTCC_ADD2(abs2(G[k]), bc2(3e-6f));
+	const float ebv[3] = {es.x, es.y, es.z};
+	unsigned dj = 0u;
+#define MPTCC_CMP2(lhs, rhs)                                                       \
+	{                                                                              \
+		const float2 l_ = (lhs), r_ = (rhs);                                       \
+		dj |= (fabsf(l_.x) > r_.x ? 1u : 0u) | (fabsf(l_.y) > r_.y ? 2u : 0u);     \
+	}
+	// face axes of the child: |t_i| > ea_i + (F[3i] eb0 + F[3i+1] eb1 + F[3i+2] eb2) + mg
+#pragma unroll
+	for (int i = 0; i < 3; ++i)
+		MPTCC_CMP2(t[i], MPTCC_FMA2(F[3 * i + 2], bc2(ebv[2]), MPTCC_FMA2(F[3 * i + 1], bc2(ebv[1]), MPTCC_FMA2(F[3 * i], bc2(ebv[0]), MPTCC_ADD2(C.e[i], mg)))))
+	// face axes of S: |t . G(:,j)| > eb_j + (F[j] ea0 + F[3+j] ea1 + F[6+j] ea2) + mg
+#pragma unroll
+	for (int j = 0; j < 3; ++j)
+		MPTCC_CMP2(MPTCC_FMA2(t[2], G[6 + j], MPTCC_FMA2(t[1], G[3 + j], MPTCC_MUL2(t[0], G[j]))),
+		           MPTCC_FMA2(F[6 + j], C.e[2], MPTCC_FMA2(F[3 + j], C.e[1], MPTCC_FMA2(F[j], C.e[0], MPTCC_ADD2(bc2(ebv[j]), mg)))))
+	// edge axes a_i x b_j, (i1, i2) = the other two child axes, (j1, j2) = the other two axes of S:
+	//   |t_i2 G(i1,j) - t_i1 G(i2,j)| > ea_i1 F(i2,j) + ea_i2 F(i1,j) + eb_j1 F(i,j2) + eb_j2 F(i,j1) + mg
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+#pragma unroll
+		for (int j = 0; j < 3; ++j) {
+			const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+			MPTCC_CMP2(MPTCC_FMA2(t[i2], G[3 * i1 + j], MPTCC_MUL2(nt[i1], G[3 * i2 + j])),
+			           MPTCC_FMA2(F[3 * i + j1], bc2(ebv[j2]), MPTCC_FMA2(F[3 * i + j2], bc2(ebv[j1]), MPTCC_FMA2(C.e[i2], F[3 * i1 + j], MPTCC_FMA2(C.e[i1], F[3 * i2 + j], mg)))))
+		}
+	}
+#undef MPTCC_CMP2
+	return dj;
 }
 
 }  // namespace

@@ -26,21 +26,32 @@ cub = [f for f in os.listdir(tmp) if f.startswith(os.environ.get("NCU_CUBIN", "c
 dis = subprocess.run(["nvdisasm", "-g", "-c", os.path.join(tmp, cub)], capture_output=True, text=True).stdout
 # offset -> (function, line)
 line_of = {}
-cur_fn, cur_line = None, 0
+cur_fn, cur_line = None, ("?", 0)
 for l in dis.splitlines():
     m = re.match(r"\s*\.section\s+\.text\.(\S+?),", l)
     if m:
         cur_fn = m.group(1)
         continue
-    m = re.search(r'//## File ".*?", line (\d+)', l)
+    m = re.search(r'//## File "(.*?)", line (\d+)', l)
     if m:
-        cur_line = int(m.group(1))
+        cur_line = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
     m = re.match(r"\s*/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
     if m and cur_fn:
         line_of[(cur_fn, int(m.group(1), 16))] = cur_line
 
-src = open(os.path.join(ROOT, "motionplanningtoolkit_b200", "csrc", os.environ.get("NCU_SRC","collide_device.cuh"))).read().splitlines()
+_src_cache = {}
+
+
+def src_text(f, ln):
+    if f not in _src_cache:
+        path = os.path.join(ROOT, "motionplanningtoolkit_b200", "csrc", f)
+        _src_cache[f] = open(path).read().splitlines() if os.path.exists(path) else []
+    t = _src_cache[f]
+    return t[ln - 1].strip()[:80] if 0 < ln <= len(t) else "?"
+
+
+SORT = os.environ.get("NCU_SORT", "samples")  # or "inst"
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 # the report may hold several kernels; each starts with a "Kernel Name" row followed by a header row
@@ -69,7 +80,7 @@ agg = collections.defaultdict(lambda: collections.Counter())
 tot = collections.Counter()
 for r in body:
     off = int(r[ci["Address"]], 16) - base
-    ln = line_of.get((fn, off), -1)
+    ln = line_of.get((fn, off), ("?", -1))
     a = agg[ln]
     a["samples"] += int(r[ci["# Samples"]])
     a["inst"] += int(r[ci["Instructions Executed"]])
@@ -86,9 +97,9 @@ print("total samples %d, warp-instructions %d, avg threads/inst %.1f" % (tot["sa
 print("stall mix:", ", ".join("%s %.1f%%" % (k[6:], 100.0 * tot[k] / max(1, tot["samples"]))
                               for k in sorted(stall_keys, key=lambda k: -tot[k])[:8]))
 print("%7s %7s %5s  line  source" % ("samp%", "inst%", "thr"))
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1]["samples"])[:topn]:
+for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][SORT])[:topn]:
     st = sorted(((a[k], k[6:]) for k in stall_keys), reverse=True)[:3]
-    text = src[ln - 1].strip()[:80] if 0 < ln <= len(src) else "?"
-    print("%6.2f%% %6.2f%% %5.1f  %4d  %-80s %s" % (100.0 * a["samples"] / max(1, tot["samples"]), 100.0 * a["inst"] / max(1, tot["inst"]),
-                                                  a["thr"] / max(1, a["inst"]), ln, text,
+    text = src_text(*ln)
+    print("%6.2f%% %6.2f%% %5.1f  %-22s %-80s %s" % (100.0 * a["samples"] / max(1, tot["samples"]), 100.0 * a["inst"] / max(1, tot["inst"]),
+                                                  a["thr"] / max(1, a["inst"]), "%s:%d" % (ln[0][:16], ln[1]), text,
                                                   " ".join("%s:%d" % (k, v) for v, k in st if v)))

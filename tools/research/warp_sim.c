@@ -29,6 +29,7 @@ typedef struct {
 	int has;
 	int cand; /* candidate of everything this lane holds */
 	int paused;
+	int last_s; /* stationary node of the lane's previous step: kind * 2^24 + id, -1 = none */
 } wlane;
 
 typedef struct {
@@ -41,7 +42,7 @@ typedef struct {
 	int nlq;
 	int qhead, qend; /* mode 0: unstarted candidates [qhead, qend) of the batch */
 	int done;
-	uint64_t steps_node, steps_leaf, active_lanes, stolen;
+	uint64_t steps_node, steps_leaf, active_lanes, stolen, same_s, lane_steps;
 } wwarp;
 
 static int wtest(const orc_model *m1, const orc_model *m2, const wcand *c, int b1, int b2, double *d2) {
@@ -61,7 +62,7 @@ static int wtest(const orc_model *m1, const orc_model *m2, const wcand *c, int b
 
 typedef struct {
 	int mode, batch, leaf_thresh, n_warps, pause_on_leaf, steal_in_stream;
-	uint64_t rounds, steps_node, steps_leaf, tests, leaf_tests, active_lanes, stolen;
+	uint64_t rounds, steps_node, steps_leaf, tests, leaf_tests, active_lanes, stolen, same_s, lane_steps;
 } wsim_cfg;
 
 int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double *poses, int fmt, wsim_cfg *cfg) {
@@ -127,6 +128,7 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					wlane *L = &ww->lane[l];
 					if (!L->has && !L->paused && ww->qhead < ww->qend) {
 						L->cand = ww->qhead++;
+						L->last_s = -1;
 						L->cur = (wplan){0, 0, 0};
 						L->has = 1;
 						L->top = 0;
@@ -137,6 +139,7 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					wlane *L = &ww->lane[l];
 					if (!L->has && !L->paused && next < nc) {
 						L->cand = (int)next++;
+						L->last_s = -1;
 						L->cur = (wplan){0, 0, 0};
 						L->has = 1;
 						L->top = 0;
@@ -153,6 +156,7 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					if (d == 32) break;
 					L->cur = ww->lane[d].stk[--ww->lane[d].top];
 					L->cand = ww->lane[d].cand;
+					L->last_s = -1;
 					L->has = 1;
 					L->top = 0;
 					ww->stolen++;
@@ -211,6 +215,12 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					L->top = 0;
 					continue;
 				}
+				{
+					const int sid = pl.kind == 2 ? (2 << 24) + pl.x : (1 << 24) + pl.y;
+					ww->lane_steps++;
+					if (sid == L->last_s) ww->same_s++;
+					L->last_s = sid;
+				}
 				const orc_model *m1 = env->models[c->obj];
 				wplan out[2];
 				int ok[2] = {0, 0};
@@ -253,12 +263,14 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 	cfg->rounds = rounds;
 	cfg->tests = tests;
 	cfg->leaf_tests = leaf_tests;
-	cfg->steps_node = cfg->steps_leaf = cfg->active_lanes = cfg->stolen = 0;
+	cfg->steps_node = cfg->steps_leaf = cfg->active_lanes = cfg->stolen = cfg->same_s = cfg->lane_steps = 0;
 	for (int w = 0; w < cfg->n_warps; ++w) {
 		cfg->steps_node += W[w].steps_node;
 		cfg->steps_leaf += W[w].steps_leaf;
 		cfg->active_lanes += W[w].active_lanes;
 		cfg->stolen += W[w].stolen;
+		cfg->same_s += W[w].same_s;
+		cfg->lane_steps += W[w].lane_steps;
 	}
 	free(W);
 	free(dead);
