@@ -792,7 +792,8 @@ __device__ __forceinline__ void make_candidate_record(const KernelParams &p, con
 // is not a rotation to within 1e-11 (then (R^T, Tinv) is not the inverse and the caller must route the launch to
 // the fused kernel, which makes no such assumption).
 __device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, const double *pose_rec, const DevObject &ob,
-                                                       const DevModel &m2, float4 *rec, double *rel64, uint2 &base) {
+                                                       const DevModel &m2, float4 *rec, double *rel64, uint2 &base,
+                                                       float *cert = nullptr) {
 	const DevModel &m1 = p.env.models[ob.model];
 	double R2[9], T2[3], rl[12];
 	Quat q;
@@ -829,6 +830,14 @@ __device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, co
 	rec[2] = make_float4((float)rl[8], (float)tc[0], (float)tc[1], (float)tc[2]);
 	rec[3] = make_float4((float)ti[0], (float)ti[1], (float)ti[2], S);
 	base = make_uint2(m1.node_base, m1.tri_base);
+	if (cert != nullptr) {
+		// Path certificate threshold: 1e-5 x an upper bound of the magnitudes entering FCL's OBB
+		// tests on the path to any leaf pair of this candidate -- |T|_1 of the exact transform is bounded through the
+		// recentred translation -- rounded up to fp32.  NaN compares false, i.e. "replay".
+		const double mag = (fabs(tc[0]) + fabs(tc[1]) + fabs(tc[2])) * (1.0 + 4e-6) + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
+		                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 + m1.esum + m2.esum;
+		*cert = __double2float_ru(1e-5 * mag * (1.0 + 1e-12));
+	}
 	return finite && defect <= 1e-11;
 }
 

@@ -134,6 +134,8 @@ struct KernelParams {
 	uint32_t qnode;                // 1: traverse nodeq (32-byte nodes), 0: node32
 	uint32_t agent_top;            // agent nodes [0, agent_top) of link model 0 are staged in shared memory (breadth-first ids)
 	// third-generation narrowphase (np3_kernels.cu)
+	float *cand_cert;              // [cand_cap] path-certificate threshold of the candidate: a positive leaf pair needs no path
+	                               // replay if the mu_chain of both triangles is >= this
 	const float4 *agent_swz;       // link model 0's node32 records in the bank-swizzled order the np3 kernel stages with TMA
 };
 

@@ -485,6 +485,7 @@ struct SplitBufs {
 	DevBuf<double> rel;
 	DevBuf<uint32_t> obj, pose;
 	DevBuf<uint2> base;        // node_base / tri_base of each candidate's environment model
+	DevBuf<float> cert;        // path-certificate threshold of each candidate
 	DevBuf<uint4> xq;          // exact-pass queue (np2_kernels.cu)
 	DevBuf<unsigned int> ctl;  // [0] cand_total, [1] overflow flags (1 = list full, 2 = non-rigid pose), [2] narrowphase
 	                           // batch counter, [3] exact-queue length
@@ -494,6 +495,7 @@ struct SplitBufs {
 		obj.release();
 		pose.release();
 		base.release();
+		cert.release();
 		xq.release();
 		ctl.release();
 	}
@@ -714,6 +716,7 @@ int reserve_split(mptcc_ctx *ctx, SplitBufs &sb, uint64_t n) {
 	CU(sb.obj.reserve(cap64));
 	CU(sb.pose.reserve(cap64));
 	CU(sb.base.reserve(cap64));
+	CU(sb.cert.reserve(cap64));
 	CU(sb.xq.reserve(cap64));
 	CU(sb.ctl.reserve(4));
 	return MPTCC_OK;
@@ -790,6 +793,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		const bool np3 = ctx->opt_np3 != 0;
 		const bool np2 = ctx->opt_np2 != 0 || np3;
 		kp.cand_base = sb->base.p;
+		kp.cand_cert = sb->cert.p;
 		kp.xq = sb->xq.p;
 		kp.xq_total = sb->ctl.p + 3;
 		kp.xq_cap = (unsigned int)cap64;

@@ -329,7 +329,6 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			bool certified = false;
 			uint4 e = make_uint4(0u, 0u, 0u, 0xfffffffeu);
 			uint2 base = make_uint2(0u, 0u);
-			float tn1 = 0.f;
 			if (lane < k) {
 				e = leafq[lq + lane];
 				if (!pose_settled(hits, e.w)) {
@@ -340,7 +339,6 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					x.R[4] = ra.b.x; x.R[5] = ra.b.y; x.R[6] = ra.b.z; x.R[7] = ra.b.w;
 					x.R[8] = rb.a.x; x.T[0] = rb.a.y; x.T[1] = rb.a.z; x.T[2] = rb.a.w;
 					x.S = rb.b.w;
-					tn1 = (fabsf(x.T[0]) + fabsf(x.T[1]) + fabsf(x.T[2])) * 1.000001f;
 					base = p.cand_base[e.z];
 					const float4 *t1 = p.env.tri32 + 3ull * (base.y + e.x);
 					const float4 *t2 = tris2 + 3ull * e.y;
@@ -348,14 +346,9 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
 					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
 					if (verdict == TRI_INTERSECT && !p.always_replay) {
-						// path certificate, evaluated from the fp32 record: a larger magnitude
-						// only makes it stricter
-						const DevModel &m1 = p.env.models[p.objects[p.cand_obj[e.z]].model];
-						const double mag = (double)tn1 + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
-						                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
-						                   m1.esum + m2.esum;
-						const double mu = fmin((double)p.env.mu_chain[base.y + e.x], (double)p.agent.mu_chain[m2.tri_base + e.y]);
-						certified = mu >= 1e-5 * mag;
+						// path certificate against the candidate's threshold from the broadphase kernel
+						const float mu = fminf(p.env.mu_chain[base.y + e.x], p.agent.mu_chain[m2.tri_base + e.y]);
+						certified = mu >= p.cand_cert[e.z];
 					}
 				}
 			}
@@ -386,12 +379,8 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					if (hit) {  // certificate with the record's magnitudes; uncertified contacts go to exact_kernel (path replay)
 						bool cert2 = false;
 						if (lane == from && !p.always_replay) {
-							const DevModel &m1 = p.env.models[p.objects[p.cand_obj[c]].model];
-							const double mag = (double)tn1 + fabs(m1.ctr[0]) + fabs(m1.ctr[1]) + fabs(m1.ctr[2]) +
-							                   1.75 * (fabs(m2.ctr[0]) + fabs(m2.ctr[1]) + fabs(m2.ctr[2])) + m1.cmax1 + m2.cmax1 +
-							                   m1.esum + m2.esum;
-							const double mu = fmin((double)p.env.mu_chain[tb + t1], (double)p.agent.mu_chain[m2.tri_base + t2]);
-							if (mu >= 1e-5 * mag) {
+							const float mu = fminf(p.env.mu_chain[tb + t1], p.agent.mu_chain[m2.tri_base + t2]);
+							if (mu >= p.cand_cert[c]) {
 								atomicOr(p.verdict_bits + (ps >> 5), 1u << (ps & 31u));
 								verdict = TRI_SEPARATED;  // settled
 								cert2 = true;

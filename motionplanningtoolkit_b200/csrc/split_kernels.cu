@@ -166,9 +166,11 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 							float4 *out = p.cand_rec + 4ull * dst;
 							if (NP2) {
 								uint2 mbase;
-								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase))
+								float cert;
+								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase, &cert))
 									atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
 								p.cand_base[dst] = mbase;
+								p.cand_cert[dst] = cert;
 							} else {
 								make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
 							}
