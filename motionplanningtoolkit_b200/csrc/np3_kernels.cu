@@ -233,7 +233,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					pose = __float_as_uint(s4.z);
 					nb1 = __float_as_uint(s4.x);
 					if (!pose_settled(hits, pose)) {
-						cur = make_uint2(0u, kPlan3Single);
+						cur = make_uint2(0u, kPlan3Single | kPlan3Env);  // root pair: (environment root, agent root)
 						has = true;
 					}
 				}
@@ -431,52 +431,54 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 		if (has) {
 			const uint2 pr = cur;
 			has = false;
+			// plan = (x, y | flags): x = first child of the sibling pair in the tree that is descended, y = the stationary node
+			// of the other tree, kPlan3Env: the descended tree is the environment's
 			const bool single = (pr.y & kPlan3Single) != 0u;
-			const bool env_side = single || (pr.y & kPlan3Env) != 0u;  // the children are environment nodes
-			const uint32_t i2base = pr.y & kPlan3Idx;
+			const bool env_side = (pr.y & kPlan3Env) != 0u;
+			const uint32_t xi = pr.x, yi = pr.y & kPlan3Idx;
 			const float4 *rs = NP3_SLOT(lane, rd);
 			const float4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3];  // R (9), Tc (3), Tinv (3), S
 			const float ti0 = r3.x, ti1 = r3.y, ti2 = r3.z;
 			// Loads only: nothing below consumes a loaded value before every load of the step has been issued, so the
 			// two kinds of step (children = environment nodes / agent nodes) do not wait for memory one after the other.
-			const float4 *ep = p.env.node32 + 4ull * ((unsigned long long)nb1 + pr.x);
-			const unsigned second = single ? 0u : 4u;  // (the root pair is one test: its "second child" repeats the first)
+			const unsigned second = single ? 0u : 1u;  // (the root pair is one test: its "second child" repeats the first)
 			Node S;
 			Node2 C2;  // both children, side by side (np_sat.cuh)
 			if (TOP) {
 				Node C0, C1;
+				const float4 *ep = p.env.node32 + 4ull * ((unsigned long long)nb1 + (env_side ? xi : yi));
+				const uint32_t ia = env_side ? yi : xi;
 				if (env_side) {
 					C0 = node_global(ep);
-					C1 = node_global(ep + second);
-					if (i2base < ktop) S = node_shared_swz(atop, i2base);
-					else S = node_global(nodes2 + 4ull * i2base);
+					C1 = node_global(ep + 4u * second);
+					if (ia < ktop) S = node_shared_swz(atop, ia);
+					else S = node_global(nodes2 + 4ull * ia);
 				} else {
 					S = node_global(ep);
-					if (i2base + 1u < ktop) {
-						C0 = node_shared_swz(atop, i2base);
-						C1 = node_shared_swz(atop, i2base + 1u);
+					if (ia + 1u < ktop) {
+						C0 = node_shared_swz(atop, ia);
+						C1 = node_shared_swz(atop, ia + 1u);
 					} else {
-						C0 = node_global(nodes2 + 4ull * i2base);
-						C1 = node_global(nodes2 + 4ull * i2base + 4);
+						C0 = node_global(nodes2 + 4ull * ia);
+						C1 = node_global(nodes2 + 4ull * ia + 4);
 					}
 				}
 				C2 = pack_nodes(C0, C1);
 			} else if (Q) {
 				// 32-byte quantised nodes (device_layout.hpp, nodeq): one 256-bit load per node
-				const uint4 *eq = p.env.nodeq + 2ull * ((unsigned long long)nb1 + pr.x);
-				const uint4 *aq = p.agent.nodeq + 2ull * ((unsigned long long)m2.node_base + i2base);
-				const uint4 *op = env_side ? aq : eq, *cp = env_side ? eq : aq;
+				const uint4 *eq = p.env.nodeq + 2ull * nb1, *aq = p.agent.nodeq + 2ull * m2.node_base;
+				const uint4 *cp = (env_side ? eq : aq) + 2ull * xi, *op = (env_side ? aq : eq) + 2ull * yi;
 				uint4 s0, s1, a0, a1, b0, b1;
 				ldg256u(op, s0, s1);
 				ldg256u(cp, a0, a1);
-				ldg256u(cp + (second >> 1), b0, b1);
+				ldg256u(cp + 2u * second, b0, b1);
 				S = node_decode(s0, s1);
 				C2 = node2_decode(a0, a1, b0, b1);
 			} else {
-				const float4 *ap = nodes2 + 4ull * i2base;
-				const float4 *op = env_side ? ap : ep, *cp = env_side ? ep : ap;
+				const float4 *e4 = p.env.node32 + 4ull * nb1;
+				const float4 *cp = (env_side ? e4 : nodes2) + 4ull * xi, *op = (env_side ? nodes2 : e4) + 4ull * yi;
 				S = node_global(op);
-				const Node C0 = node_global(cp), C1 = node_global(cp + second);
+				const Node C0 = node_global(cp), C1 = node_global(cp + 4u * second);
 				C2 = pack_nodes(C0, C1);
 			}
 			// (Ry, Ty): the relative transform when the children are environment nodes, its inverse otherwise
@@ -511,6 +513,8 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			const unsigned djm = pair_disjoint<Q>(f, C2, S.v3, d2p);
 			const float2 sC2 = MPTCC_FMA2(C2.e[2], C2.e[2], MPTCC_FMA2(C2.e[1], C2.e[1], MPTCC_MUL2(C2.e[0], C2.e[0])));
 			n_tests = single ? 1u : 2u;
+			const bool lS = linkS < 0;
+			const uint32_t same = env_side ? kPlan3Env : 0u, flip = env_side ? 0u : kPlan3Env;
 #pragma unroll
 			for (int k = 0; k < 2; ++k) {
 				if (k == 1 && single) break;
@@ -518,20 +522,17 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				if (k == 0) d2_0 = d2p.x; else d2_1 = d2p.y;
 				const int linkC = k == 0 ? C2.link0 : C2.link1;
 				const float sC = k == 0 ? sC2.x : sC2.y;
-				// back to (environment, agent) roles
-				const int link1 = env_side ? linkC : linkS, link2 = env_side ? linkS : linkC;
-				const uint32_t i1 = pr.x + ((env_side && k) ? 1u : 0u);
-				const uint32_t i2 = i2base + ((!env_side && k) ? 1u : 0u);
-				const bool l1 = link1 < 0, l2 = link2 < 0;
-				if (l1 && l2) {
-					const uint2 lf = make_uint2((uint32_t)(-(link1 + 1)), (uint32_t)(-(link2 + 1)));
+				const bool lC = linkC < 0;
+				if (lC && lS) {  // two leaves: (environment primitive, agent primitive); primitive = -(link + 1) = ~link
+					const uint32_t pC = ~(uint32_t)linkC, pS = ~(uint32_t)linkS;
+					const uint2 lf = env_side ? make_uint2(pC, pS) : make_uint2(pS, pC);
 					if (k == 0) { leaf0 = true; lf0 = lf; } else { leaf1 = true; lf1 = lf; }
 					continue;
 				}
-				// firstOverSecond: descend the environment tree iff l2 || (!l1 && size1 > size2)
-				const float s1 = env_side ? sC : sS, s2 = env_side ? sS : sC;
-				const bool first = l2 || (!l1 && s1 > s2);
-				const uint2 pl = first ? make_uint2((uint32_t)link1, i2 | kPlan3Env) : make_uint2(i1, (uint32_t)link2);
+				// FCL's firstOverSecond (descend the environment node iff the agent node is a leaf, or the environment node is
+				// not and is the larger one), stated for "descend the child's tree again" (descX) against "now descend S":
+				const bool descX = !lC && (lS || (env_side ? sC > sS : !(sS > sC)));
+				const uint2 pl = descX ? make_uint2((uint32_t)linkC, yi | same) : make_uint2((uint32_t)linkS, (xi + (uint32_t)k) | flip);
 				if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
 			}
 			if (ok0 && ok1) {
