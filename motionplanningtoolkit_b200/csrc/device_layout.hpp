@@ -52,6 +52,26 @@ __host__ __device__
 #endif
 inline constexpr unsigned pose_rec_len(unsigned fmt) { return fmt == 1u ? 7u : fmt == 2u ? 3u : fmt == 3u ? 5u : 12u; }
 
+// Broadphase grid (single-link agents, split pipeline).  The scene box is cut into grid_n[0] x [1] x [2] cells no
+// smaller than the largest world box a pose of the agent can have, so a pose box touches at most two cells per axis.
+// Cell (i, j, k) owns the list of the objects whose box touches one of the cells [i, i+1] x [j, j+1] x [k, k+1]:
+// grid_cells[(i n1 + j) n2 + k] = (first entry, count), entries = 64 bytes: the object's exact fp64 world box
+// (min xyz, max xyz, what obj_aabb holds), the object index (as the low word of the 7th double) and padding.
+// grid_cell() is the one cell-index function of the host (objects) and the device (poses); it is monotone in x, so
+// two boxes that overlap always share a cell along every axis.
+struct GridEntry {
+	double aabb[6];
+	unsigned long long obj;
+	unsigned long long pad;
+};
+#ifdef __CUDACC__
+__host__ __device__
+#endif
+inline int grid_cell(double x, float origin, float inv, int n) {
+	const float v = ((float)x - origin) * inv;
+	return v >= (float)n ? n - 1 : (v > 0.0f ? (int)v : 0);
+}
+
 struct DevModel {
 	uint32_t node_base;
 	uint32_t tri_base;
@@ -134,6 +154,10 @@ struct KernelParams {
 	uint32_t qnode;                // 1: traverse nodeq (32-byte nodes), 0: node32
 	uint32_t agent_top;            // agent nodes [0, agent_top) of link model 0 are staged in shared memory (breadth-first ids)
 	// third-generation narrowphase (np3_kernels.cu)
+	const uint2 *grid_cells;       // broadphase grid (see above); nullptr: walk the cluster tree
+	const GridEntry *grid_entries;
+	float grid_origin[3], grid_inv[3];
+	int grid_n[3];
 	float *cand_cert;              // [cand_cap] path-certificate threshold of the candidate: a positive leaf pair needs no path
 	                               // replay if the mu_chain of both triangles is >= this
 	const float4 *agent_swz;       // link model 0's node32 records in the bank-swizzled order the np3 kernel stages with TMA

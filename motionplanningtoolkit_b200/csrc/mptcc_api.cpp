@@ -513,6 +513,8 @@ struct Device {
 	DevBuf<uint4> bp_nodes;
 	DevBuf<uint32_t> link_model;
 	DevBuf<DevObject> self_objects;  // one per link (model id only): the "objects" of the self-collision kernel
+	DevBuf<uint2> grid_cells;        // broadphase grid (device_layout.hpp)
+	DevBuf<GridEntry> grid_entries;
 	DevBuf<float4> agent_swz;        // link model 0's traversal nodes, bank-swizzled for the np3 kernel's shared-memory copy
 	DevBuf<double> poses[kPipe];
 	DevBuf<uint32_t> bits[kPipe];
@@ -551,6 +553,10 @@ struct mptcc_ctx {
 	std::vector<uint32_t> link_model_h;
 	std::vector<DevObject> self_objects_h;
 	std::vector<float4> agent_swz_h;
+	std::vector<uint2> grid_cells_h;  // broadphase grid: empty = not available (the tree is walked instead)
+	std::vector<GridEntry> grid_entries_h;
+	float grid_origin[3] = {0.f, 0.f, 0.f}, grid_inv[3] = {1.f, 1.f, 1.f};
+	int grid_n[3] = {1, 1, 1};
 	bool env_set = false, agent_set = false;
 	bool env_q_ok = true, agent_q_ok = true;  // every model small enough for the 24-bit links of the quantised nodes
 	std::string err;
@@ -573,6 +579,7 @@ struct mptcc_ctx {
 	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
 	long opt_qnode = 1;              // np2/np3 traverse the 32-byte quantised nodes (one 256-bit load per node); 0 = the 64-byte fp32 nodes
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
+	long opt_grid = 1;               // grid broadphase for single-link agents (0 = always walk the cluster tree)
 	long opt_np3 = 1;                // third-generation narrowphase (np3_kernels.cu, streaming lanes): the default; 0 = the round-1 kernel
 	                                 // (split_kernels.cu), or np2_kernels.cu with np2 = 1
 	mptcc_counters ctr{};
@@ -648,6 +655,90 @@ int upload_scene_part(mptcc_ctx *ctx, bool env) {
 	return MPTCC_OK;
 }
 
+// Broadphase grid for a single-link agent (device_layout.hpp).  Needs the environment (object boxes) and the agent
+// (largest pose box); rebuilt whenever either changes.  Leaves grid_cells_h empty when the grid does not apply.
+int build_grid(mptcc_ctx *ctx) {
+	ctx->grid_cells_h.clear();
+	ctx->grid_entries_h.clear();
+	const auto upload = [&]() -> int {
+		for (auto &d : ctx->devs) {
+			CU(cudaSetDevice(d.id));
+			CU(d.grid_cells.upload(ctx->grid_cells_h, d.stream[0]));
+			CU(d.grid_entries.upload(ctx->grid_entries_h, d.stream[0]));
+			CU(cudaStreamSynchronize(d.stream[0]));
+		}
+		return MPTCC_OK;
+	};
+	if (ctx->objects_h.empty() || ctx->link_model_h.size() != 1 || ctx->agent_h.models.empty()) return upload();
+	const DevModel &am = ctx->agent_h.models[ctx->link_model_h[0]];
+	double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, amax = 0.0;
+	for (const auto &o : ctx->objects_h)
+		for (int k = 0; k < 3; ++k) {
+			if (!std::isfinite(o.aabb[k]) || !std::isfinite(o.aabb[3 + k])) return upload();
+			lo[k] = std::min(lo[k], o.aabb[k]);
+			hi[k] = std::max(hi[k], o.aabb[3 + k]);
+			amax = std::max(amax, std::max(std::fabs(o.aabb[k]), std::fabs(o.aabb[3 + k])));
+		}
+	// Every pose box is at most this wide: the sphere box of a rotated pose is 2 radius wide and contains the tight
+	// box of an unrotated one.  The slack covers the fp32 rounding of the coordinates inside grid_cell().
+	if (!std::isfinite(am.aabb_radius)) return upload();
+	const double side = 2.0 * am.aabb_radius * (1.0 + 1e-4) + 8.0 * (amax + 2.0 * am.aabb_radius) * 1.2e-7 + 1e-30;
+	for (int nmax = 128; nmax >= 1; nmax /= 2) {
+		for (int k = 0; k < 3; ++k) {
+			const double ext = hi[k] - lo[k];
+			const double cell = std::max(side, ext / nmax);
+			ctx->grid_origin[k] = round_down_f32(lo[k]);
+			ctx->grid_inv[k] = round_down_f32(1.0 / cell);
+			ctx->grid_n[k] = std::max(1, std::min(nmax, (int)std::ceil(ext / cell) + 1));
+			if (!(ctx->grid_inv[k] > 0.f) || !std::isfinite(ctx->grid_inv[k])) return upload();
+		}
+		const int n0 = ctx->grid_n[0], n1 = ctx->grid_n[1], n2 = ctx->grid_n[2];
+		const size_t ncell = (size_t)n0 * n1 * n2;
+		std::vector<uint32_t> cnt(ncell + 1, 0u);
+		// blocks (i, j, k) whose cells [i, i+1] touch the object's cells [a, b]: i in [a - 1, b]
+		int rng[6];
+		const auto range_of = [&](const DevObject &o) {
+			for (int k = 0; k < 3; ++k) {
+				const int a = grid_cell(o.aabb[k], ctx->grid_origin[k], ctx->grid_inv[k], ctx->grid_n[k]);
+				const int b = grid_cell(o.aabb[3 + k], ctx->grid_origin[k], ctx->grid_inv[k], ctx->grid_n[k]);
+				rng[k] = std::max(0, a - 1);
+				rng[3 + k] = b;
+			}
+		};
+		size_t total = 0;
+		for (const auto &o : ctx->objects_h) {
+			range_of(o);
+			total += (size_t)(rng[3] - rng[0] + 1) * (rng[4] - rng[1] + 1) * (rng[5] - rng[2] + 1);
+		}
+		if (total > (size_t)(3u << 19) && nmax > 1) continue;  // more than 96 MB of entries: a coarser grid
+		for (const auto &o : ctx->objects_h) {
+			range_of(o);
+			for (int i = rng[0]; i <= rng[3]; ++i)
+				for (int j = rng[1]; j <= rng[4]; ++j)
+					for (int k = rng[2]; k <= rng[5]; ++k) ++cnt[((size_t)i * n1 + j) * n2 + k + 1];
+		}
+		for (size_t c = 0; c < ncell; ++c) cnt[c + 1] += cnt[c];
+		ctx->grid_cells_h.resize(ncell);
+		for (size_t c = 0; c < ncell; ++c) ctx->grid_cells_h[c] = make_uint2(cnt[c], cnt[c + 1] - cnt[c]);
+		ctx->grid_entries_h.assign(total, GridEntry{});
+		std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+		for (size_t oi = 0; oi < ctx->objects_h.size(); ++oi) {
+			const DevObject &o = ctx->objects_h[oi];
+			range_of(o);
+			for (int i = rng[0]; i <= rng[3]; ++i)
+				for (int j = rng[1]; j <= rng[4]; ++j)
+					for (int k = rng[2]; k <= rng[5]; ++k) {
+						GridEntry &g = ctx->grid_entries_h[fill[((size_t)i * n1 + j) * n2 + k]++];
+						for (int a = 0; a < 6; ++a) g.aabb[a] = o.aabb[a];
+						g.obj = oi;
+						g.pad = 0;
+					}
+		}
+		break;
+	}
+	return upload();
+}
+
 // Outstanding submits and device-buffer launches still read the scene arrays: a set_* call (which may overwrite
 // them in place) or an option that changes what later launches do first waits for all of it.
 int drain(mptcc_ctx *ctx) {
@@ -693,6 +784,13 @@ void fill_params(mptcc_ctx *ctx, Device &d, KernelParams &kp) {
 	kp.n_links = (uint32_t)ctx->link_model_h.size();
 	kp.counters = ctx->count ? d.counters.p : nullptr;
 	kp.always_replay = ctx->opt_always_replay ? 1u : 0u;
+	kp.grid_cells = ctx->opt_grid && !ctx->grid_cells_h.empty() ? d.grid_cells.p : nullptr;
+	kp.grid_entries = d.grid_entries.p;
+	for (int k = 0; k < 3; ++k) {
+		kp.grid_origin[k] = ctx->grid_origin[k];
+		kp.grid_inv[k] = ctx->grid_inv[k];
+		kp.grid_n[k] = ctx->grid_n[k];
+	}
 	kp.cand_rec = nullptr;
 	kp.cand_rel = nullptr;
 	kp.cand_obj = nullptr;
@@ -981,6 +1079,8 @@ void mptcc_destroy(mptcc_ctx *ctx) {
 		d.link_model.release();
 		d.self_objects.release();
 		d.agent_swz.release();
+		d.grid_cells.release();
+		d.grid_entries.release();
 		d.counters.release();
 		d.work_user.release();
 		for (auto &sb : d.split) sb.release();
@@ -1104,6 +1204,7 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 	const int rc = upload_scene_part(ctx, true);
 	if (rc != MPTCC_OK) return rc;
 	ctx->env_set = true;
+	if (ctx->agent_set) return build_grid(ctx);
 	return MPTCC_OK;
 }
 
@@ -1148,6 +1249,7 @@ int mptcc_set_agent(mptcc_ctx *ctx, int n_links, const mptcc_mesh *link_meshes) 
 	const int rc = upload_scene_part(ctx, false);
 	if (rc != MPTCC_OK) return rc;
 	ctx->agent_set = true;
+	if (ctx->env_set) return build_grid(ctx);
 	return MPTCC_OK;
 }
 
@@ -1495,6 +1597,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 			if (drc != MPTCC_OK) return drc;
 		}
 		ctx->opt_self_collision = value != 0;
+	} else if (k == "grid") {
+		ctx->opt_grid = value != 0;
 	} else if (k == "np3") {
 		ctx->opt_np3 = value != 0;
 	} else if (k == "np2") {

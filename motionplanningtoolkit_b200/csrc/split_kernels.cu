@@ -40,6 +40,69 @@ __host__ __device__ constexpr unsigned np_warp_smem_bytes(unsigned batch) {
 	return kLeafQueueCap * 8u + batch * 64u + 16u * 8u + batch * 4u + batch * 4u + batch + 32u;
 }
 
+// Phase C2 + append: the `ncand` candidates (pose slot << 26 | object) in wm.cand_ids are grouped by pose slot, their
+// records are computed (fp64 relative transform -> fp32 record) and appended to the global candidate list.
+template <bool NP2>
+__device__ __forceinline__ void flush_candidates(const KernelParams &p, const WarpMem &wm, unsigned *pfx, int ncand,
+                                                 const double *chunk_poses, unsigned rec_len, bool aligned32,
+                                                 unsigned long long pose0, const DevModel &m2, int lane) {
+	// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
+	int mine = 0;
+	for (int i = 0; i < ncand; ++i) mine += (wm.cand_ids[i] >> 26) == (unsigned)lane;
+	int pre = mine;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int v = __shfl_up_sync(FULL, pre, o);
+		if (lane >= o) pre += v;
+	}
+	pfx[lane] = (unsigned)(pre - mine);
+	unsigned gbase = 0;
+	if (lane == 0) gbase = atomicAdd(p.cand_total, (unsigned)ncand);
+	gbase = __shfl_sync(FULL, gbase, 0);
+	__syncwarp();
+	if ((unsigned long long)gbase + (unsigned)ncand > (unsigned long long)p.cand_cap) {
+		if (lane == 0) atomicOr(p.overflow, 1u);  // the fused fall-back recomputes this launch
+		return;
+	}
+	for (int i = lane; i < ncand; i += 32) {
+		const uint32_t id = wm.cand_ids[i];
+		const unsigned sl = id >> 26, e = id & 0x3ffffffu;
+		int rank = 0;  // candidates of the same pose slot that precede i
+		for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
+		const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
+		float4 rec[4];
+		double pose[12], rel[12];
+		load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
+		float4 *out = p.cand_rec + 4ull * dst;
+		if (NP2) {
+			uint2 mbase;
+			float cert;
+			if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase, &cert))
+				atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
+			p.cand_base[dst] = mbase;
+			p.cand_cert[dst] = cert;
+		} else {
+			make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
+		}
+		// FCL's fp64 relative transform goes along for the exact pass.  (Recomputing it there from the pose
+		// record instead was measured: the broadphase kernel is not faster without these 96 bytes per
+		// candidate, and the narrowphase kernel is 3 % slower.)
+		double *orel = p.cand_rel + 12ull * dst;
+		stg256(orel, rel[0], rel[1], rel[2], rel[3]);
+		stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
+		stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
+#ifdef MPTCC_LIST_EF
+		stg256_evict_first(out, rec[0], rec[1]);
+		stg256_evict_first(out + 2, rec[2], rec[3]);
+#else
+		stg256(out, rec[0], rec[1]);
+		stg256(out + 2, rec[2], rec[3]);
+#endif
+		p.cand_obj[dst] = e;
+		p.cand_pose[dst] = (uint32_t)(pose0 + sl);
+	}
+}
+
 template <bool COUNT, bool NP2>
 __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -137,67 +200,133 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 			// ---- flush: group by pose slot, phase C2, append to the global candidate list --------------------
 			if (ncand > kCandCap - 32 || (!more && ncl == 0)) {
 				if (ncand > 0) {
-					// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
-					int mine = 0;
-					for (int i = 0; i < ncand; ++i) mine += (wm.cand_ids[i] >> 26) == (unsigned)lane;
-					int pre = mine;
-#pragma unroll
-					for (int o = 1; o < 32; o <<= 1) {
-						const int v = __shfl_up_sync(FULL, pre, o);
-						if (lane >= o) pre += v;
-					}
-					pfx[lane] = (unsigned)(pre - mine);
-					unsigned gbase = 0;
-					if (lane == 0) gbase = atomicAdd(p.cand_total, (unsigned)ncand);
-					gbase = __shfl_sync(FULL, gbase, 0);
-					__syncwarp();
-					if ((unsigned long long)gbase + (unsigned)ncand > (unsigned long long)p.cand_cap) {
-						if (lane == 0) atomicOr(p.overflow, 1u);  // the fused fall-back recomputes this launch
-					} else {
-						for (int i = lane; i < ncand; i += 32) {
-							const uint32_t id = wm.cand_ids[i];
-							const unsigned sl = id >> 26, e = id & 0x3ffffffu;
-							int rank = 0;  // candidates of the same pose slot that precede i
-							for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
-							const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
-							float4 rec[4];
-							double pose[12], rel[12];
-							load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
-							float4 *out = p.cand_rec + 4ull * dst;
-							if (NP2) {
-								uint2 mbase;
-								float cert;
-								if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase, &cert))
-									atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
-								p.cand_base[dst] = mbase;
-								p.cand_cert[dst] = cert;
-							} else {
-								make_candidate_record(p, pose, p.objects[e], m2, 0u, rec, rel);
-							}
-							// FCL's fp64 relative transform goes along for the exact pass.  (Recomputing it there from the pose
-							// record instead was measured: the broadphase kernel is not faster without these 96 bytes per
-							// candidate, and the narrowphase kernel is 3 % slower.)
-							double *orel = p.cand_rel + 12ull * dst;
-							stg256(orel, rel[0], rel[1], rel[2], rel[3]);
-							stg256(orel + 4, rel[4], rel[5], rel[6], rel[7]);
-							stg256(orel + 8, rel[8], rel[9], rel[10], rel[11]);
-#ifdef MPTCC_LIST_EF
-							stg256_evict_first(out, rec[0], rec[1]);
-							stg256_evict_first(out + 2, rec[2], rec[3]);
-#else
-							stg256(out, rec[0], rec[1]);
-							stg256(out + 2, rec[2], rec[3]);
-#endif
-							p.cand_obj[dst] = e;
-							p.cand_pose[dst] = (uint32_t)(pose0 + sl);
-						}
-					}
+					flush_candidates<NP2>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane);
 					n_cand_total += (unsigned)ncand;
 				}
 				ncand = 0;
 				__syncwarp();
 			}
 		}
+	}
+	if (COUNT && lane == 0 && n_cand_total) atomicAdd(p.counters + CTR_CAND, n_cand_total);
+}
+
+
+// Grid broadphase (device_layout.hpp, "Broadphase grid"): the world box of a pose of a single-link agent spans at most
+// two cells per axis, and every cell carries the list of the objects that touch its 2 x 2 x 2 block, with their exact
+// fp64 boxes inline: one header load and one coalesced stream of 64-byte entries per pose instead of a tree walk.
+// The list is a superset of FCL's candidates (the cell index is the same monotone function of a coordinate on the host
+// and here); every entry is re-tested with FCL's exact fp64 AABB::overlap.
+template <bool COUNT, bool NP2>
+__global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_grid_kernel(const __grid_constant__ KernelParams p) {
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	const int lane = threadIdx.x & 31;
+	const int warp = threadIdx.x >> 5;
+	unsigned char *base = smem_raw + (size_t)warp * bp_warp_smem_bytes();
+	WarpMem wm{};
+	wm.box = reinterpret_cast<double *>(base);
+	base += 6 * 32 * 8;
+	unsigned *excl = reinterpret_cast<unsigned *>(base);  // [32] first flat index of each pose slot's entries (cluster queue space)
+	unsigned *first = excl + 32;                           // [32] first list entry of each pose slot
+	base += kClusterQueueCap * 4;
+	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
+	base += kCandCap * 4;
+	unsigned *pfx = reinterpret_cast<unsigned *>(base);
+
+	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
+	const unsigned rec_len = pose_rec_len(p.pose_format);
+	const bool aligned32 = (reinterpret_cast<unsigned long long>(p.poses) & 31ull) == 0ull;
+	const unsigned lt = (1u << lane) - 1u;
+	const DevModel &m2 = p.agent.models[p.link_model[0]];
+	unsigned long long n_cand_total = 0;
+
+	while (true) {
+		unsigned chunk = 0;
+		if (lane == 0) chunk = atomicAdd(p.work_counter, 1u);
+		chunk = __shfl_sync(FULL, chunk, 0);
+		if (chunk >= n_chunks) break;
+		const unsigned long long pose0 = (unsigned long long)chunk << 5;
+		const unsigned long long left = p.n_pose_sets - pose0;
+		const unsigned nvalid = left < 32ull ? (unsigned)left : 32u;
+		const bool valid = (unsigned)lane < nvalid;
+		const double *chunk_poses = p.poses + pose0 * rec_len;
+
+		// ---- phase A + cell look-up (lane = pose) -------------------------------------------------------------------
+		unsigned start = 0, count = 0;
+		bool bad = false;
+		if (valid) {
+			double rec[12];
+			float amin[3], amax[3];
+			load_pose_record(chunk_poses + (size_t)lane * rec_len, p.pose_format, aligned32, rec);
+			pose_world_box(rec, p.pose_format, m2, wm.box + lane, amin, amax);
+			int c[3];
+#pragma unroll
+			for (int k = 0; k < 3; ++k) {
+				const double lo = wm.box[k * 32 + lane], hi = wm.box[(3 + k) * 32 + lane];
+				const int a = grid_cell(lo, p.grid_origin[k], p.grid_inv[k], p.grid_n[k]);
+				const int b = grid_cell(hi, p.grid_origin[k], p.grid_inv[k], p.grid_n[k]);
+				// a box that is not finite, or spans more than two cells (coordinates too large for the fp32 cell function):
+				// the launch goes to the fused kernel, which walks the tree with FCL's semantics for such boxes
+				bad = bad || !(fabs(lo) <= 1.7e308) || !(fabs(hi) <= 1.7e308) || b - a > 1 || b < a;
+				c[k] = a;
+			}
+			if (!bad) {
+				const uint2 hdr = __ldg(p.grid_cells + ((size_t)c[0] * p.grid_n[1] + c[1]) * p.grid_n[2] + c[2]);
+				start = hdr.x;
+				count = hdr.y;
+			}
+		}
+		if (__any_sync(FULL, bad)) {
+			if (lane == 0) atomicOr(p.overflow, 2u);
+			break;  // (every warp that sees the flag stops early; the fall-back recomputes everything)
+		}
+		unsigned pre = count;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const unsigned v = __shfl_up_sync(FULL, pre, o);
+			if (lane >= o) pre += v;
+		}
+		const unsigned total = __shfl_sync(FULL, pre, 31);
+		excl[lane] = pre - count;
+		first[lane] = start;
+		__syncwarp();
+		// ---- exact fp64 AABB::overlap of every (pose, list entry), 32 at a time -----------------------------------------
+		int ncand = 0;
+		for (unsigned t0 = 0; t0 < total; t0 += 32u) {
+			const unsigned t = t0 + (unsigned)lane;
+			bool ov = false;
+			unsigned sl = 0, eobj = 0;
+			if (t < total) {
+				// slot = the last one whose first flat index is <= t
+#pragma unroll
+				for (unsigned s = 16u; s > 0u; s >>= 1)
+					if (excl[sl + s] <= t) sl += s;
+				const GridEntry *ge = p.grid_entries + (first[sl] + (t - excl[sl]));
+				double e[8];
+				asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e[0]), "=d"(e[1]), "=d"(e[2]), "=d"(e[3]) : "l"(ge));
+				asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(e[4]), "=d"(e[5]), "=d"(e[6]), "=d"(e[7]) : "l"(reinterpret_cast<const double *>(ge) + 4));
+				eobj = (unsigned)__double_as_longlong(e[6]);
+				const bool out = (e[0] > wm.box[3 * 32 + sl]) | (e[1] > wm.box[4 * 32 + sl]) | (e[2] > wm.box[5 * 32 + sl]) |
+				                 (e[3] < wm.box[0 * 32 + sl]) | (e[4] < wm.box[1 * 32 + sl]) | (e[5] < wm.box[2 * 32 + sl]);
+				ov = !out;
+			}
+			const unsigned om = __ballot_sync(FULL, ov);
+			if (ov) wm.cand_ids[ncand + __popc(om & lt)] = (sl << 26) | eobj;
+			ncand += __popc(om);
+			if (ncand > kCandCap - 32) {
+				__syncwarp();
+				flush_candidates<NP2>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane);
+				n_cand_total += (unsigned)ncand;
+				ncand = 0;
+				__syncwarp();
+			}
+		}
+		__syncwarp();
+		if (ncand > 0) {
+			flush_candidates<NP2>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane);
+			n_cand_total += (unsigned)ncand;
+		}
+		__syncwarp();
 	}
 	if (COUNT && lane == 0 && n_cand_total) atomicAdd(p.counters + CTR_CAND, n_cand_total);
 }
@@ -307,6 +436,13 @@ int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads
 
 int launch_broadphase(const KernelParams &p, int sm_count, bool count, bool np2, void *stream) {
 	const size_t smem = (size_t)kBpWarpsPerCta * bp_warp_smem_bytes();
+	if (p.grid_cells != nullptr) {
+		if (np2)
+			return count ? launch_persistent(broadphase_grid_kernel<true, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
+			             : launch_persistent(broadphase_grid_kernel<false, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
+		return count ? launch_persistent(broadphase_grid_kernel<true, false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
+		             : launch_persistent(broadphase_grid_kernel<false, false>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
+	}
 	if (np2)
 		return count ? launch_persistent(broadphase_kernel<true, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
 		             : launch_persistent(broadphase_kernel<false, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
