@@ -561,11 +561,14 @@ def run_ours(args):
         alg_bytes_per_pose = in_bytes + 0.125 + 64.0 * bv + 72.0 * lf
         alg_flops_per_pose = 330.0 * bv + 800.0 * lf
         step_ms = dev_ms / args.steps
-        np2 = "np2=1" in os.environ.get("MPTCC_OPTS", "")
+        opts_env = os.environ.get("MPTCC_OPTS", "") + "," + os.environ.get("MPTCC_OPTIONS", "")
+        np2 = "np2=1" in opts_env
+        np1 = "np3=0" in opts_env and not np2
         if phase_ms is not None:
             # dominant kernel = the narrowphase kernel: it does the OBB and triangle tests (64 n_bv + 72 n_leaf); the
             # pose records are read by the broadphase kernel
-            kernel_name = "narrowphase2_kernel<false, 128, false>" if np2 else "narrowphase_kernel<false, 128>"
+            kernel_name = ("narrowphase2_kernel<false, 128, false>" if np2 else "narrowphase_kernel<false, 128>" if np1
+                           else "narrowphase3_kernel<false, false, true>")
             kernel_ms = float(phase_ms[1])
             kernel_alg = 64.0 * bv + 72.0 * lf
         else:
@@ -599,10 +602,11 @@ def run_ours(args):
         latency = max(fracs.values()) < 0.5
         line["roofline"] = {"bound": "hbm",
                             "bound_measured": "latency" if latency else top,
-                            "bound_note": ("the contract's HBM roofline is reported in `frac`; of the three measured rooflines the largest "
-                                           "fraction is %s and all are below 0.5: the kernel is latency-bound at 16 warps/SM "
-                                           "(sm__warps_active 23 %%, a third of the stall samples on the first use of a gathered node; "
-                                           "profiles/r2_*)" % top) if latency else None,
+                            "bound_note": ("the contract's HBM roofline is reported in `frac` (algorithmic bytes = FCL-order tests x "
+                                           "64-byte fp32 nodes; the kernel itself gathers 32-byte quantised nodes, mostly from L1/L2: "
+                                           "DRAM traffic is `traffic`); ncu: 16 warps/SM (128 registers), issue slots 56 %% busy, "
+                                           "L1 data pipe 43 %%, stalls spread over dependency waits, node gathers and the fp32 pipe "
+                                           "(profiles/r2_narrowphase3_*)"),
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "hbm_frac": fracs["hbm"], "l2_frac": fracs.get("l2"), "fp32_frac": fracs.get("fp32"),
                             "l2_gather_frac": achieved / pk["gather64_l2_gbs"] if pk.get("gather64_l2_gbs") else None,

@@ -1340,6 +1340,8 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		if (len == 0) continue;
 		const uint64_t pieces = (len + sub_words - 1) / sub_words;
 		const uint64_t per = (len + pieces - 1) / pieces;
+		// (ramping the first pieces up was measured again with the round-2 kernels: 2.095 against 2.109 ms blocking, but
+		// 2.0 against 1.7 ms with two calls in flight)
 		for (uint64_t w = b; w < e; w += per) jobs[di].push_back(Job{di, w, std::min(e, w + per)});
 		max_jobs = std::max(max_jobs, jobs[di].size());
 		ctx->devs[di].last_ms = 0.f;

@@ -81,7 +81,10 @@ __device__ __forceinline__ bool pose_settled(const uint32_t *hits, uint32_t pose
 #ifdef MPTCC_NP3_MAXREG
 #define NP3_BOUNDS __maxnreg__(MPTCC_NP3_MAXREG)
 #else
-#define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, 1)
+#ifndef MPTCC_NP3_CTAS
+#define MPTCC_NP3_CTAS 1
+#endif
+#define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, MPTCC_NP3_CTAS)
 #endif
 
 template <bool COUNT, bool TOP, bool Q>
@@ -176,6 +179,8 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 	uint2 cur = make_uint2(0u, 0u);
 	bool has = false;
 	unsigned qhead = 0, qend = 0, hit_w = 0;
+	unsigned seen = 0;  // end of this warp's last reservation: how far the list had been handed out at that time
+	const unsigned n_warps_all = gridDim.x * (unsigned)kNp3Warps;
 	bool exhausted = false;
 	int lq = 0;
 
@@ -243,18 +248,27 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 		// ---- prefetch: every lane keeps kNp3Depth candidates in flight ---------------------------------------------
 		young = 0u;
 		if (im && !exhausted) {
-			unsigned need = __ballot_sync(FULL, pf < kNp3Depth);
+			// Guided self-scheduling: list indices are reserved in chunks that shrink as the list drains (a quarter of an
+			// even share of what was left at this warp's last reservation, 8..kNp3Chunk), and near the end a lane keeps one
+			// candidate in flight instead of two -- short launches (the 2^18-pose pieces of the host-buffer path give a
+			// warp ~150 candidates) would otherwise end with a few warps holding the last hundreds of candidates.
+			const unsigned left = total > seen ? total - seen : 0u;
+			const unsigned depth = left > n_warps_all * 64u ? kNp3Depth : 1u;
+			unsigned need = __ballot_sync(FULL, pf < depth);
 			while (need) {
 				if (qhead == qend) {
+					unsigned want = left / (4u * n_warps_all);
+					want = want < 8u ? 8u : (want > kNp3Chunk ? kNp3Chunk : want);
 					unsigned first = 0;
-					if (lane == 0) first = atomicAdd(p.work_counter2, kNp3Chunk);
+					if (lane == 0) first = atomicAdd(p.work_counter2, want);
 					first = __shfl_sync(FULL, first, 0);
+					seen = first + want;
 					if (first >= total) {
 						exhausted = true;
 						break;
 					}
 					qhead = first;
-					qend = total - first < kNp3Chunk ? total : first + kNp3Chunk;
+					qend = total - first < want ? total : first + want;
 				}
 				const unsigned avail = qend - qhead;
 				const unsigned rank = (unsigned)__popc(need & lt);
@@ -274,7 +288,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				}
 				const unsigned nneed = (unsigned)__popc(need);
 				qhead += nneed < avail ? nneed : avail;
-				need = __ballot_sync(FULL, pf < kNp3Depth);
+				need = __ballot_sync(FULL, pf < depth);
 			}
 		}
 		cp_async_commit();
@@ -577,7 +591,7 @@ unsigned np3_agent_top_max();
 
 // Agent nodes the kernel can stage beside its per-warp state (whole sibling pairs: an odd count).
 unsigned np3_agent_top_max() {
-	const unsigned budget = 227u * 1024u - kNp3TopOffset - (unsigned)kNp3Warps * kNp3WarpBytes - 256u;
+	const unsigned budget = (227u * 1024u) / MPTCC_NP3_CTAS - 1024u * (MPTCC_NP3_CTAS - 1) - kNp3TopOffset - (unsigned)kNp3Warps * kNp3WarpBytes - 256u;
 	unsigned n = budget / 64u;
 	if (n % 2u == 0u) --n;
 	return n;

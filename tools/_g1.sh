@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$GRAFT_REPO_ROOT
-( timeout 300 python tools/ab_np.py ; timeout 300 python tools/ab_np.py grid=0 ) > gpurun_out/ab9.txt 2>&1
-cat gpurun_out/ab9.txt
-timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.txt 2>&1; tail -3 gpurun_out/gpu_tests.txt
+V=motionplanningtoolkit_b200/variants
+( for v in c2 c4; do MPTCC_LIB=$V/libmptcc_$v.so timeout 300 python tools/ab_np.py;  MPTCC_LIB=$V/libmptcc_$v.so timeout 300 python tools/ab_np.py 262144; done ) > gpurun_out/ab11.txt 2>&1; cat gpurun_out/ab11.txt
+( timeout 600 python tools/perf_e2e.py ramp=0; for v in c2 c4; do MPTCC_LIB=$V/libmptcc_$v.so timeout 600 python tools/perf_e2e.py ramp=0; done ) > gpurun_out/e2e3.txt 2>&1; cat gpurun_out/e2e3.txt
