@@ -62,6 +62,7 @@ static int wtest(const orc_model *m1, const orc_model *m2, const wcand *c, int b
 
 typedef struct {
 	int mode, batch, leaf_thresh, n_warps, pause_on_leaf, steal_in_stream;
+	int cta_warps; /* > 1: once the list is exhausted, idle lanes also take pending plans from the other warps of their CTA */
 	uint64_t rounds, steps_node, steps_leaf, tests, leaf_tests, active_lanes, stolen, same_s, lane_steps;
 } wsim_cfg;
 
@@ -163,14 +164,49 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					++d;
 				}
 			}
+			if (cfg->cta_warps > 1 && cfg->mode == 1 && next >= nc) {
+				const int c0 = w / cfg->cta_warps * cfg->cta_warps;
+				for (int l = 0; l < 32; ++l) {
+					wlane *L = &ww->lane[l];
+					if (L->has || L->paused) continue;
+					int found = 0;
+					for (int w2 = c0; w2 < c0 + cfg->cta_warps && w2 < cfg->n_warps && !found; ++w2) {
+						if (w2 == w || W[w2].done) continue;
+						for (int d2 = 0; d2 < 32; ++d2) {
+							wlane *D = &W[w2].lane[d2];
+							if (D->has && D->top > 0) {
+								L->cur = D->stk[--D->top];
+								L->cand = D->cand;
+								L->last_s = -1;
+								L->has = 1;
+								L->top = 0;
+								ww->stolen++;
+								found = 1;
+								break;
+							}
+						}
+					}
+				}
+			}
 			int n_act = 0;
 			for (int l = 0; l < 32; ++l) n_act += ww->lane[l].has;
 			if (n_act == 0 && ww->nlq == 0) {
 				int anyp = 0;
 				for (int l = 0; l < 32; ++l) anyp |= ww->lane[l].paused;
 				if (cfg->mode == 1 && next >= nc && !anyp) {
-					ww->done = 1;
-					--alive;
+					int others = 0;
+					if (cfg->cta_warps > 1) {
+						const int c0 = w / cfg->cta_warps * cfg->cta_warps;
+						for (int w2 = c0; w2 < c0 + cfg->cta_warps && w2 < cfg->n_warps; ++w2) {
+							if (w2 == w || W[w2].done) continue;
+							for (int d2 = 0; d2 < 32; ++d2) others |= W[w2].lane[d2].has || W[w2].lane[d2].top > 0;
+							others |= W[w2].nlq > 0;
+						}
+					}
+					if (!others) {
+						ww->done = 1;
+						--alive;
+					}
 				}
 				if (!anyp) continue;
 			}
