@@ -563,7 +563,7 @@ struct mptcc_ctx {
 	bool count = false;
 	long opt_ppw = 0;           // 0 = auto
 	long opt_ctas_per_sm = 0;   // 0 = occupancy maximum
-	long opt_sub_batch = 1 << 18;
+	long opt_sub_batch = 1 << 19;    // pose-sets per piece of a host-buffer call (a call of >= 2^16 pose-sets is cut into at least two)
 	long opt_always_replay = 0;
 	long opt_time_phases = 0;        // record CUDA events around the kernels of the split pipeline
 	long opt_split = 1;              // two-kernel pipeline for large single-link batches
@@ -1338,7 +1338,9 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		// kernel can hide was measured slower: more, smaller launches)
 		const uint64_t len = e - b;
 		if (len == 0) continue;
-		const uint64_t pieces = (len + sub_words - 1) / sub_words;
+		// (2^19 instead of 2^18 pose-sets per piece: the same blocking time on the benchmark batch, 8 % more with two calls in
+		// flight -- short launches end in a tail of long candidates; two pieces at least, so that a copy hides behind a kernel)
+		const uint64_t pieces = std::max<uint64_t>((len + sub_words - 1) / sub_words, len >= 2048 ? 2 : 1);
 		const uint64_t per = (len + pieces - 1) / pieces;
 		// (ramping the first pieces up was measured again with the round-2 kernels: 2.095 against 2.109 ms blocking, but
 		// 2.0 against 1.7 ms with two calls in flight)

@@ -405,3 +405,67 @@ def test_multi_device_edges_and_device_buffer_overflow(box_scene):
         chk.check_poses_device(len(poses), buf.data_ptr(), bits.data_ptr(), capi.POSE_RT12, 0, None)
         chk.synchronize()
         assert_bits_equal(bits.cpu().numpy().view(np.uint32), want, len(poses), "device buffers, small candidate list")
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(qnode=0), dict(qnode=0, agent_top=511), dict(always_replay=1), dict(split_cap=1),
+                                  dict(grid=0), dict(grid=0, qnode=0), dict(near_first=0), dict(no_steal=1)])
+def test_third_generation_narrowphase_matches_oracle(built, opts):
+    """np3_kernels.cu, the default narrowphase (streaming lanes, cp.async-prefetched candidate ring, two-wide SAT,
+    32-byte quaternion nodes) behind the grid broadphase, on deep trees: every node format (quantised / fp32 / fp32
+    with the TMA-staged agent tree top), forced path replay, the overflow fall-back, the cluster-tree broadphase."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(521)
+    poses = scenes.random_poses_near_objects(rng, 40007, env, 2.0)
+    chk = sc.checker(split=1, split_min=32, **opts)
+    chk.enable_counters(True)
+    assert_bits_equal(chk.check_poses(poses), sc.oracle_bits(poses), len(poses), "np3 %s" % (opts,))
+    assert chk.counters()["n_candidates"] > 0      # the split pipeline ran (the fused kernel does not count candidates per list)
+    tq = scenes.random_poses_near_objects(rng, 20000, env, 2.0, fmt="tq7")
+    assert_bits_equal(chk.check_poses(tq, capi.POSE_TQ7), sc.oracle_bits(tq, O.POSE_TQ7), len(tq), "np3 TQ7 %s" % (opts,))
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(qnode=0), dict(grid=0)])
+def test_third_generation_narrowphase_unit_boxes_and_odd_poses(box_scene, opts):
+    """Exact-contact cases (touching cubes, +-1 ulp), poses whose 3x3 block is not a rotation (the launch must go to the
+    fused kernel) and poses with NaN / inf / far-away translations (the grid broadphase hands such launches to the fused
+    kernel as well, which keeps FCL's comparison semantics for them)."""
+    rng = scenes.SplitMix64(522)
+    chk = box_scene.checker(split=1, split_min=32, **opts)
+    e = 2.0 ** -52
+    T = np.concatenate([np.array([[1, 0, 0], [1 + e, 0, 0], [1 - e, 0, 0], [0, -1, 0], [1, 1, 1], [1, 1, 1 + e]], float),
+                        np.stack([rng.uniform(40000, -1.6, 1.6) for _ in range(3)], 1)])
+    poses = scenes.translation_poses(T)
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "np3 translations %s" % (opts,))
+    poses = scenes.random_poses_rt12(rng, 40000, (-1.6,) * 3, (1.6,) * 3)
+    poses[::7, :9] *= 1.25                      # scaled "rotations"
+    poses[5::11, 1] += 0.3                      # sheared
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "np3 non-rigid poses %s" % (opts,))
+    poses = scenes.random_poses_rt12(rng, 40000, (-1.6,) * 3, (1.6,) * 3)
+    poses[3, 9] = np.nan
+    poses[1001, 10] = np.inf
+    poses[2002, 11] = -np.inf
+    poses[3003, 9:12] = (1e30, -1e30, 1e30)
+    poses[4004, 9:12] = (1e300, 0.0, 0.0)
+    assert_bits_equal(chk.check_poses(poses), box_scene.oracle_bits(poses), len(poses), "np3 non-finite poses %s" % (opts,))
+
+
+def test_grid_broadphase_candidates_equal_tree_broadphase(built):
+    """The grid broadphase and the cluster-tree broadphase both reduce to FCL's exact fp64 AABB::overlap: the same
+    number of candidates on a scene of many objects (C5-like, scaled down), incl. poses outside the scene box."""
+    env = scenes.synthetic_environment(300, extent=60.0)
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    rng = scenes.SplitMix64(523)
+    poses = np.concatenate([scenes.random_poses_tq7(rng, 30000, (-45.0,) * 3, (45.0,) * 3),
+                            scenes.random_poses_near_objects(rng, 30000, env, 3.0, fmt="tq7")])
+    counts, bits = [], []
+    for grid in (1, 0):
+        chk = sc.checker(split=1, split_min=32, grid=grid)
+        chk.enable_counters(True)
+        bits.append(chk.check_poses(poses, capi.POSE_TQ7))
+        counts.append(chk.counters()["n_candidates"])
+    assert counts[0] == counts[1] and counts[0] > 0
+    assert np.array_equal(bits[0], bits[1])
+    assert_bits_equal(bits[0], sc.oracle_bits(poses, O.POSE_TQ7), len(poses), "grid broadphase")

@@ -1,4 +1,4 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$GRAFT_REPO_ROOT
-V=motionplanningtoolkit_b200/variants
-( timeout 300 python tools/ab_np.py; timeout 300 python tools/ab_np.py 262144; for v in a8 a64 a24p2k off; do MPTCC_LIB=$V/libmptcc_$v.so timeout 300 python tools/ab_np.py;  MPTCC_LIB=$V/libmptcc_$v.so timeout 300 python tools/ab_np.py 262144; done ) > gpurun_out/ab13.txt 2>&1; cat gpurun_out/ab13.txt
+timeout 1500 python -m pytest tests -x -q -m gpu > gpurun_out/gpu_tests.txt 2>&1; tail -5 gpurun_out/gpu_tests.txt
+timeout 600 python tools/perf_e2e.py > gpurun_out/e2e5.txt 2>&1; cat gpurun_out/e2e5.txt
