@@ -316,7 +316,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 						const float4 *src = NP3_SLOT(from, frd);
 						float4 *to = NP3_SLOT(lane, rd);
 #pragma unroll
-						for (int k = 0; k < 4; ++k) to[k] = src[k];
+						for (int k = 0; k < 5; ++k) to[k] = src[k];  // (the record and node_base, tri_base, pose-set, list index)
 						nb1 = fnb1;
 						ci = fci;
 						pose = fpose;
@@ -341,29 +341,29 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			lq -= k;
 			int verdict = TRI_SEPARATED;
 			bool certified = false;
-			uint4 e = make_uint4(0u, 0u, 0u, 0xfffffffeu);
-			uint2 base = make_uint2(0u, 0u);
+			uint4 e = make_uint4(0u, 0u, 0u, 0xfffffffeu);  // (environment triangle in the pack, agent triangle, list index, pose-set)
+			float mu = 0.f, cert = 0.f;
 			if (lane < k) {
 				e = leafq[lq + lane];
 				if (!pose_settled(hits, e.w)) {
+					// every load of the phase is issued before the first use: one memory round trip, not three
 					const float4 *rp = p.cand_rec + 4ull * e.z;
 					const F8 ra = ldg256(rp), rb = ldg256(rp + 2);
+					const float4 *t1 = p.env.tri32 + 3ull * e.x;
+					const float4 *t2 = tris2 + 3ull * e.y;
+					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
+					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
+					// path certificate: the smaller mu_chain of the two triangles against the candidate's
+					// threshold from the broadphase kernel
+					mu = fminf(__ldg(p.env.mu_chain + e.x), __ldg(p.agent.mu_chain + m2.tri_base + e.y));
+					cert = __ldg(p.cand_cert + e.z);
 					RelF x;
 					x.R[0] = ra.a.x; x.R[1] = ra.a.y; x.R[2] = ra.a.z; x.R[3] = ra.a.w;
 					x.R[4] = ra.b.x; x.R[5] = ra.b.y; x.R[6] = ra.b.z; x.R[7] = ra.b.w;
 					x.R[8] = rb.a.x; x.T[0] = rb.a.y; x.T[1] = rb.a.z; x.T[2] = rb.a.w;
 					x.S = rb.b.w;
-					base = p.cand_base[e.z];
-					const float4 *t1 = p.env.tri32 + 3ull * (base.y + e.x);
-					const float4 *t2 = tris2 + 3ull * e.y;
-					const float4 P1 = __ldg(t1), P2 = __ldg(t1 + 1), P3 = __ldg(t1 + 2);
-					const float4 Q1 = __ldg(t2), Q2 = __ldg(t2 + 1), Q3 = __ldg(t2 + 2);
 					verdict = tri_filter_f32(P1, P2, P3, Q1, Q2, Q3, x);
-					if (verdict == TRI_INTERSECT && !p.always_replay) {
-						// path certificate against the candidate's threshold from the broadphase kernel
-						const float mu = fminf(p.env.mu_chain[base.y + e.x], p.agent.mu_chain[m2.tri_base + e.y]);
-						certified = mu >= p.cand_cert[e.z];
-					}
+					certified = verdict == TRI_INTERSECT && !p.always_replay && mu >= cert;
 				}
 			}
 			if (COUNT) ctr[CTR_LEAF] += (unsigned)k;
@@ -379,7 +379,6 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					um &= um - 1;
 					const uint32_t c = __shfl_sync(FULL, e.z, from), ps = __shfl_sync(FULL, e.w, from);
 					const uint32_t t1 = __shfl_sync(FULL, e.x, from), t2 = __shfl_sync(FULL, e.y, from);
-					const uint32_t tb = __shfl_sync(FULL, base.y, from);
 					// settled by an earlier pair of this round?  (warp-uniform)
 					unsigned same = __ballot_sync(FULL, ((hm >> lane) & 1u) && e.w == ps);
 					if (same) {
@@ -387,14 +386,13 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 						continue;
 					}
 					if (COUNT) ctr[CTR_EXACT] += 1;
-					const bool hit = exact_tri_intersect_warp(p.cand_rel + 12ull * c, p.env.tri64 + 9ull * (tb + t1),
+					const bool hit = exact_tri_intersect_warp(p.cand_rel + 12ull * c, p.env.tri64 + 9ull * t1,
 					                                          p.agent.tri64 + 9ull * (m2.tri_base + t2), lane);
 					if (lane == from) verdict = hit ? TRI_INTERSECT : TRI_SEPARATED;
 					if (hit) {  // certificate with the record's magnitudes; uncertified contacts go to exact_kernel (path replay)
 						bool cert2 = false;
 						if (lane == from && !p.always_replay) {
-							const float mu = fminf(p.env.mu_chain[tb + t1], p.agent.mu_chain[m2.tri_base + t2]);
-							if (mu >= p.cand_cert[c]) {
+							if (mu >= cert) {
 								atomicOr(p.verdict_bits + (ps >> 5), 1u << (ps & 31u));
 								verdict = TRI_SEPARATED;  // settled
 								cert2 = true;
@@ -416,7 +414,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				if (defer) {
 					const unsigned at = qb + __popc(dmk & lt);
 					if (at < p.xq_cap)
-						p.xq[at] = make_uint4(e.z, e.x, e.y, verdict == TRI_INTERSECT ? 1u : 0u);
+						p.xq[at] = make_uint4(e.z, e.x - p.cand_base[e.z].y, e.y, verdict == TRI_INTERSECT ? 1u : 0u);  // (exact_kernel counts triangles per model)
 					else
 						atomicOr(p.overflow, 1u);  // the fused fall-back recomputes the launch
 				}
@@ -568,13 +566,16 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
 			ctr[CTR_BV] += t;
 		}
+		// (queue entries carry the triangle's index in the environment pack: tri_base of the candidate's model is word 17
+		// of its record slot)
+		const unsigned tb = (leaf0 || leaf1) ? __float_as_uint(NP3_SLOT(lane, rd)[4].y) : 0u;
 		{
 			const unsigned lm0 = __ballot_sync(FULL, leaf0);
-			if (leaf0) leafq[lq + __popc(lm0 & lt)] = make_uint4(lf0.x, lf0.y, ci, pose);
+			if (leaf0) leafq[lq + __popc(lm0 & lt)] = make_uint4(tb + lf0.x, lf0.y, ci, pose);
 			lq += __popc(lm0);
 		}
 		const unsigned lm = __ballot_sync(FULL, leaf1);
-		if (leaf1) leafq[lq + __popc(lm & lt)] = make_uint4(lf1.x, lf1.y, ci, pose);
+		if (leaf1) leafq[lq + __popc(lm & lt)] = make_uint4(tb + lf1.x, lf1.y, ci, pose);
 		lq += __popc(lm);
 		__syncwarp();
 	}

@@ -29,6 +29,7 @@ typedef struct {
 	int has;
 	int cand; /* candidate of everything this lane holds */
 	int paused;
+	int age;    /* node steps on the current candidate */
 	int last_s; /* stationary node of the lane's previous step: kind * 2^24 + id, -1 = none */
 } wlane;
 
@@ -62,6 +63,8 @@ static int wtest(const orc_model *m1, const orc_model *m2, const wcand *c, int b
 
 typedef struct {
 	int mode, batch, leaf_thresh, n_warps, pause_on_leaf, steal_in_stream;
+	int steal_age; /* > 0: an idle lane first takes the top pending plan of a lane that has spent >= steal_age steps on its
+	                  candidate, and only otherwise the next candidate of the list */
 	int cta_warps; /* > 1: once the list is exhausted, idle lanes also take pending plans from the other warps of their CTA */
 	uint64_t rounds, steps_node, steps_leaf, tests, leaf_tests, active_lanes, stolen, same_s, lane_steps;
 } wsim_cfg;
@@ -136,11 +139,32 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 					}
 				}
 			} else {
+				if (cfg->steal_age > 0) {
+					for (int l = 0; l < 32; ++l) {
+						wlane *L = &ww->lane[l];
+						if (L->has || L->paused) continue;
+						int best = -1;
+						for (int d2 = 0; d2 < 32; ++d2) {
+							wlane *D = &ww->lane[d2];
+							if (D->has && D->top > 0 && D->age >= cfg->steal_age && (best < 0 || D->age > ww->lane[best].age)) best = d2;
+						}
+						if (best < 0) break;
+						wlane *D = &ww->lane[best];
+						L->cur = D->stk[--D->top];
+						L->cand = D->cand;
+						L->age = D->age;
+						L->last_s = -1;
+						L->has = 1;
+						L->top = 0;
+						ww->stolen++;
+					}
+				}
 				for (int l = 0; l < 32; ++l) {
 					wlane *L = &ww->lane[l];
 					if (!L->has && !L->paused && next < nc) {
 						L->cand = (int)next++;
 						L->last_s = -1;
+						L->age = 0;
 						L->cur = (wplan){0, 0, 0};
 						L->has = 1;
 						L->top = 0;
@@ -245,6 +269,7 @@ int wsim_run(const orc_env *env, const orc_model *link, uint64_t n, const double
 				wlane *L = &ww->lane[l];
 				if (!L->has) continue;
 				L->has = 0;
+				L->age++;
 				const wplan pl = L->cur;
 				const wcand *c = &cl[L->cand];
 				if (dead[c->pose]) {
