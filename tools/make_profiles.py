@@ -21,7 +21,9 @@ KEEP = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__shared_mem_per_block_dynamic',
         'launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'sass__inst_executed_local_loads',
-        'sass__inst_executed_local_stores', 'sm__cycles_elapsed.avg.per_second']
+        'sass__inst_executed_local_stores', 'sm__cycles_elapsed.avg.per_second',
+        'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld_lookup_hit.sum',
+        'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum']
 
 
 def launches():
@@ -76,9 +78,13 @@ def kernel(rep, name, cubin):
 
 
 launches()
-t = kernel("prof_%s_narrowphase.ncu-rep" % tag, "narrowphase_kernel", "split_kernels")
-kernel("prof_%s_broadphase.ncu-rep" % tag, "broadphase_kernel", "split_kernels")
-json.dump({"dram_bytes_per_launch": t, "kernel": "narrowphase_kernel<false, 128>",
-           "source": "profiles/%s_narrowphase_kernel_metrics.txt (ncu --set full, one launch on the C5 batch)" % tag},
+# round 1 / first half of round 2: narrowphase_kernel + broadphase_kernel; from "r2f" on the defaults are
+# narrowphase3_kernel (np3_kernels.cu) and broadphase_grid_kernel (split_kernels.cu)
+NP, NPCUBIN, BP = (("narrowphase3_kernel", "np3_kernels", "broadphase_grid_kernel") if tag >= "r2f"
+                   else ("narrowphase_kernel", "split_kernels", "broadphase_kernel"))
+t = kernel("prof_%s_narrowphase.ncu-rep" % tag, NP, NPCUBIN)
+kernel("prof_%s_broadphase.ncu-rep" % tag, BP, "split_kernels")
+json.dump({"dram_bytes_per_launch": t, "kernel": NP,
+           "source": "profiles/%s_%s_metrics.txt (ncu --set full, one launch on the C5 batch)" % (tag, NP)},
           open(os.path.join(P, "traffic.json"), "w"))
 print("traffic", t)
