@@ -156,7 +156,7 @@ int mptcc_reset_counters(mptcc_ctx *ctx);
 int mptcc_last_kernel_ms(mptcc_ctx *ctx, int slot, float *ms);
 /* With option "time_phases" = 1: device milliseconds of the four kernels of the last split-pipeline launch
  * on `slot` (CUDA events on the launching stream): ms4 = {broadphase, narrowphase, exact pass, overflow fall-back}
- * (the round-1 narrowphase, option "np2" = 0, has no separate exact pass: ms4[2] is then ~0). */
+ * (the round-1 narrowphase, options "np3" = 0 and "np2" = 0, has no separate exact pass: ms4[2] is then ~0). */
 int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4);
 /* Behaviour: "self_collision" (0/1, default 0) = the checkSelfCollision argument of
  * MeshHandler::isInCollision (/root/reference/utilities/meshhandler.hpp:187-219): every later check also
@@ -164,8 +164,12 @@ int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4);
  * narrowphase) and reports self-collision OR environment collision.
  * Tuning knobs: "poses_per_warp" (0 = auto, power of two <= 64), "ctas_per_sm", "sub_batch", "split" (0/1),
  * "split_min", "split_cap", "long_batches" (-1 = by launch size), "always_replay", "time_phases", "near_first",
- * "no_steal", "steal_bottom", "np2" (0 = round-1 narrowphase kernel), "agent_top" (agent tree nodes staged in
- * shared memory, -1 = auto). */
+ * "no_steal", "steal_bottom"; kernel selection of the split pipeline (large single-link batches): "grid" (1 = grid
+ * broadphase, the default; 0 = cluster-tree walk), "np3" (1 = streaming narrowphase, the default; 0 = the round-1
+ * kernel), "np2" (1 = second-generation narrowphase; selects it instead of np3), "qnode" (1 = 32-byte quantised
+ * traversal nodes, the default; 0 = 64-byte fp32 nodes), "agent_top" (fp32 nodes only: agent tree nodes staged in
+ * shared memory by TMA; np3: 0 / -1 = none, np2: -1 = as many as fit).  Every combination gives the same verdicts.
+ * The environment variable MPTCC_OPTIONS="name=value,..." applies options to every new context. */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */
