@@ -78,12 +78,12 @@ __device__ __forceinline__ bool pose_settled(const uint32_t *hits, uint32_t pose
 	return a.x == pose || a.y == pose || a.z == pose || a.w == pose || b.x == pose || b.y == pose || b.z == pose || b.w == pose;
 }
 
-#ifdef MPTCC_NP3_MAXREG
-#define NP3_BOUNDS __maxnreg__(MPTCC_NP3_MAXREG)
-#else
 #ifndef MPTCC_NP3_CTAS
 #define MPTCC_NP3_CTAS 1
 #endif
+#ifdef MPTCC_NP3_MAXREG
+#define NP3_BOUNDS __maxnreg__(MPTCC_NP3_MAXREG)
+#else
 #define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, MPTCC_NP3_CTAS)
 #endif
 
