@@ -171,6 +171,11 @@ int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4);
  * shared memory by TMA; np3: 0 / -1 = none, np2: -1 = as many as fit).  Every combination gives the same verdicts.
  * The environment variable MPTCC_OPTIONS="name=value,..." applies options to every new context. */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
+/* What the current scene and options resolve to (tests and tools): "qnode_active" (1: the split pipeline traverses the
+ * 32-byte quantised nodes; 0: a pack could not be quantised -- an extent above 65 000, a model beyond 2^22 triangles --
+ * or the option is off), "grid_cells" / "grid_entries" (size of the broadphase grid; 0: the cluster tree is walked),
+ * "agent_nodes", "env_nodes". */
+int mptcc_get_info(mptcc_ctx *ctx, const char *name, long *value);
 
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */
 typedef struct mptcc_bvh mptcc_bvh;

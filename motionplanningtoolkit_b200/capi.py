@@ -28,7 +28,7 @@ EXPORTS = [
     "mptcc_create", "mptcc_destroy", "mptcc_last_error", "mptcc_num_devices", "mptcc_set_environment",
     "mptcc_set_agent", "mptcc_check_poses", "mptcc_submit_poses", "mptcc_wait", "mptcc_check_segments", "mptcc_check_omni_edges", "mptcc_check_poses_device",
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
-    "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option",
+    "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option", "mptcc_get_info",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
     "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb",
 ]
@@ -104,6 +104,8 @@ def load():
     L.mptcc_last_kernel_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
     L.mptcc_last_phase_ms.restype = C.c_int
     L.mptcc_last_phase_ms.argtypes = [vp, C.c_int, C.POINTER(C.c_float)]
+    L.mptcc_get_info.restype = C.c_int
+    L.mptcc_get_info.argtypes = [vp, C.c_char_p, C.POINTER(C.c_long)]
     L.mptcc_set_option.restype = C.c_int
     L.mptcc_set_option.argtypes = [vp, C.c_char_p, C.c_long]
     L.mptcc_bvh_build.restype = C.c_int
@@ -291,6 +293,11 @@ class Checker:
         ms = (C.c_float * 4)()
         self._check(self.lib.mptcc_last_phase_ms(self.h, slot, ms))
         return tuple(ms)
+
+    def info(self, name):
+        v = C.c_long(0)
+        self._check(self.lib.mptcc_get_info(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
 
     def set_option(self, name, value):
         self._check(self.lib.mptcc_set_option(self.h, name.encode(), int(value)))

@@ -1584,6 +1584,18 @@ int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4) {
 	return MPTCC_OK;
 }
 
+int mptcc_get_info(mptcc_ctx *ctx, const char *name, long *value) {
+	if (!ctx || !name || !value) return MPTCC_ERR_INVALID;
+	const std::string k(name);
+	if (k == "qnode_active") *value = (ctx->opt_qnode && ctx->env_q_ok && ctx->env_h.q_ok && ctx->agent_h.q_ok) ? 1 : 0;
+	else if (k == "grid_cells") *value = ctx->opt_grid ? (long)ctx->grid_cells_h.size() : 0;
+	else if (k == "grid_entries") *value = ctx->opt_grid ? (long)ctx->grid_entries_h.size() : 0;
+	else if (k == "agent_nodes") *value = (long)(ctx->agent_h.node32.size() / 4);
+	else if (k == "env_nodes") *value = (long)(ctx->env_h.node32.size() / 4);
+	else return fail(ctx, MPTCC_ERR_INVALID, "unknown info: " + k);
+	return MPTCC_OK;
+}
+
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	if (!ctx || !name) return MPTCC_ERR_INVALID;
 	const std::string k(name);

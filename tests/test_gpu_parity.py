@@ -469,3 +469,33 @@ def test_grid_broadphase_candidates_equal_tree_broadphase(built):
     assert counts[0] == counts[1] and counts[0] > 0
     assert np.array_equal(bits[0], bits[1])
     assert_bits_equal(bits[0], sc.oracle_bits(poses, O.POSE_TQ7), len(poses), "grid broadphase")
+
+
+def test_quantised_nodes_and_grid_are_in_use_and_fall_back_when_they_do_not_apply(built):
+    """The fast structures are really what the default pipeline runs on the fixtures (quantised nodes, grid), and scenes
+    they cannot represent -- extents beyond binary16, coordinates beyond what the fp32 cell function resolves -- take the
+    fp32 nodes / the cluster tree and still give the oracle's verdicts."""
+    env = meshio.environment_submeshes(meshio.load_mptm("divider"))
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    sc = Scene(env, [agent])
+    chk = sc.checker(split=1, split_min=32)
+    assert chk.info("qnode_active") == 1 and chk.info("grid_cells") > 0 and chk.info("grid_entries") > 0
+    rng = scenes.SplitMix64(524)
+    # the same scene a hundred thousand times larger: extents up to ~1e6 (no binary16), coordinates ~1e6
+    k = 1.0e5
+    env_big = [(v * k, t) for v, t in env]
+    agent_big = (agent[0] * k, agent[1])
+    sb = Scene(env_big, [agent_big])
+    chkb = sb.checker(split=1, split_min=32)
+    assert chkb.info("qnode_active") == 0
+    poses = scenes.random_poses_near_objects(rng, 20011, env_big, 2.0 * k, fmt="tq7")
+    assert_bits_equal(chkb.check_poses(poses, capi.POSE_TQ7), sb.oracle_bits(poses, O.POSE_TQ7), len(poses), "scaled scene")
+    # a small agent far from the origin: a pose box is ~1 wide at coordinates ~1e7 (fp32 spacing 1): the grid must cope
+    far = np.array([1.0e7, -1.0e7, 1.0e7])
+    box = unit_box()
+    env_far = [(box[0] * 3.0 + far, box[1]), (box[0] * 3.0 + far + np.array([9.0, 0.0, 0.0]), box[1])]
+    sf = Scene(env_far, [box])
+    chkf = sf.checker(split=1, split_min=32)
+    T = far + np.stack([rng.uniform(30000, -8.0, 16.0), rng.uniform(30000, -8.0, 8.0), rng.uniform(30000, -8.0, 8.0)], 1)
+    poses = np.concatenate([T, scenes.random_quaternions(rng, len(T))], axis=1)
+    assert_bits_equal(chkf.check_poses(poses, capi.POSE_TQ7), sf.oracle_bits(poses, O.POSE_TQ7), len(poses), "far scene")
