@@ -579,6 +579,7 @@ struct mptcc_ctx {
 	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
 	long opt_qnode = 1;              // np2/np3 traverse the 32-byte quantised nodes (one 256-bit load per node); 0 = the 64-byte fp32 nodes
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
+	long opt_first_half = 1;         // a host-buffer call that finds the device idle cuts its first piece in two
 	long opt_grid = 1;               // grid broadphase for single-link agents (0 = always walk the cluster tree)
 	long opt_np3 = 1;                // third-generation narrowphase (np3_kernels.cu, streaming lanes): the default; 0 = the round-1 kernel
 	                                 // (split_kernels.cu), or np2_kernels.cu with np2 = 1
@@ -1319,6 +1320,7 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		rc = mptcc_wait(ctx, ctx->completed + 1);
 		if (rc != MPTCC_OK) return rc;
 	}
+	const bool idle_at_submit = ctx->submitted == ctx->completed;
 	const int tslot = (int)(ctx->submitted % kInFlight);
 	const size_t rec = pose_rec_len((unsigned)fmt) * ctx->link_model_h.size();  // doubles per pose-set
 	const uint64_t n_words = (n + 31) / 32;
@@ -1344,7 +1346,19 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		const uint64_t per = (len + pieces - 1) / pieces;
 		// (ramping the first pieces up was measured again with the round-2 kernels: 2.095 against 2.109 ms blocking, but
 		// 2.0 against 1.7 ms with two calls in flight)
-		for (uint64_t w = b; w < e; w += per) jobs[di].push_back(Job{di, w, std::min(e, w + per)});
+		uint64_t w = b;
+		if (ctx->opt_first_half && idle_at_submit && per >= 4096) {
+			// Nothing is in flight, so the copy of the first piece is the one no kernel hides: cut that piece in two
+			// (blocking call on the benchmark batch 2.13 -> 1.98 ms).  With an earlier submit still running the copy hides
+			// behind its kernels and the extra, shorter launch only costs (two calls in flight: 1.49 -> 1.83 ms), so the
+			// pieces stay whole then.
+			// (an eighth, an eighth and a quarter of the call first: 2.00 ms, no better)
+			const uint64_t h = per / 2;
+			jobs[di].push_back(Job{di, w, w + h});
+			jobs[di].push_back(Job{di, w + h, std::min(e, w + per)});
+			w += per;
+		}
+		for (; w < e; w += per) jobs[di].push_back(Job{di, w, std::min(e, w + per)});
 		max_jobs = std::max(max_jobs, jobs[di].size());
 		ctx->devs[di].last_ms = 0.f;
 	}
@@ -1613,6 +1627,8 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 			if (drc != MPTCC_OK) return drc;
 		}
 		ctx->opt_self_collision = value != 0;
+	} else if (k == "first_half") {
+		ctx->opt_first_half = value != 0;
 	} else if (k == "grid") {
 		ctx->opt_grid = value != 0;
 	} else if (k == "np3") {

@@ -1,3 +1,3 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$GRAFT_REPO_ROOT
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu > gpurun_out/np3_parity.txt 2>&1; tail -30 gpurun_out/np3_parity.txt
+timeout 600 python tools/perf_e2e.py first_half=2 first_half=1 > gpurun_out/e2e8.txt 2>&1; cat gpurun_out/e2e8.txt
