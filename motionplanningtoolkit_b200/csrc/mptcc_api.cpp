@@ -1347,11 +1347,12 @@ int mptcc_submit_poses(mptcc_ctx *ctx, uint64_t n, const double *poses, int fmt,
 		// (ramping the first pieces up was measured again with the round-2 kernels: 2.095 against 2.109 ms blocking, but
 		// 2.0 against 1.7 ms with two calls in flight)
 		uint64_t w = b;
-		if (ctx->opt_first_half && idle_at_submit && per >= 4096) {
+		if (ctx->opt_first_half && idle_at_submit && per * 32 * rec * sizeof(double) >= (24u << 20)) {
 			// Nothing is in flight, so the copy of the first piece is the one no kernel hides: cut that piece in two
 			// (blocking call on the benchmark batch 2.13 -> 1.98 ms).  With an earlier submit still running the copy hides
 			// behind its kernels and the extra, shorter launch only costs (two calls in flight: 1.49 -> 1.83 ms), so the
-			// pieces stay whole then.
+			// pieces stay whole then.  The extra launch costs ~0.08 ms, half a copy of 24 MB saves ~0.11 ms: smaller first
+			// pieces stay whole as well (C1-C3 of BASELINE.md lose 3-6 % otherwise).
 			// (an eighth, an eighth and a quarter of the call first: 2.00 ms, no better)
 			const uint64_t h = per / 2;
 			jobs[di].push_back(Job{di, w, w + h});
