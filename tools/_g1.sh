@@ -1,3 +1,4 @@
 cd $GRAFT_REPO_ROOT
 export PYTHONPATH=$GRAFT_REPO_ROOT
-timeout 600 python tools/perf_e2e.py first_half=2 first_half=1 > gpurun_out/e2e8.txt 2>&1; cat gpurun_out/e2e8.txt
+V=motionplanningtoolkit_b200/variants
+( timeout 300 python tools/ab_np.py; for v in s0 s4 s5 s8; do MPTCC_LIB=$V/libmptcc_$v.so timeout 300 python tools/ab_np.py; done; timeout 300 python tools/ab_np.py ) > gpurun_out/ab17.txt 2>&1; grep "^libmptcc\|Error" gpurun_out/ab17.txt
