@@ -518,47 +518,35 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			}
 			const int linkS = __float_as_int(S.v3.w);
 			const float sS = S.v3.x * S.v3.x + S.v3.y * S.v3.y + S.v3.z * S.v3.z;
-			uint2 plan0 = make_uint2(0u, 0u), plan1 = make_uint2(0u, 0u);
-			bool ok0 = false, ok1 = false;
-			float d2_0 = 0.f, d2_1 = 0.f;
 			float2 d2p;
 			const unsigned djm = pair_disjoint<Q>(f, C2, S.v3, d2p);
 			const float2 sC2 = MPTCC_FMA2(C2.e[2], C2.e[2], MPTCC_FMA2(C2.e[1], C2.e[1], MPTCC_MUL2(C2.e[0], C2.e[0])));
 			n_tests = single ? 1u : 2u;
+			// What the two tests lead to, in straight-line code for both children (as branches this block ran at 9-15
+			// active lanes and drew 13 % of the stall samples).  Child k overlaps S iff its bit of djm is clear; two leaves
+			// make a triangle pair (environment primitive, agent primitive; primitive = -(link + 1) = ~link); otherwise
+			// FCL's firstOverSecond -- descend the environment node iff the agent node is a leaf, or the environment node
+			// is not and is the larger one -- stated for "descend the child's tree again" (desc) against "now descend S".
 			const bool lS = linkS < 0;
-			const uint32_t same = env_side ? kPlan3Env : 0u, flip = env_side ? 0u : kPlan3Env;
-#pragma unroll
-			for (int k = 0; k < 2; ++k) {
-				if (k == 1 && single) break;
-				if ((djm >> k) & 1u) continue;
-				if (k == 0) d2_0 = d2p.x; else d2_1 = d2p.y;
-				const int linkC = k == 0 ? C2.link0 : C2.link1;
-				const float sC = k == 0 ? sC2.x : sC2.y;
-				const bool lC = linkC < 0;
-				if (lC && lS) {  // two leaves: (environment primitive, agent primitive); primitive = -(link + 1) = ~link
-					const uint32_t pC = ~(uint32_t)linkC, pS = ~(uint32_t)linkS;
-					const uint2 lf = env_side ? make_uint2(pC, pS) : make_uint2(pS, pC);
-					if (k == 0) { leaf0 = true; lf0 = lf; } else { leaf1 = true; lf1 = lf; }
-					continue;
-				}
-				// FCL's firstOverSecond (descend the environment node iff the agent node is a leaf, or the environment node is
-				// not and is the larger one), stated for "descend the child's tree again" (descX) against "now descend S":
-				const bool descX = !lC && (lS || (env_side ? sC > sS : !(sS > sC)));
-				const uint2 pl = descX ? make_uint2((uint32_t)linkC, yi | same) : make_uint2((uint32_t)linkS, (xi + (uint32_t)k) | flip);
-				if (k == 0) { ok0 = true; plan0 = pl; } else { ok1 = true; plan1 = pl; }
-			}
-			if (ok0 && ok1) {
-				const bool swap = p.near_first && d2_1 < d2_0;
-				cur = swap ? plan1 : plan0;
-				has = true;
-				NP3_PUSH(swap ? plan0 : plan1)
-			} else if (ok0) {
-				cur = plan0;
-				has = true;
-			} else if (ok1) {
-				cur = plan1;
-				has = true;
-			}
+			const uint32_t same = yi | (env_side ? kPlan3Env : 0u), flip = env_side ? 0u : kPlan3Env;
+			const bool hit0 = (djm & 1u) == 0u, hit1 = !single && (djm & 2u) == 0u;
+			const bool lC0 = C2.link0 < 0, lC1 = C2.link1 < 0;
+			const uint32_t pS = ~(uint32_t)linkS, pC0 = ~(uint32_t)C2.link0, pC1 = ~(uint32_t)C2.link1;
+			leaf0 = hit0 && lC0 && lS;
+			leaf1 = hit1 && lC1 && lS;
+			lf0 = make_uint2(env_side ? pC0 : pS, env_side ? pS : pC0);
+			lf1 = make_uint2(env_side ? pC1 : pS, env_side ? pS : pC1);
+			const bool ok0 = hit0 && !(lC0 && lS), ok1 = hit1 && !(lC1 && lS);
+			const bool desc0 = !lC0 && (lS || (env_side ? sC2.x > sS : !(sS > sC2.x)));
+			const bool desc1 = !lC1 && (lS || (env_side ? sC2.y > sS : !(sS > sC2.y)));
+			const uint2 plan0 = make_uint2(desc0 ? (uint32_t)C2.link0 : (uint32_t)linkS, desc0 ? same : (xi | flip));
+			const uint2 plan1 = make_uint2(desc1 ? (uint32_t)C2.link1 : (uint32_t)linkS, desc1 ? same : ((xi + 1u) | flip));
+			// both children overlap: the nearer one first, the other one is stacked
+			const bool both = ok0 && ok1;
+			const bool first1 = both ? (p.near_first && d2p.y < d2p.x) : ok1;
+			cur = first1 ? plan1 : plan0;
+			has = ok0 || ok1;
+			if (both) NP3_PUSH(first1 ? plan0 : plan1)
 		}
 		if (COUNT) {
 			unsigned t = n_tests;

@@ -54,6 +54,10 @@ def launches():
     print(open(os.path.join(P, "%s_launch_summary.txt" % tag)).read())
 
 
+# mangled-name fragments that pick the profiled template instance (the line table is per instance)
+SYMS = {"narrowphase3_kernel": "narrowphase3_kernelILb0ELb0ELb1", "broadphase_grid_kernel": "broadphase_grid_kernelILb0ELb1"}
+
+
 def kernel(rep, name, cubin):
     path = os.path.join(G, rep)
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -68,7 +72,7 @@ def kernel(rep, name, cubin):
                 f.write("%-75s %-16s %s\n" % (h, units[i], vals[i]))
                 got[h] = (units[i], vals[i])
     env = dict(os.environ, NCU_CUBIN=cubin)
-    hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot_lines.py"), path, name + "ILb0", "30"],
+    hot = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_hot_lines.py"), path, SYMS.get(name, name + "ILb0"), "40"],
                          capture_output=True, text=True, env=env).stdout
     open(os.path.join(P, "%s_%s_hot_lines.txt" % (tag, name)), "w").write(hot)
 
