@@ -556,7 +556,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 		}
 		// (queue entries carry the triangle's index in the environment pack: tri_base of the candidate's model is word 17
 		// of its record slot)
-		const unsigned tb = (leaf0 || leaf1) ? __float_as_uint(NP3_SLOT(lane, rd)[4].y) : 0u;
+		const unsigned tb = __float_as_uint(NP3_SLOT(lane, rd)[4].y);  // (unconditional: one conflict-free LDS, no branch)
 		{
 			const unsigned lm0 = __ballot_sync(FULL, leaf0);
 			if (leaf0) leafq[lq + __popc(lm0 & lt)] = make_uint4(tb + lf0.x, lf0.y, ci, pose);
