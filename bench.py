@@ -604,8 +604,8 @@ def run_ours(args):
                             "bound_measured": "latency" if latency else top,
                             "bound_note": ("the contract's HBM roofline is reported in `frac` (algorithmic bytes = FCL-order tests x "
                                            "64-byte fp32 nodes; the kernel itself gathers 32-byte quantised nodes, mostly from L1/L2: "
-                                           "DRAM traffic is `traffic`); ncu: 16 warps/SM (128 registers), issue slots 56 %% busy, "
-                                           "L1 data pipe 47 %%, stalls spread over dependency waits, node gathers and the fp32 pipe "
+                                           "DRAM traffic is `traffic`); ncu: 16 warps/SM (128 registers), issue slots 56 % busy, "
+                                           "L1 data pipe 47 %, stalls spread over dependency waits, node gathers and the fp32 pipe "
                                            "(profiles/r2_narrowphase3_*)"),
                             "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                             "hbm_frac": fracs["hbm"], "l2_frac": fracs.get("l2"), "fp32_frac": fracs.get("fp32"),
