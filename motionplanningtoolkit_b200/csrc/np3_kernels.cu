@@ -537,8 +537,9 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			lf0 = make_uint2(env_side ? pC0 : pS, env_side ? pS : pC0);
 			lf1 = make_uint2(env_side ? pC1 : pS, env_side ? pS : pC1);
 			const bool ok0 = hit0 && !(lC0 && lS), ok1 = hit1 && !(lC1 && lS);
-			const bool desc0 = !lC0 && (lS || (env_side ? sC2.x > sS : !(sS > sC2.x)));
-			const bool desc1 = !lC1 && (lS || (env_side ? sC2.y > sS : !(sS > sC2.y)));
+			// (bitwise on purpose: as && / || the second line came back as a branch at 14 active lanes)
+			const bool big0 = env_side ? sC2.x > sS : !(sS > sC2.x), big1 = env_side ? sC2.y > sS : !(sS > sC2.y);
+			const bool desc0 = !lC0 & (lS | big0), desc1 = !lC1 & (lS | big1);
 			const uint2 plan0 = make_uint2(desc0 ? (uint32_t)C2.link0 : (uint32_t)linkS, desc0 ? same : (xi | flip));
 			const uint2 plan1 = make_uint2(desc1 ? (uint32_t)C2.link1 : (uint32_t)linkS, desc1 ? same : ((xi + 1u) | flip));
 			// both children overlap: the nearer one first, the other one is stacked
