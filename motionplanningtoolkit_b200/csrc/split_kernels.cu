@@ -212,13 +212,16 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_kernel(cons
 }
 
 
+#ifndef MPTCC_BP_GRID_CTAS
+#define MPTCC_BP_GRID_CTAS 3
+#endif
 // Grid broadphase (device_layout.hpp, "Broadphase grid"): the world box of a pose of a single-link agent spans at most
 // two cells per axis, and every cell carries the list of the objects that touch its 2 x 2 x 2 block, with their exact
 // fp64 boxes inline: one header load and one coalesced stream of 64-byte entries per pose instead of a tree walk.
 // The list is a superset of FCL's candidates (the cell index is the same monotone function of a coordinate on the host
 // and here); every entry is re-tested with FCL's exact fp64 AABB::overlap.
 template <bool COUNT, bool NP2>
-__global__ void __launch_bounds__(kBpWarpsPerCta * 32, 3) broadphase_grid_kernel(const __grid_constant__ KernelParams p) {
+__global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broadphase_grid_kernel(const __grid_constant__ KernelParams p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
