@@ -723,10 +723,16 @@ struct SplitTrav {
 // q.transform(center) + T), stored component-major in `box` (stride 32 doubles) plus the outward-rounded
 // fp32 copy used by the broadphase tree walk.
 __device__ __forceinline__ void pose_world_box(const double *rec, uint32_t fmt, const DevModel &m2, double *box,
-                                               float *amin, float *amax) {
+                                               float *amin, float *amax, double *rt_out = nullptr) {
 	double R[9], T[3], bmin[3], bmax[3];
 	Quat q;
 	decode_pose(rec, fmt, R, T, q, true);
+	if (rt_out != nullptr) {  // the decoded R (9), T (3) of the pose, component-major with stride 32 (one column per lane)
+#pragma unroll
+		for (int k = 0; k < 9; ++k) rt_out[k * 32] = R[k];
+#pragma unroll
+		for (int k = 0; k < 3; ++k) rt_out[(9 + k) * 32] = T[k];
+	}
 	if (q.w == 1.0 && q.x == 0.0 && q.y == 0.0 && q.z == 0.0) {
 #pragma unroll
 		for (int k = 0; k < 3; ++k) {
@@ -791,13 +797,12 @@ __device__ __forceinline__ void make_candidate_record(const KernelParams &p, con
 // of its inverse (fp64, rounded once).  `base` = node_base / tri_base of the object's model.  Returns false if R
 // is not a rotation to within 1e-11 (then (R^T, Tinv) is not the inverse and the caller must route the launch to
 // the fused kernel, which makes no such assumption).
-__device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, const double *pose_rec, const DevObject &ob,
-                                                       const DevModel &m2, float4 *rec, double *rel64, uint2 &base,
-                                                       float *cert = nullptr) {
+// (R2, T2 = the decoded pose, see decode_pose)
+__device__ __forceinline__ bool make_candidate_record2_rt(const KernelParams &p, const double *R2, const double *T2, const DevObject &ob,
+                                                          const DevModel &m2, float4 *rec, double *rel64, uint2 &base,
+                                                          float *cert = nullptr) {
 	const DevModel &m1 = p.env.models[ob.model];
-	double R2[9], T2[3], rl[12];
-	Quat q;
-	decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
+	double rl[12];
 #pragma unroll
 	for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
 	if (rel64 != nullptr) {
@@ -839,6 +844,14 @@ __device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, co
 		*cert = __double2float_ru(1e-5 * mag * (1.0 + 1e-12));
 	}
 	return finite && defect <= 1e-11;
+}
+__device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, const double *pose_rec, const DevObject &ob,
+                                                       const DevModel &m2, float4 *rec, double *rel64, uint2 &base,
+                                                       float *cert = nullptr) {
+	double R2[9], T2[3];
+	Quat q;
+	decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
+	return make_candidate_record2_rt(p, R2, T2, ob, m2, rec, rel64, base, cert);
 }
 
 // Pose box -> the integer grid of the broadphase tree (device_layout.hpp), rounded outward by one extra cell

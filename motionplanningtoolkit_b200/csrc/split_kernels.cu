@@ -34,6 +34,8 @@ constexpr int kNpBatch = MPTCC_NP_BATCH, kNpBatchLong = MPTCC_NP_BATCH_LONG;
 
 // per-warp shared memory of the broadphase kernel: pose boxes + cluster queue + candidate ids
 __host__ __device__ constexpr unsigned bp_warp_smem_bytes() { return 6u * 32u * 8u + kClusterQueueCap * 4u + kCandCap * 4u + 32u * 4u; }
+// ... of the grid broadphase kernel: + the decoded poses of the chunk
+__host__ __device__ constexpr unsigned bp_grid_warp_smem_bytes() { return bp_warp_smem_bytes() + 12u * 32u * 8u; }
 
 // per-warp shared memory of the narrowphase kernel
 __host__ __device__ constexpr unsigned np_warp_smem_bytes(unsigned batch) {
@@ -42,22 +44,28 @@ __host__ __device__ constexpr unsigned np_warp_smem_bytes(unsigned batch) {
 
 // Phase C2 + append: the `ncand` candidates (pose slot << 26 | object) in wm.cand_ids are grouped by pose slot, their
 // records are computed (fp64 relative transform -> fp32 record) and appended to the global candidate list.
-template <bool NP2>
+// SORTED: the candidates arrive grouped by pose slot already (grid broadphase) and `rt` holds the decoded poses of the
+// chunk (R 9, T 3, component-major with stride 32): no regrouping, no second decode.
+template <bool NP2, bool SORTED = false>
 __device__ __forceinline__ void flush_candidates(const KernelParams &p, const WarpMem &wm, unsigned *pfx, int ncand,
                                                  const double *chunk_poses, unsigned rec_len, bool aligned32,
-                                                 unsigned long long pose0, const DevModel &m2, int lane) {
-	// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
-	int mine = 0;
-	for (int i = 0; i < ncand; ++i) mine += (wm.cand_ids[i] >> 26) == (unsigned)lane;
-	int pre = mine;
-#pragma unroll
-	for (int o = 1; o < 32; o <<= 1) {
-		const int v = __shfl_up_sync(FULL, pre, o);
-		if (lane >= o) pre += v;
-	}
-	pfx[lane] = (unsigned)(pre - mine);
+                                                 unsigned long long pose0, const DevModel &m2, int lane,
+                                                 const double *rt = nullptr) {
+	// (the reservation first: its round trip to L2 overlaps the counting below)
 	unsigned gbase = 0;
 	if (lane == 0) gbase = atomicAdd(p.cand_total, (unsigned)ncand);
+	if (!SORTED) {
+		// lane = pose slot: count its candidates; exclusive prefix over the slots -> pfx[]
+		int mine = 0;
+		for (int i = 0; i < ncand; ++i) mine += (wm.cand_ids[i] >> 26) == (unsigned)lane;
+		int pre = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int v = __shfl_up_sync(FULL, pre, o);
+			if (lane >= o) pre += v;
+		}
+		pfx[lane] = (unsigned)(pre - mine);
+	}
 	gbase = __shfl_sync(FULL, gbase, 0);
 	__syncwarp();
 	if ((unsigned long long)gbase + (unsigned)ncand > (unsigned long long)p.cand_cap) {
@@ -67,17 +75,31 @@ __device__ __forceinline__ void flush_candidates(const KernelParams &p, const Wa
 	for (int i = lane; i < ncand; i += 32) {
 		const uint32_t id = wm.cand_ids[i];
 		const unsigned sl = id >> 26, e = id & 0x3ffffffu;
-		int rank = 0;  // candidates of the same pose slot that precede i
-		for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
-		const unsigned dst = gbase + pfx[sl] + (unsigned)rank;
+		unsigned dst = gbase + (unsigned)i;
+		if (!SORTED) {
+			int rank = 0;  // candidates of the same pose slot that precede i
+			for (int k = 0; k < i; ++k) rank += (wm.cand_ids[k] >> 26) == sl;
+			dst = gbase + pfx[sl] + (unsigned)rank;
+		}
 		float4 rec[4];
 		double pose[12], rel[12];
-		load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
+		if (!(SORTED && NP2)) load_pose_record(chunk_poses + (size_t)sl * rec_len, p.pose_format, aligned32, pose);
 		float4 *out = p.cand_rec + 4ull * dst;
 		if (NP2) {
 			uint2 mbase;
 			float cert;
-			if (!make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase, &cert))
+			bool rigid;
+			if (SORTED) {
+				double R2[9], T2[3];
+#pragma unroll
+				for (int k = 0; k < 9; ++k) R2[k] = rt[k * 32 + sl];
+#pragma unroll
+				for (int k = 0; k < 3; ++k) T2[k] = rt[(9 + k) * 32 + sl];
+				rigid = make_candidate_record2_rt(p, R2, T2, p.objects[e], m2, rec, rel, mbase, &cert);
+			} else {
+				rigid = make_candidate_record2(p, pose, p.objects[e], m2, rec, rel, mbase, &cert);
+			}
+			if (!rigid)
 				atomicOr(p.overflow, 2u);  // non-rigid pose: the fused fall-back recomputes the launch
 			p.cand_base[dst] = mbase;
 			p.cand_cert[dst] = cert;
@@ -225,7 +247,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broad
 	extern __shared__ __align__(16) unsigned char smem_raw[];
 	const int lane = threadIdx.x & 31;
 	const int warp = threadIdx.x >> 5;
-	unsigned char *base = smem_raw + (size_t)warp * bp_warp_smem_bytes();
+	unsigned char *base = smem_raw + (size_t)warp * bp_grid_warp_smem_bytes();
 	WarpMem wm{};
 	wm.box = reinterpret_cast<double *>(base);
 	base += 6 * 32 * 8;
@@ -235,6 +257,8 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broad
 	wm.cand_ids = reinterpret_cast<uint32_t *>(base);
 	base += kCandCap * 4;
 	unsigned *pfx = reinterpret_cast<unsigned *>(base);
+	base += 32 * 4;
+	double *rt = reinterpret_cast<double *>(base);  // [12][32] decoded pose (R, T) of every lane's pose
 
 	const unsigned long long n_chunks = (p.n_pose_sets + 31ull) >> 5;
 	const unsigned rec_len = pose_rec_len(p.pose_format);
@@ -261,7 +285,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broad
 			double rec[12];
 			float amin[3], amax[3];
 			load_pose_record(chunk_poses + (size_t)lane * rec_len, p.pose_format, aligned32, rec);
-			pose_world_box(rec, p.pose_format, m2, wm.box + lane, amin, amax);
+			pose_world_box(rec, p.pose_format, m2, wm.box + lane, amin, amax, rt + lane);
 			int c[3];
 #pragma unroll
 			for (int k = 0; k < 3; ++k) {
@@ -318,7 +342,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broad
 			ncand += __popc(om);
 			if (ncand > kCandCap - 32) {
 				__syncwarp();
-				flush_candidates<NP2>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane);
+				flush_candidates<NP2, true>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane, rt);
 				n_cand_total += (unsigned)ncand;
 				ncand = 0;
 				__syncwarp();
@@ -326,7 +350,7 @@ __global__ void __launch_bounds__(kBpWarpsPerCta * 32, MPTCC_BP_GRID_CTAS) broad
 		}
 		__syncwarp();
 		if (ncand > 0) {
-			flush_candidates<NP2>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane);
+			flush_candidates<NP2, true>(p, wm, pfx, ncand, chunk_poses, rec_len, aligned32, pose0, m2, lane, rt);
 			n_cand_total += (unsigned)ncand;
 		}
 		__syncwarp();
@@ -440,6 +464,7 @@ int launch_persistent(K kernel, const KernelParams &p, int sm_count, int threads
 int launch_broadphase(const KernelParams &p, int sm_count, bool count, bool np2, void *stream) {
 	const size_t smem = (size_t)kBpWarpsPerCta * bp_warp_smem_bytes();
 	if (p.grid_cells != nullptr) {
+		const size_t smem = (size_t)kBpWarpsPerCta * bp_grid_warp_smem_bytes();
 		if (np2)
 			return count ? launch_persistent(broadphase_grid_kernel<true, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream)
 			             : launch_persistent(broadphase_grid_kernel<false, true>, p, sm_count, kBpWarpsPerCta * 32, smem, stream);
