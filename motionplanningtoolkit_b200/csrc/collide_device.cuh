@@ -803,11 +803,22 @@ __device__ __forceinline__ bool make_candidate_record2_rt(const KernelParams &p,
                                                           float *cert = nullptr) {
 	const DevModel &m1 = p.env.models[ob.model];
 	double rl[12];
+	if (ob.identity) {
+		// R1 = I, T1 = 0 (every .inst file of the reference places the environment at the identity): FCL's
+		// R1^T R2 and R1^T (T2 - T1) are 1 x + 0 y + 0 z, i.e. x itself for finite entries (up to the sign of a zero,
+		// which no comparison sees); entries that are not finite make the launch fall back below, as they do with the
+		// general formula (0 * inf = NaN there, inf here: both fail the finite test).
 #pragma unroll
-	for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
+		for (int k = 0; k < 9; ++k) rl[k] = R2[k];
+#pragma unroll
+		for (int k = 0; k < 3; ++k) rl[9 + k] = T2[k];
+	} else {
+#pragma unroll
+		for (int k = 0; k < 12; ++k) rl[k] = rel_element(ob, R2, T2, k);
+	}
 	if (rel64 != nullptr) {
 #pragma unroll
-		for (int k = 0; k < 12; ++k) rel64[k] = rl[k];  // FCL's R (9), T (3) verbatim, for the exact pass
+		for (int k = 0; k < 12; ++k) rel64[k] = rl[k];  // FCL's R (9), T (3) (verbatim unless the object sits at the identity)
 	}
 	double tc[3];
 	float tinf = 0.f;

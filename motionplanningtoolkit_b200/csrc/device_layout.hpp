@@ -95,7 +95,7 @@ struct DevObject {
 	double T[3];     // tf1 translation
 	double aabb[6];  // world AABB: min xyz, max xyz (CollisionObject::computeAABB)
 	uint32_t model;
-	uint32_t pad;
+	uint32_t identity;  // 1: R is exactly the identity and T exactly zero (environment vertices given in world coordinates)
 };
 
 // One set of flattened models (the environment's, or the agent's).

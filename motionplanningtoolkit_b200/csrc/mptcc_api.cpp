@@ -1182,6 +1182,11 @@ int mptcc_set_environment(mptcc_ctx *ctx, int n_objects, const mptcc_mesh *meshe
 				o.aabb[3 + k] = ck + b.aabb_radius;
 			}
 		}
+		{
+			bool ident = o.T[0] == 0.0 && o.T[1] == 0.0 && o.T[2] == 0.0;
+			for (int k = 0; k < 9; ++k) ident = ident && o.R[k] == ((k % 4 == 0) ? 1.0 : 0.0);
+			o.identity = ident ? 1u : 0u;
+		}
 		ctx->objects_h.push_back(o);
 	}
 	sort_objects_morton(ctx->objects_h);
