@@ -18,7 +18,7 @@
 //              [1].y, .z, .w = 96 bits: the orientation as a unit quaternion (w, x, y, z), four 22-bit fixed-point
 //                      components Q (value Q * 2^-21 - 1) in bits [0,22) [22,44) [44,66) [66,88), then link[23:16]
 //            The rows of the quaternion's rotation matrix are the box axes (a left-handed triple is stored with axis 2
-//            negated: the same box).  link (24 bit): bit 23 = leaf, low 23 bits = first child / primitive.  A decoded
+//            negated: the same box).  link: the node32 link as a 24-bit two's-complement number (one PRMT sign-extends it).  A decoded
 //            axis component is within 4e-6 of the true one; the extents are widened by sqrt(3) * 4e-6 * (sum of
 //            extents) and (1 + 1e-6) so that the decoded box contains FCL's box.
 //   tri32  : float4[3] per triangle (recentred corner xyz, w unused), indexed by primitive id.

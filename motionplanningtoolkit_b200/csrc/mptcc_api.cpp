@@ -253,7 +253,8 @@ struct HostPack {
 					if (!(e <= 65000.0)) q_ok = false;
 					he[k] = float_to_half(round_up_f32(e), true);
 				}
-				const uint32_t raw = link >= 0 ? (uint32_t)link : (0x800000u | (uint32_t)(-(link + 1)));
+				if (link >= (1 << 23) || link < -(1 << 23)) q_ok = false;
+				const uint32_t raw = (uint32_t)link & 0xffffffu;  // 24-bit two's complement
 				const float cq[3] = {(float)(C[0] - m.ctr[0]), (float)(C[1] - m.ctr[1]), (float)(C[2] - m.ctr[2])};
 				uint4 q0, q1;
 				std::memcpy(&q0.x, &cq[0], 4);

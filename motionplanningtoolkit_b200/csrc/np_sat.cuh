@@ -23,18 +23,27 @@ __device__ __forceinline__ Node node_global(const float4 *p) {
 __device__ __forceinline__ Node node_shared(const float4 *p) { return Node{p[0], p[1], p[2], p[3]}; }
 
 // Quantised node (device_layout.hpp, nodeq) -> Node.  v3.w carries the link as the int the rest of the code expects.
-// A 22-bit fixed-point component Q stands for Q * 2^-21 - 1: OR-ing Q << 1 into the mantissa of 1.0f gives
-// 1 + Q * 2^-22 exactly, and 2 f - 3 is exact too (no integer-to-float conversion).
-__device__ __forceinline__ float qcomp(uint32_t Q) { return fmaf(__uint_as_float(0x3f800000u | (Q << 1)), 2.0f, -3.0f); }
+// A 22-bit fixed-point component Q stands for q = Q * 2^-21 - 1.  The bits of Q, read as a float, are the subnormal
+// Q * 2^-149, and fma(Q * 2^-149, 2^127, -0.5) = q / 2 exactly (sm_100 FFMA takes subnormal operands at full speed): a
+// mask and one FFMA per component, no shift into a mantissa and no integer-to-float conversion.  The rotation matrix is
+// quadratic in the quaternion, so the factor 1/2 per component turns its 2 into 8 -- every product below is the
+// product of the unscaled formula times a power of two, i.e. bit-identical to it.
+constexpr float kQHalfScale = 1.7014118346046923e38f;  // 2^127
+__device__ __forceinline__ float qcomp(uint32_t Q) { return fmaf(__uint_as_float(Q), kQHalfScale, -0.5f); }
+// the 24-bit two's-complement link: bytes 2, 3 of q1.x, byte 3 of q1.w, sign-extended by one PRMT
+__device__ __forceinline__ int qlink(const uint4 q1) {
+	int r;
+	asm("prmt.b32 %0, %1, %2, 0xF732;" : "=r"(r) : "r"(q1.x), "r"(q1.w));
+	return r;
+}
 __device__ __forceinline__ Node node_decode(const uint4 q0, const uint4 q1) {
 	constexpr uint32_t M22 = 0x3fffffu;
 	const float w = qcomp(q1.y & M22), x = qcomp(__funnelshift_r(q1.y, q1.z, 22) & M22);
-	const float y = qcomp(__funnelshift_r(q1.z, q1.w, 12) & M22), z = qcomp((q1.w >> 2) & M22);
+	const float y = qcomp(__funnelshift_r(q1.z, q1.w, 12) & M22), z = qcomp((q1.w >> 2) & M22);  // (halves of the components)
 	const float2 e = __half22float2(*reinterpret_cast<const __half2 *>(&q0.w));  // extent.x, extent.y
 	const float ez = __half2float(__ushort_as_half((unsigned short)(q1.x & 0xffffu)));
-	const uint32_t raw = (q1.x >> 16) | ((q1.w >> 24) << 16);
-	const int link = (raw & 0x800000u) ? -(int)(raw & 0x7fffffu) - 1 : (int)raw;
-	const float tx = x + x, ty = y + y, tz = z + z;
+	const int link = qlink(q1);
+	const float tx = 8.0f * x, ty = 8.0f * y, tz = 8.0f * z;
 	const float twx = tx * w, twy = ty * w, twz = tz * w;
 	const float txx = tx * x, txy = ty * x, txz = tz * x;
 	const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
@@ -148,12 +157,8 @@ __device__ __forceinline__ Node2 pack_nodes(const Node &A, const Node &B) {
 }
 
 // Two quantised nodes (device_layout.hpp, nodeq) decoded side by side.
-__device__ __forceinline__ int qlink(const uint4 q1) {
-	const uint32_t raw = (q1.x >> 16) | ((q1.w >> 24) << 16);
-	return (raw & 0x800000u) ? -(int)(raw & 0x7fffffu) - 1 : (int)raw;
-}
 __device__ __forceinline__ float2 qcomp2(uint32_t Qa, uint32_t Qb) {
-	return MPTCC_FMA2(make_float2(__uint_as_float(0x3f800000u | (Qa << 1)), __uint_as_float(0x3f800000u | (Qb << 1))), bc2(2.0f), bc2(-3.0f));
+	return MPTCC_FMA2(make_float2(__uint_as_float(Qa), __uint_as_float(Qb)), bc2(kQHalfScale), bc2(-0.5f));
 }
 __device__ __forceinline__ Node2 node2_decode(const uint4 a0, const uint4 a1, const uint4 b0, const uint4 b1) {
 	constexpr uint32_t M22 = 0x3fffffu;
@@ -161,7 +166,7 @@ __device__ __forceinline__ Node2 node2_decode(const uint4 a0, const uint4 a1, co
 	const float2 x = qcomp2(__funnelshift_r(a1.y, a1.z, 22) & M22, __funnelshift_r(b1.y, b1.z, 22) & M22);
 	const float2 y = qcomp2(__funnelshift_r(a1.z, a1.w, 12) & M22, __funnelshift_r(b1.z, b1.w, 12) & M22);
 	const float2 z = qcomp2((a1.w >> 2) & M22, (b1.w >> 2) & M22);
-	const float2 tx = MPTCC_ADD2(x, x), ty = MPTCC_ADD2(y, y), tz = MPTCC_ADD2(z, z);
+	const float2 tx = MPTCC_MUL2(x, bc2(8.0f)), ty = MPTCC_MUL2(y, bc2(8.0f)), tz = MPTCC_MUL2(z, bc2(8.0f));
 	const float2 twx = MPTCC_MUL2(tx, w), twy = MPTCC_MUL2(ty, w), twz = MPTCC_MUL2(tz, w);
 	const float2 txx = MPTCC_MUL2(tx, x), tyy = MPTCC_MUL2(ty, y), tzz = MPTCC_MUL2(tz, z);
 	const float2 one = bc2(1.0f), m1 = bc2(-1.0f);
@@ -239,14 +244,21 @@ __device__ __forceinline__ unsigned pair_disjoint(const StepFrame &f, const Node
 		           MPTCC_FMA2(F[6 + j], C.e[2], MPTCC_FMA2(F[3 + j], C.e[1], MPTCC_FMA2(F[j], C.e[0], MPTCC_ADD2(bc2(ebv[j]), mg)))))
 	// edge axes a_i x b_j, (i1, i2) = the other two child axes, (j1, j2) = the other two axes of S:
 	//   |t_i2 G(i1,j) - t_i1 G(i2,j)| > ea_i1 F(i2,j) + ea_i2 F(i1,j) + eb_j1 F(i,j2) + eb_j2 F(i,j1) + mg
+#ifndef MPTCC_SAT_EDGE_MASK
+// bit 3 i + j: test axis a_i x b_j.  A subset only makes the filter more conservative (verdicts do not depend on it).
+// Measured on C5 (tools/ab_np.py, gpurun_out/ab19-20): all nine 1.040 ms at 51.2 tests per pose-set, none 1.033 ms at
+// 58.6; the four axes between the two longest axes of each box (FCL's fit puts the direction of largest spread first, the thinnest last) 0.997 ms at 52.2.
+#define MPTCC_SAT_EDGE_MASK 0x1b
+#endif
 #pragma unroll
 	for (int i = 0; i < 3; ++i) {
 		const int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
 #pragma unroll
 		for (int j = 0; j < 3; ++j) {
 			const int j1 = (j + 1) % 3, j2 = (j + 2) % 3;
-			MPTCC_CMP2(MPTCC_FMA2(t[i2], G[3 * i1 + j], MPTCC_MUL2(nt[i1], G[3 * i2 + j])),
-			           MPTCC_FMA2(F[3 * i + j1], bc2(ebv[j2]), MPTCC_FMA2(F[3 * i + j2], bc2(ebv[j1]), MPTCC_FMA2(C.e[i2], F[3 * i1 + j], MPTCC_FMA2(C.e[i1], F[3 * i2 + j], mg)))))
+			if ((MPTCC_SAT_EDGE_MASK >> (3 * i + j)) & 1)
+				MPTCC_CMP2(MPTCC_FMA2(t[i2], G[3 * i1 + j], MPTCC_MUL2(nt[i1], G[3 * i2 + j])),
+				           MPTCC_FMA2(F[3 * i + j1], bc2(ebv[j2]), MPTCC_FMA2(F[3 * i + j2], bc2(ebv[j1]), MPTCC_FMA2(C.e[i2], F[3 * i1 + j], MPTCC_FMA2(C.e[i1], F[3 * i2 + j], mg)))))
 		}
 	}
 #undef MPTCC_CMP2
