@@ -577,7 +577,7 @@ struct mptcc_ctx {
 	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
 	long opt_np2 = 0;                // 1 = second-generation narrowphase (np2_kernels.cu): same speed on C5, see DESIGN.md section 5
 	long opt_expand4 = 0;            // np2: 1 = expand both trees per step (four tests); measured 37 % slower on C5
-	long opt_l2_persist = 0;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase
+	long opt_l2_persist = 1;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase (C5: 1.191 -> 1.156 ms per launch)
 	long opt_qnode = 1;              // np2/np3 traverse the 32-byte quantised nodes (one 256-bit load per node); 0 = the 64-byte fp32 nodes
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
 	long opt_first_half = 1;         // a host-buffer call that finds the device idle cuts its first piece in two

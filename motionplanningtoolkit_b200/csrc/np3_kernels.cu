@@ -24,6 +24,11 @@
 #include "collide_device.cuh"
 #include "np_sat.cuh"
 #include "launch_cache.hpp"
+#ifdef MPTCC_NP3_TRACE
+#include <algorithm>
+#include <cstdio>
+#include <vector>
+#endif
 
 namespace mptcc {
 namespace {
@@ -85,6 +90,17 @@ __device__ __forceinline__ bool pose_settled(const uint32_t *hits, uint32_t pose
 #define NP3_BOUNDS __maxnreg__(MPTCC_NP3_MAXREG)
 #else
 #define NP3_BOUNDS __launch_bounds__(kNp3Warps * 32, MPTCC_NP3_CTAS)
+#endif
+
+#ifdef MPTCC_NP3_TRACE
+// Research build (tools/build_variants.sh ... "-DMPTCC_NP3_TRACE"): per-warp time stamps (start, list exhausted, exit)
+// and node steps / busy lanes before and after the list ran out, printed by launch_narrowphase3 every 8th launch.
+__device__ unsigned long long np3_trace[8192 * 5];
+__device__ __forceinline__ unsigned long long gtime() {
+	unsigned long long t;
+	asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+	return t;
+}
 #endif
 
 template <bool COUNT, bool TOP, bool Q>
@@ -161,6 +177,14 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 	if (skip) return;
 	const unsigned total = *p.cand_total;
 	if (lane < 8) hits[lane] = 0xffffffffu;
+#ifdef MPTCC_NP3_TRACE
+	unsigned long long *tr = np3_trace + 4ull * ((blockIdx.x * (unsigned)kNp3Warps + (unsigned)warp) & 8191u);
+	if (lane == 0) {
+		tr[0] = gtime();
+		tr[1] = 0;
+	}
+	unsigned long long fin_steps = 0, run_steps = 0;
+#endif
 	__syncwarp();
 
 	const float4 *__restrict__ nodes2 = p.agent.node32 + 4ull * m2.node_base;
@@ -265,6 +289,9 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 					seen = first + want;
 					if (first >= total) {
 						exhausted = true;
+#ifdef MPTCC_NP3_TRACE
+						if (lane == 0) tr[1] = gtime();
+#endif
 						break;
 					}
 					qhead = first;
@@ -436,6 +463,10 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			continue;
 		}
 
+#ifdef MPTCC_NP3_TRACE
+		if (exhausted) fin_steps += (1ull << 32) + (unsigned)__popc(am);
+		else run_steps += (1ull << 32) + (unsigned)__popc(am);
+#endif
 		// ---- node step: both children of the descended tree against the stationary node of the other ----------------
 		bool leaf0 = false, leaf1 = false;
 		uint2 lf0 = make_uint2(0u, 0u), lf1 = make_uint2(0u, 0u);
@@ -573,6 +604,13 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 		for (int i = 0; i < CTR_N; ++i)
 			if (ctr[i]) atomicAdd(p.counters + i, ctr[i]);
 	}
+#ifdef MPTCC_NP3_TRACE
+	if (lane == 0) {
+		tr[2] = gtime();
+		tr[3] = fin_steps;
+		np3_trace[4ull * 8192 + ((blockIdx.x * (unsigned)kNp3Warps + (unsigned)warp) & 8191u)] = run_steps;
+	}
+#endif
 }
 
 }  // namespace
@@ -602,6 +640,38 @@ int launch_narrowphase3(const KernelParams &p, int sm_count, bool count, void *s
 	if (e != cudaSuccess) return (int)e;
 	if (per_sm < 1) per_sm = 1;
 	k<<<sm_count * per_sm, kNp3Warps * 32, smem, static_cast<cudaStream_t>(stream)>>>(p);
+#ifdef MPTCC_NP3_TRACE
+	{
+		static int calls = 0;
+		if (++calls % 8 == 0) {
+			const int nw = std::min(8192, sm_count * per_sm * kNp3Warps);
+			std::vector<unsigned long long> h(4 * (size_t)nw), h2(nw);
+			cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+			cudaMemcpyFromSymbol(h.data(), np3_trace, h.size() * 8);
+			cudaMemcpyFromSymbol(h2.data(), np3_trace, h2.size() * 8, 4ull * 8192 * 8);
+			unsigned long long t0 = ~0ull, fi = 0, fl = 0, ri = 0, rl = 0;
+			for (int w = 0; w < nw; ++w) {
+				t0 = std::min(t0, h[4 * w]);
+				fi += h[4 * w + 3] >> 32;
+				fl += h[4 * w + 3] & 0xffffffffull;
+				ri += h2[w] >> 32;
+				rl += h2[w] & 0xffffffffull;
+			}
+			fprintf(stderr, "np3 trace: node steps before the list ran out %.1f per warp at %.1f lanes, after %.1f per warp at %.1f lanes\n", (double)ri / nw,
+			        (double)rl / (double)(ri ? ri : 1), (double)fi / nw, (double)fl / (double)(fi ? fi : 1));
+			std::vector<double> ex, en;
+			for (int w = 0; w < nw; ++w) {
+				ex.push_back(h[4 * w + 1] ? (h[4 * w + 1] - t0) * 1e-3 : -1.0);
+				en.push_back((h[4 * w + 2] - t0) * 1e-3);
+			}
+			std::sort(ex.begin(), ex.end());
+			std::sort(en.begin(), en.end());
+			auto pc = [&](const std::vector<double> &v, double q) { return v[(size_t)(q * (v.size() - 1))]; };
+			fprintf(stderr, "np3 trace (us after the first warp started), %d warps: list ran out min %.1f 50%% %.1f max %.1f | exit min %.1f 10%% %.1f 50%% %.1f 90%% %.1f 99%% %.1f max %.1f\n", nw,
+			        pc(ex, 0), pc(ex, .5), pc(ex, 1), pc(en, 0), pc(en, .1), pc(en, .5), pc(en, .9), pc(en, .99), pc(en, 1));
+		}
+	}
+#endif
 	return (int)cudaGetLastError();
 }
 

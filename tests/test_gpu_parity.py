@@ -318,7 +318,7 @@ def test_device_resident_buffers_any_alignment(box_scene, n, offset_doubles):
 
 
 @pytest.mark.parametrize("opts", [dict(np2=1), dict(np2=1, qnode=1), dict(np2=1, always_replay=1), dict(np2=1, qnode=1, agent_top=0),
-                                  dict(np2=1, split_cap=1), dict(np2=1, long_batches=0), dict(np2=1, l2_persist=1)])
+                                  dict(np2=1, split_cap=1), dict(np2=1, long_batches=0), dict(np2=1, l2_persist=0)])
 def test_second_generation_narrowphase_matches_oracle(built, opts):
     """np2_kernels.cu (TMA-staged agent tree top, child-frame SAT, exact-pass kernel; optionally the 32-byte
     quantised nodes) gives the oracle's verdicts on deep trees, incl. forced path replay and the overflow fall-back."""
