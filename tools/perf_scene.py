@@ -57,3 +57,7 @@ c = chk.counters()
 print("%-8s n=%d links=%d  e2e %.3f ms  %.1f Mposes/s  device %.3f ms  collide %.3f  cand/pose %.2f  bv/pose %.1f  leaf/pose %.2f  exact/pose %.3f"
       % (scene, n, len(links), dt * 1e3, n / dt / 1e6, chk.last_kernel_ms(), hits / n, c["n_candidates"] / n, c["n_bv_tests"] / n,
          c["n_leaf_tests"] / n, c["n_exact_tri"] / n))
+if any(a.startswith("time_phases=1") for a in sys.argv[3:]):
+    chk.enable_counters(False)
+    chk.check_poses(pin.array, out=out.array)
+    print("         phases of the last piece (broadphase, narrowphase, exact, fall-back) ms:", ["%.3f" % v for v in chk.last_phase_ms(0)])
