@@ -169,9 +169,9 @@ int mptcc_last_phase_ms(mptcc_ctx *ctx, int slot, float *ms4);
  * kernel), "np2" (1 = second-generation narrowphase; selects it instead of np3), "qnode" (1 = 32-byte quantised
  * traversal nodes, the default; 0 = 64-byte fp32 nodes), "agent_top" (fp32 nodes only: agent tree nodes staged in
  * shared memory by TMA; np3: 0 / -1 = none, np2: -1 = as many as fit), "l2_persist" (1 = the narrowphase runs with a
- * persisting-L2 access-policy window over the environment's traversal nodes, the default; the window is set on the
- * launch stream before the narrowphase and cleared after it, so a caller-supplied stream loses a window of its own;
- * 0 = off).  Every combination gives the same verdicts.
+ * persisting-L2 access-policy window over the environment's traversal nodes; the window is set on the launch stream
+ * before the narrowphase and cleared after it, so a caller-supplied stream loses a window of its own; 0 = off; -1, the
+ * default = on for agents of >= 128 triangles against >= 16 MB of environment nodes, where the narrowphase dominates).  Every combination gives the same verdicts.
  * The environment variable MPTCC_OPTIONS="name=value,..." applies options to every new context. */
 int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
 /* What the current scene and options resolve to (tests and tools): "qnode_active" (1: the split pipeline traverses the

@@ -577,7 +577,7 @@ struct mptcc_ctx {
 	long opt_self_collision = 0;     // checkSelfCollision = true of MeshHandler::isInCollision
 	long opt_np2 = 0;                // 1 = second-generation narrowphase (np2_kernels.cu): same speed on C5, see DESIGN.md section 5
 	long opt_expand4 = 0;            // np2: 1 = expand both trees per step (four tests); measured 37 % slower on C5
-	long opt_l2_persist = 1;         // persisting-L2 access window over the environment's traversal nodes during the narrowphase (C5: 1.191 -> 1.156 ms per launch)
+	long opt_l2_persist = -1;        // persisting-L2 access window over the environment's traversal nodes during the narrowphase: 1 / 0, -1 = when it pays (enqueue_kernel)
 	long opt_qnode = 1;              // np2/np3 traverse the 32-byte quantised nodes (one 256-bit load per node); 0 = the 64-byte fp32 nodes
 	long opt_agent_top = -1;         // agent nodes staged in shared memory by the np2 kernel: -1 = as many as fit (511)
 	long opt_first_half = 1;         // a host-buffer call that finds the device idle cuts its first piece in two
@@ -930,7 +930,16 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 		// warps per SM) can expect at least four of them
 		const bool long_batches = ctx->opt_long_batches == 1 ||
 		                          (ctx->opt_long_batches < 0 && n >= (uint64_t)d.sm_count * 16u * 128u * 3u);
-		if (ctx->opt_l2_persist && d.l2_persist_max > 0) {
+		// Persisting-L2 window over the environment's traversal nodes while the narrowphase runs.  It pays when the
+		// narrowphase dominates the launch and the nodes would otherwise compete for L2 (C5, blimp vs 73 MB of nodes:
+		// 1.191 -> 1.156 ms per launch); with a 12-triangle agent on the same environment the launch is all broadphase and
+		// the set-aside only takes L2 away from it (on-device edges: 11.7 -> 13.4 ms per 11 M pose-sets).  -1 = on for
+		// agents of >= 128 triangles against >= 16 MB of environment nodes.
+		const bool l2_persist = d.l2_persist_max > 0 &&
+		                        (ctx->opt_l2_persist > 0 ||
+		                         (ctx->opt_l2_persist < 0 && ctx->agent_h.models[ctx->link_model_h[0]].num_tris >= 128u &&
+		                          (kp.qnode ? d.env.nodeq.n * sizeof(uint4) : d.env.node32.n * sizeof(float4)) >= (16u << 20)));
+		if (l2_persist) {
 			// keep (a fraction of) the environment's traversal nodes in the persisting part of L2 while the narrowphase runs
 			cudaStreamAttrValue av;
 			std::memset(&av, 0, sizeof av);
@@ -955,7 +964,7 @@ int enqueue_kernel(mptcc_ctx *ctx, Device &d, uint64_t n, const double *d_poses,
 			if (timed) CU(cudaEventRecord(d.phase_ev[2], s));
 		}
 		if (timed) CU(cudaEventRecord(d.phase_ev[3], s));
-		if (ctx->opt_l2_persist && d.l2_persist_max > 0) {
+		if (l2_persist) {
 			cudaStreamAttrValue av;
 			std::memset(&av, 0, sizeof av);
 			CU(cudaStreamSetAttribute(s, cudaStreamAttributeAccessPolicyWindow, &av));  // num_bytes = 0: window off
@@ -1646,7 +1655,7 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	} else if (k == "expand4") {
 		ctx->opt_expand4 = value != 0;
 	} else if (k == "l2_persist") {
-		ctx->opt_l2_persist = value != 0;
+		ctx->opt_l2_persist = value < 0 ? -1 : (value != 0);
 	} else if (k == "qnode") {
 		ctx->opt_qnode = value != 0;
 	} else if (k == "agent_top") {

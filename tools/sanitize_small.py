@@ -14,7 +14,7 @@ agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
 rng = scenes.SplitMix64(99)
 poses = scenes.random_poses_near_objects(rng, 6000, env, 2.0, fmt="tq7")
 ref = None
-for opts in (dict(), dict(qnode=0), dict(qnode=0, agent_top=255), dict(grid=0), dict(np2=1), dict(np3=0), dict(split=0)):
+for opts in (dict(), dict(l2_persist=0), dict(qnode=0), dict(qnode=0, agent_top=255), dict(grid=0), dict(np2=1), dict(np3=0), dict(split=0)):
     chk = capi.Checker(1)
     chk.set_option("split_min", 32)
     for k, v in opts.items():
