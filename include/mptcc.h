@@ -191,6 +191,12 @@ uint32_t mptcc_bvh_depth(const mptcc_bvh *b);
 void mptcc_bvh_get_nodes(const mptcc_bvh *b, double *axis, double *To, double *extent, int32_t *first_child,
                          int32_t *first_primitive, int32_t *num_primitives);
 void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out);
+/* The 32-byte quantised traversal nodes the device would get for this model (csrc/device_layout.hpp, nodeq):
+ * words [n][8]; device_id [n] (may be NULL) = device number of FCL node i (node n of `words` is device node n);
+ * ctr3 (may be NULL) = the model's recentring origin the stored centres are relative to.  Returns 1 if every node
+ * could be quantised within the bounds of DESIGN.md section 6, 0 if the pack would fall back to fp32 nodes, -1 on
+ * bad arguments. */
+int mptcc_bvh_get_quantised_nodes(const mptcc_bvh *b, int breadth_first, uint32_t *words, uint32_t *device_id, double *ctr3);
 /* aabb6 = min xyz, max xyz */
 void mptcc_bvh_get_local_aabb(const mptcc_bvh *b, double *aabb6, double *center3, double *radius);
 

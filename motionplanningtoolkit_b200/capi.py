@@ -30,7 +30,7 @@ EXPORTS = [
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option", "mptcc_get_info",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
-    "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb",
+    "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb", "mptcc_bvh_get_quantised_nodes",
 ]
 
 
@@ -120,6 +120,8 @@ def load():
     L.mptcc_bvh_get_nodes.argtypes = [vp, dp, dp, dp, i32p, i32p, i32p]
     L.mptcc_bvh_get_primitive_indices.restype = None
     L.mptcc_bvh_get_primitive_indices.argtypes = [vp, u32p]
+    L.mptcc_bvh_get_quantised_nodes.restype = C.c_int
+    L.mptcc_bvh_get_quantised_nodes.argtypes = [vp, C.c_int, u32p, u32p, dp]
     L.mptcc_bvh_get_local_aabb.restype = None
     L.mptcc_bvh_get_local_aabb.argtypes = [vp, dp, dp, dp]
     _LIB = L
@@ -336,6 +338,16 @@ class HostBvh:
         i32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_int32))
         self.lib.mptcc_bvh_get_nodes(self.h, _dp(axis), _dp(To), _dp(ext), i32(fc), i32(fp), i32(npr))
         return dict(axis=axis, To=To, extent=ext, first_child=fc, first_primitive=fp, num_primitives=npr)
+
+    def quantised_nodes(self, breadth_first=False):
+        """(words [n, 8] uint32, device_id [n], ctr [3], ok): the 32-byte traversal nodes the device would get."""
+        n = self.num_nodes
+        words = np.zeros((n, 8), np.uint32); dev = np.zeros(n, np.uint32); ctr = np.zeros(3)
+        u32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        rc = self.lib.mptcc_bvh_get_quantised_nodes(self.h, int(breadth_first), u32(words), u32(dev), _dp(ctr))
+        if rc < 0:
+            raise MptccError(rc, "mptcc_bvh_get_quantised_nodes")
+        return words, dev, ctr, bool(rc)
 
     def primitive_indices(self):
         out = np.empty(self.nt, np.uint32)

@@ -1713,6 +1713,35 @@ void mptcc_bvh_get_nodes(const mptcc_bvh *b, double *axis, double *To, double *e
 	if (num_primitives) std::memcpy(num_primitives, h.num_primitives.data(), sizeof(int32_t) * n);
 }
 
+int mptcc_bvh_get_quantised_nodes(const mptcc_bvh *b, int breadth_first, uint32_t *words, uint32_t *device_id, double *ctr3) {
+	if (!b || !words) return -1;
+	HostPack pk;
+	pk.add(b->b, breadth_first != 0);
+	const DevModel &m = pk.models[0];
+	const size_t n = b->b.num_nodes();
+	std::memcpy(words, pk.nodeq.data() + 2 * (size_t)m.node_base, sizeof(uint4) * 2 * n);
+	if (ctr3) std::memcpy(ctr3, m.ctr, 24);
+	if (device_id) {
+		// the numbering HostPack::add uses (FCL's allocation order, or breadth-first with siblings adjacent)
+		std::vector<uint32_t> order(n);
+		if (breadth_first) {
+			uint32_t head = 0, tail = 0;
+			order[tail++] = 0;
+			while (head < tail) {
+				const uint32_t v = order[head++];
+				if (b->b.first_child[v] >= 0) {
+					order[tail++] = (uint32_t)b->b.first_child[v];
+					order[tail++] = (uint32_t)b->b.first_child[v] + 1u;
+				}
+			}
+		} else {
+			for (uint32_t i = 0; i < n; ++i) order[i] = i;
+		}
+		for (uint32_t i = 0; i < n; ++i) device_id[order[i]] = i;
+	}
+	return pk.q_ok ? 1 : 0;
+}
+
 void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out) {
 	std::memcpy(out, b->b.primitive_indices.data(), sizeof(uint32_t) * b->b.primitive_indices.size());
 }

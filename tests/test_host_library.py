@@ -58,6 +58,69 @@ def test_host_bvh_on_procedural_meshes(built):
         assert a.num_nodes == 2 * len(t) - 1 and a.depth >= int(np.ceil(np.log2(len(t)))) + 1
 
 
+def _half_to_float(h):
+    return np.asarray(h, np.uint16).view(np.float16).astype(np.float64)
+
+
+@pytest.mark.parametrize("breadth_first", [False, True])
+def test_quantised_nodes_decode_within_their_bounds(built, breadth_first):
+    """The 32-byte traversal nodes (csrc/device_layout.hpp, nodeq), decoded here the way np_sat.cuh decodes them, against
+    the fp64 nodes they stand for: link round trip (24-bit two's complement, device numbering), axes within 2e-6 of
+    FCL's (third axis possibly negated), centre = the fp32 rounding of the recentred centre, extents widened as DESIGN.md
+    section 6 states and never by more than binary16 costs, and the decoded box CONTAINS FCL's box."""
+    meshes = [(n, v, t) for n in ("blimp", "model", "divider") for (v, t) in meshio.environment_submeshes(meshio.load_mptm(n))]
+    meshes += [("synthetic", v, t) for v, t in scenes.synthetic_environment(6)]
+    for name, v, t in meshes:
+        hb = capi.HostBvh(v, t)
+        words, dev, ctr, ok = hb.quantised_nodes(breadth_first)
+        assert ok, name
+        nd = hb.nodes()
+        n = hb.num_nodes
+        w = words[dev]                                     # row i = the device node of FCL node i
+        q0, q1 = w[:, :4].astype(np.uint64), w[:, 4:].astype(np.uint64)
+        # link: bytes 2, 3 of q1.x and byte 3 of q1.w, sign-extended
+        raw = (q1[:, 0] >> 16) | ((q1[:, 3] >> 24) << 16)
+        link = np.where(raw & 0x800000, raw.astype(np.int64) - (1 << 24), raw.astype(np.int64))
+        fc = nd["first_child"].astype(np.int64)
+        want = np.where(fc >= 0, dev[np.maximum(fc, 0)].astype(np.int64), fc)
+        assert np.array_equal(link, want), name
+        if breadth_first:                                  # siblings adjacent, parents before children
+            inner = fc >= 0
+            assert np.all(dev[fc[inner] + 1] == dev[fc[inner]] + 1) and np.all(dev[fc[inner]] > dev[np.nonzero(inner)[0]])
+        # quaternion: four 22-bit components in bits [0,22) [22,44) [44,66) [66,88) of q1.y, .z, .w
+        bits = q1[:, 1] | (q1[:, 2] << 32)                 # low 64 of the 96
+        Q = np.stack([bits & 0x3fffff, (bits >> 22) & 0x3fffff, ((bits >> 44) | (q1[:, 3] << 20)) & 0x3fffff,
+                      (q1[:, 3] >> 2) & 0x3fffff], 1)
+        # the kernel's evaluation: the bits as a subnormal float times 2^127 minus 0.5 = half the component, exactly
+        half = (Q.astype(np.uint32).view(np.float32) * np.float32(2.0 ** 127) - np.float32(0.5)).astype(np.float64)
+        qd = Q.astype(np.float64) / 2097152.0 - 1.0
+        assert np.array_equal(half * 2.0, qd), name
+        qw, qx, qy, qz = qd.T
+        R = np.stack([np.stack([1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qw * qz), 2 * (qx * qz + qw * qy)], 1),
+                      np.stack([2 * (qx * qy + qw * qz), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qw * qx)], 1),
+                      np.stack([2 * (qx * qz - qw * qy), 2 * (qy * qz + qw * qx), 1 - 2 * (qx * qx + qy * qy)], 1)], 1)
+        A = nd["axis"].copy()                              # rows = box axes
+        A[np.linalg.det(A) < 0, 2] *= -1.0                 # a left-handed triple is stored with axis 2 negated: the same box
+        assert np.abs(R - A).max() <= 2e-6, (name, np.abs(R - A).max())
+        # centre
+        c32 = w[:, :3].copy().view(np.float32).astype(np.float64)
+        assert np.array_equal(c32, (nd["To"] - ctr).astype(np.float32).astype(np.float64)), name
+        # extents: binary16, rounded up from (e + sqrt(3) 4e-6 sum(e)) (1 + 1e-6)
+        E = nd["extent"]
+        eq = np.stack([_half_to_float(q0[:, 3] & 0xffff), _half_to_float(q0[:, 3] >> 16), _half_to_float(q1[:, 0] & 0xffff)], 1)
+        lo = (E + np.sqrt(3.0) * 4e-6 * E.sum(1, keepdims=True)) * (1 + 1e-6)
+        assert np.all(eq >= lo), name
+        assert np.all(eq <= lo * (1 + 2.0 ** -10) * (1 + 1e-6) + 6.2e-5), name       # (one binary16 ulp; subnormal halves below 6.1e-5)
+        # containment: every corner of FCL's box lies inside the decoded box
+        for sx in (-1, 1):
+            for sy in (-1, 1):
+                for sz in (-1, 1):
+                    corner = (sx * E[:, 0, None] * nd["axis"][:, 0] + sy * E[:, 1, None] * nd["axis"][:, 1] +
+                              sz * E[:, 2, None] * nd["axis"][:, 2])     # relative to the (common) centre
+                    proj = np.abs(np.einsum("nij,nj->ni", R, corner))
+                    assert np.all(proj <= eq), name
+
+
 def test_empty_mesh_is_rejected(built):
     with pytest.raises(capi.MptccError):
         capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
