@@ -121,6 +121,13 @@ def test_quantised_nodes_decode_within_their_bounds(built, breadth_first):
                     assert np.all(proj <= eq), name
 
 
+def test_quantised_nodes_refuse_what_they_cannot_represent(built):
+    """Extents beyond binary16 (65 000): the pack reports that it cannot be quantised (the kernels then traverse fp32 nodes)."""
+    v, t = meshio.load_mptm("unit_box")[0]
+    assert capi.HostBvh(v, t).quantised_nodes()[3]
+    assert not capi.HostBvh(np.asarray(v) * 2.0e5, t).quantised_nodes()[3]
+
+
 def test_empty_mesh_is_rejected(built):
     with pytest.raises(capi.MptccError):
         capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
