@@ -481,7 +481,6 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 			const uint32_t xi = pr.x, yi = pr.y & kPlan3Idx;
 			const float4 *rs = NP3_SLOT(lane, rd);
 			const float4 r0 = rs[0], r1 = rs[1], r2 = rs[2], r3 = rs[3];  // R (9), Tc (3), Tinv (3), S
-			const float ti0 = r3.x, ti1 = r3.y, ti2 = r3.z;
 			// Loads only: nothing below consumes a loaded value before every load of the step has been issued, so the
 			// two kinds of step (children = environment nodes / agent nodes) do not wait for memory one after the other.
 			const unsigned second = single ? 0u : 1u;  // (the root pair is one test: its "second child" repeats the first)
@@ -525,28 +524,7 @@ __global__ void NP3_BOUNDS narrowphase3_kernel(const __grid_constant__ KernelPar
 				C2 = pack_nodes(C0, C1);
 			}
 			// (Ry, Ty): the relative transform when the children are environment nodes, its inverse otherwise
-			StepFrame f;
-			{
-				const float y00 = r0.x, y11 = r1.x, y22 = r2.x;
-				const float y01 = env_side ? r0.y : r0.w, y10 = env_side ? r0.w : r0.y;
-				const float y02 = env_side ? r0.z : r1.z, y20 = env_side ? r1.z : r0.z;
-				const float y12 = env_side ? r1.y : r1.w, y21 = env_side ? r1.w : r1.y;
-				const float ty0 = env_side ? r2.y : ti0, ty1 = env_side ? r2.z : ti1, ty2 = env_side ? r2.w : ti2;
-				f.W[0] = y00 * S.v0.x + y01 * S.v0.y + y02 * S.v0.z;
-				f.W[1] = y00 * S.v1.x + y01 * S.v1.y + y02 * S.v1.z;
-				f.W[2] = y00 * S.v2.x + y01 * S.v2.y + y02 * S.v2.z;
-				f.W[3] = y10 * S.v0.x + y11 * S.v0.y + y12 * S.v0.z;
-				f.W[4] = y10 * S.v1.x + y11 * S.v1.y + y12 * S.v1.z;
-				f.W[5] = y10 * S.v2.x + y11 * S.v2.y + y12 * S.v2.z;
-				f.W[6] = y20 * S.v0.x + y21 * S.v0.y + y22 * S.v0.z;
-				f.W[7] = y20 * S.v1.x + y21 * S.v1.y + y22 * S.v1.z;
-				f.W[8] = y20 * S.v2.x + y21 * S.v2.y + y22 * S.v2.z;
-				const float cx = S.v0.w, cy = S.v1.w, cz = S.v2.w;
-				f.w[0] = y00 * cx + y01 * cy + y02 * cz + ty0;
-				f.w[1] = y10 * cx + y11 * cy + y12 * cz + ty1;
-				f.w[2] = y20 * cx + y21 * cy + y22 * cz + ty2;
-				f.s1 = (fabsf(ty0) + fabsf(ty1) + fabsf(ty2)) + (fabsf(cx) + fabsf(cy) + fabsf(cz));
-			}
+			const StepFrame f = step_frame(r0, r1, r2, r3, env_side, S);
 			const int linkS = __float_as_int(S.v3.w);
 			const float sS = S.v3.x * S.v3.x + S.v3.y * S.v3.y + S.v3.z * S.v3.z;
 			float2 d2p;

@@ -2,9 +2,11 @@
 // narrowphase kernels (np2_kernels.cu, np3_kernels.cu).  Margins: DESIGN.md section 6.
 #pragma once
 
+#ifndef MPTCC_NP_SAT_HOST  // tests/host_sat.cpp compiles the arithmetic of this header for the CPU against its own stand-ins
 #include <cuda_fp16.h>
 
 #include "collide_device.cuh"
+#endif
 
 namespace mptcc {
 namespace {
@@ -32,9 +34,14 @@ constexpr float kQHalfScale = 1.7014118346046923e38f;  // 2^127
 __device__ __forceinline__ float qcomp(uint32_t Q) { return fmaf(__uint_as_float(Q), kQHalfScale, -0.5f); }
 // the 24-bit two's-complement link: bytes 2, 3 of q1.x, byte 3 of q1.w, sign-extended by one PRMT
 __device__ __forceinline__ int qlink(const uint4 q1) {
+#ifdef __CUDA_ARCH__
 	int r;
 	asm("prmt.b32 %0, %1, %2, 0xF732;" : "=r"(r) : "r"(q1.x), "r"(q1.w));
 	return r;
+#else  // (the host compile of tests/host_sat.cpp)
+	const uint32_t raw = (q1.x >> 16) | ((q1.w >> 24) << 16);
+	return (int)(raw << 8) >> 8;
+#endif
 }
 __device__ __forceinline__ Node node_decode(const uint4 q0, const uint4 q1) {
 	constexpr uint32_t M22 = 0x3fffffu;
@@ -98,6 +105,34 @@ struct StepFrame {
 	float W[9], w[3];
 	float s1;  // |Ty|_1 + |cS|_1
 };
+
+// The frame of a step from the candidate record r0..r3 = R (9), Tc (3), Tinv (3), S: (Ry, Ty) is the relative transform
+// (R, Tc) when the children are environment nodes (env_side), its inverse (R^T, Tinv) when they are agent nodes.
+__device__ __forceinline__ StepFrame step_frame(const float4 r0, const float4 r1, const float4 r2, const float4 r3, const bool env_side,
+                                                const Node &S) {
+	StepFrame f;
+	const float ti0 = r3.x, ti1 = r3.y, ti2 = r3.z;
+	const float y00 = r0.x, y11 = r1.x, y22 = r2.x;
+	const float y01 = env_side ? r0.y : r0.w, y10 = env_side ? r0.w : r0.y;
+	const float y02 = env_side ? r0.z : r1.z, y20 = env_side ? r1.z : r0.z;
+	const float y12 = env_side ? r1.y : r1.w, y21 = env_side ? r1.w : r1.y;
+	const float ty0 = env_side ? r2.y : ti0, ty1 = env_side ? r2.z : ti1, ty2 = env_side ? r2.w : ti2;
+	f.W[0] = y00 * S.v0.x + y01 * S.v0.y + y02 * S.v0.z;
+	f.W[1] = y00 * S.v1.x + y01 * S.v1.y + y02 * S.v1.z;
+	f.W[2] = y00 * S.v2.x + y01 * S.v2.y + y02 * S.v2.z;
+	f.W[3] = y10 * S.v0.x + y11 * S.v0.y + y12 * S.v0.z;
+	f.W[4] = y10 * S.v1.x + y11 * S.v1.y + y12 * S.v1.z;
+	f.W[5] = y10 * S.v2.x + y11 * S.v2.y + y12 * S.v2.z;
+	f.W[6] = y20 * S.v0.x + y21 * S.v0.y + y22 * S.v0.z;
+	f.W[7] = y20 * S.v1.x + y21 * S.v1.y + y22 * S.v1.z;
+	f.W[8] = y20 * S.v2.x + y21 * S.v2.y + y22 * S.v2.z;
+	const float cx = S.v0.w, cy = S.v1.w, cz = S.v2.w;
+	f.w[0] = y00 * cx + y01 * cy + y02 * cz + ty0;
+	f.w[1] = y10 * cx + y11 * cy + y12 * cz + ty1;
+	f.w[2] = y20 * cx + y21 * cy + y22 * cz + ty2;
+	f.s1 = (fabsf(ty0) + fabsf(ty1) + fabsf(ty2)) + (fabsf(cx) + fabsf(cy) + fabsf(cz));
+	return f;
+}
 
 // Q: the decoded axes of a quantised node are within 4e-6 per component of the true ones; the stored extents are
 // widened so that the box they span contains FCL's box, and this term covers what the SAT's algebra loses because the

@@ -128,6 +128,84 @@ def test_quantised_nodes_refuse_what_they_cannot_represent(built):
     assert not capi.HostBvh(np.asarray(v) * 2.0e5, t).quantised_nodes()[3]
 
 
+def _host_sat(tmp_path):
+    """tests/host_sat.cpp: the arithmetic of csrc/np_sat.cuh compiled for the CPU (stand-ins for the CUDA types only)."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    so = str(tmp_path / "host_sat.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-I", os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc"), os.path.join(here, "host_sat.cpp"), "-o", so])
+    L = ctypes.CDLL(so)
+    u32p, f32p = ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_float)
+    L.host_pair_disjoint_q.restype = ctypes.c_uint
+    L.host_pair_disjoint_q.argtypes = [u32p, u32p, u32p, f32p, ctypes.c_int]
+    L.host_decode_difference.restype = ctypes.c_float
+    L.host_decode_difference.argtypes = [u32p, u32p]
+    return L
+
+
+def test_fp32_obb_filter_is_one_sided_against_the_oracle(built, tmp_path):
+    """The narrowphase's fast pass (quantised nodes, child-frame two-wide SAT on 11 axes, margins of DESIGN.md section 6),
+    compiled for the CPU from the kernel's own header, against FCL's fp64 obbDisjoint as the oracle restates it: on box
+    pairs pushed to the edge of touching, "certainly disjoint" must never be said of a pair FCL finds overlapping -- in
+    either descent direction -- and the filter must still catch nearly all pairs that are clearly apart."""
+    L = _host_sat(tmp_path)
+    u32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    f32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rng = np.random.default_rng(20260)
+    av, at = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    envs = sorted(meshio.environment_submeshes(meshio.load_mptm("divider")), key=lambda m: -len(m[1]))[:2] + scenes.synthetic_environment(2)
+    hbA = capi.HostBvh(av, at)
+    wA, devA, ctrA, okA = hbA.quantised_nodes(True)
+    ndA = hbA.nodes()
+    wrong = caught = apart = checked = 0
+    for ev, et in envs:
+        hbE = capi.HostBvh(ev, et)
+        wE, devE, ctrE, okE = hbE.quantised_nodes(False)
+        ndE = hbE.nodes()
+        assert okA and okE
+        # the scalar and the two-wide decode give the same boxes
+        for _ in range(200):
+            a, b = rng.integers(hbE.num_nodes), rng.integers(hbA.num_nodes)
+            # (to within the rounding of a*b+c as FMA or not: the two-wide decode spells its FMAs out, the scalar one leaves
+            # the contraction to the compiler)
+            assert L.host_decode_difference(u32(wE[devE[a]].copy()), u32(wA[devA[b]].copy())) <= 2.4e-7
+        for _ in range(400):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            R = scenes.quat_to_matrix(q[None])[0]
+            i, i2 = rng.integers(hbE.num_nodes, size=2)
+            j, j2 = rng.integers(hbA.num_nodes, size=2)
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            bE = lambda k: (ndE["axis"][k], ndE["To"][k], ndE["extent"][k])
+            bA = lambda k: (ndA["axis"][k], ndA["To"][k], ndA["extent"][k])
+            base = ndE["To"][i] - R @ ndA["To"][j]            # centres of (i, j) coincide at t = 0
+            hi = 2.0 * (np.linalg.norm(ndE["extent"][i]) + np.linalg.norm(ndA["extent"][j])) + 1e-3
+            lo = 0.0
+            if not O.obb_overlap(R, base, bE(i), bA(j)) or O.obb_overlap(R, base + hi * d, bE(i), bA(j)):
+                continue
+            for _ in range(60):                               # the edge of touching along d, to the last bit
+                mid = 0.5 * (lo + hi)
+                if O.obb_overlap(R, base + mid * d, bE(i), bA(j)):
+                    lo = mid
+                else:
+                    hi = mid
+            for t in (lo, lo * (1 - 1e-9), lo * (1 - 1e-6), lo * (1 - 1e-3), hi, hi * (1 + 1e-6), hi * (1 + 1e-3), hi * 1.05 + 1e-3, hi * 1.5 + 1e-2):
+                T = base + t * d
+                Tc = R @ ctrA + T - ctrE
+                rec = np.concatenate([R.ravel(), Tc, -(R.T @ Tc), [0.0]]).astype(np.float32)
+                # children = environment nodes i, i2 against the agent node j; then children = agent nodes j, j2 against i
+                m_env = L.host_pair_disjoint_q(u32(wA[devA[j]].copy()), u32(wE[devE[i]].copy()), u32(wE[devE[i2]].copy()), f32(rec), 1)
+                m_ag = L.host_pair_disjoint_q(u32(wE[devE[i]].copy()), u32(wA[devA[j]].copy()), u32(wA[devA[j2]].copy()), f32(rec), 0)
+                for said_disjoint, (x, y) in ((m_env & 1, (i, j)), (m_env & 2, (i2, j)), (m_ag & 1, (i, j)), (m_ag & 2, (i, j2))):
+                    overlap = O.obb_overlap(R, T, bE(x), bA(y))
+                    checked += 1
+                    wrong += bool(said_disjoint) and overlap
+                    if (x, y) == (i, j) and t >= hi * 1.05:
+                        apart += 1
+                        caught += bool(said_disjoint)
+    assert checked > 20000 and wrong == 0, (checked, wrong)
+    assert caught >= 0.9 * apart, (caught, apart)             # (5 % and 50 % beyond touching along d: the filter is not vacuous)
+
+
 def test_empty_mesh_is_rejected(built):
     with pytest.raises(capi.MptccError):
         capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
