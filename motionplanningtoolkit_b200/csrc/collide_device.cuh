@@ -388,11 +388,13 @@ __device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const Dev
 // fp32 conservative tests (hot path)
 // ------------------------------------------------------------------------------------------------
 
+// [host-test:begin]  (tests/host_filters.cpp compiles the marked regions of this header for the CPU)
 struct RelF {
 	float R[9];
 	float T[3];
 	float S;  // tri filter scale (see tri_filter_f32)
 };
+// [host-test:end]
 
 // One 256-bit read-only load (sm_100: LDG.E.256): half a node.  The L1 data pipe spends one wavefront per
 // 32-byte sector an instruction touches; the per-lane gathers of the traversal touch a different sector in
@@ -456,6 +458,7 @@ __device__ __forceinline__ void load_pose_record(const double *rec, uint32_t fmt
 	}
 }
 
+// [host-test:begin]
 // true => the two OBBs are certainly disjoint (with a margin far above fp64 round-off).
 // n1x = node of the environment model, n2x = node of the agent model; margins: DESIGN.md.
 __device__ __forceinline__ bool obb_disjoint_f32(const float4 a0, const float4 a1, const float4 a2, const float4 a3,
@@ -607,6 +610,7 @@ __device__ __forceinline__ int tri_filter_f32(const float4 P1, const float4 P2, 
 	if (g2 < -eps2 && g3 < -eps3) return TRI_INTERSECT;
 	return TRI_UNCERTAIN;
 }
+// [host-test:end]
 
 // ------------------------------------------------------------------------------------------------
 // warp-cooperative traversal of one (environment object, agent link, pose) candidate

@@ -206,6 +206,131 @@ def test_fp32_obb_filter_is_one_sided_against_the_oracle(built, tmp_path):
     assert caught >= 0.9 * apart, (caught, apart)             # (5 % and 50 % beyond touching along d: the filter is not vacuous)
 
 
+def _host_filters(tmp_path):
+    """tests/host_filters.cpp + the marked regions of csrc/collide_device.cuh, compiled for the CPU."""
+    here = os.path.dirname(os.path.abspath(__file__))
+    src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
+    regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
+    assert len(regions) == 2 and "tri_filter_f32" in regions[1] and "obb_disjoint_f32" in regions[1]
+    (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
+    cpp = tmp_path / "host_filters.cpp"
+    cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
+    so = str(tmp_path / "host_filters.so")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", so])
+    L = ctypes.CDLL(so)
+    f32p = ctypes.POINTER(ctypes.c_float)
+    for fn in (L.host_obb_disjoint_f32, L.host_tri_filter_f32):
+        fn.restype = ctypes.c_int
+        fn.argtypes = [f32p, f32p, f32p]
+    return L
+
+
+def _round_up_f32(x):
+    f = np.float32(x)
+    return f if float(f) >= x else np.nextafter(f, np.float32(np.inf))
+
+
+def _device_model(v, t):
+    """What HostPack::add (csrc/mptcc_api.cpp) gives the device for one model: recentring origin, node32 and tri32
+    records, r2 and rinf."""
+    hb = capi.HostBvh(v, t)
+    nd = hb.nodes()
+    ctr = hb.local_aabb()[1]
+    n = hb.num_nodes
+    node32 = np.zeros((n, 4, 4), np.float32)
+    node32[:, :3, :3] = nd["axis"]
+    node32[:, :3, 3] = nd["To"] - ctr
+    ext = nd["extent"] * (1.0 + 1e-6)
+    e32 = ext.astype(np.float32)
+    e32 = np.where(e32.astype(np.float64) >= ext, e32, np.nextafter(e32, np.float32(np.inf)))
+    node32[:, 3, :3] = e32
+    vv = np.asarray(v, np.float64)
+    tri32 = np.zeros((len(t), 3, 4), np.float32)
+    tri32[:, :, :3] = vv[np.asarray(t)] - ctr
+    d = vv - ctr
+    r2 = _round_up_f32(np.sqrt((d * d).sum(1).max()) * (1.0 + 1e-6))
+    rinf = _round_up_f32(np.abs(d).max() * (1.0 + 1e-6))
+    return dict(hb=hb, nd=nd, ctr=ctr, node32=node32, tri32=tri32, r2=r2, rinf=rinf, v=vv, t=np.asarray(t))
+
+
+def _record13(R, T, me, ma):
+    """R (9), Tc (3), S of the candidate record (make_candidate_record, collide_device.cuh)."""
+    tc = R @ ma["ctr"] + T - me["ctr"]
+    tf = tc.astype(np.float32)
+    tinf = np.float32(np.abs(tf).max())
+    S = np.float32(max(np.float32(5.01) * ma["r2"] + np.float32(4.0) * tinf * np.float32(1.0000002), me["rinf"])) + me["rinf"]
+    return np.concatenate([R.ravel().astype(np.float32), tf, [S]]).astype(np.float32)
+
+
+def test_fused_kernel_fp32_filters_are_one_sided_against_the_oracle(built, tmp_path):
+    """obb_disjoint_f32 (64-byte fp32 nodes: fused kernel, round-1 narrowphase) and the three-valued triangle filter of
+    every kernel, compiled for the CPU from collide_device.cuh itself, against FCL's fp64 tests as the oracle restates
+    them, on pairs pushed to the last bit of touching: "disjoint" / "separated" only where FCL separates, "certain
+    contact" only where FCL's Intersect::intersect_Triangle reports one; and both filters settle nearly every pair that
+    is clearly apart or clearly crossing."""
+    L = _host_filters(tmp_path)
+    f32 = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rng = np.random.default_rng(77031)
+    ma = _device_model(*meshio.agent_submesh(meshio.load_mptm("blimp"), "merge"))
+    envs = sorted(meshio.environment_submeshes(meshio.load_mptm("divider")), key=lambda m: -len(m[1]))[:2] + scenes.synthetic_environment(2)
+    obb_checked = obb_wrong = obb_apart = obb_caught = 0
+    tri_checked = tri_wrong = tri_clear = tri_settled = tri_deep = tri_certain = 0
+    for ev, et in envs:
+        me = _device_model(ev, et)
+        ndE, ndA = me["nd"], ma["nd"]
+        for _ in range(300):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            R = scenes.quat_to_matrix(q[None])[0]
+            d = rng.normal(size=3); d /= np.linalg.norm(d)
+            # ---- boxes
+            i, j = rng.integers(me["hb"].num_nodes), rng.integers(ma["hb"].num_nodes)
+            bE = (ndE["axis"][i], ndE["To"][i], ndE["extent"][i])
+            bA = (ndA["axis"][j], ndA["To"][j], ndA["extent"][j])
+            base = ndE["To"][i] - R @ ndA["To"][j]
+            lo, hi = 0.0, 2.0 * (np.linalg.norm(bE[2]) + np.linalg.norm(bA[2])) + 1e-3
+            if O.obb_overlap(R, base, bE, bA) and not O.obb_overlap(R, base + hi * d, bE, bA):
+                for _ in range(60):
+                    mid = 0.5 * (lo + hi)
+                    lo, hi = (mid, hi) if O.obb_overlap(R, base + mid * d, bE, bA) else (lo, mid)
+                for t in (lo, lo * (1 - 1e-9), lo * (1 - 1e-6), lo * (1 - 1e-3), hi, hi * (1 + 1e-6), hi * (1 + 1e-3), hi * 1.05 + 1e-3, hi * 1.5 + 1e-2):
+                    T = base + t * d
+                    said = L.host_obb_disjoint_f32(f32(me["node32"][i]), f32(ma["node32"][j]), f32(_record13(R, T, me, ma)))
+                    overlap = O.obb_overlap(R, T, bE, bA)
+                    obb_checked += 1
+                    obb_wrong += bool(said) and overlap
+                    if t >= hi * 1.05:
+                        obb_apart += 1
+                        obb_caught += bool(said)
+            # ---- triangles: a point of P and a point of Q coincide at t = 0, then Q moves away along d
+            a, b = rng.integers(len(me["t"])), rng.integers(len(ma["t"]))
+            P, Q = me["v"][me["t"][a]], ma["v"][ma["t"][b]]
+            wp, wq = rng.dirichlet([1, 1, 1]), rng.dirichlet([1, 1, 1])
+            base = wp @ P - R @ (wq @ Q)
+            lo, hi = 0.0, 2.0 * (np.ptp(P, 0).max() + np.ptp(Q, 0).max()) + 1e-3
+            if O.tri_intersect(P, Q, R, base) and not O.tri_intersect(P, Q, R, base + hi * d):
+                for _ in range(60):
+                    mid = 0.5 * (lo + hi)
+                    lo, hi = (mid, hi) if O.tri_intersect(P, Q, R, base + mid * d) else (lo, mid)
+                size = max(np.ptp(P, 0).max(), np.ptp(Q, 0).max())
+                band = 1e-3 * float(_record13(R, base + hi * d, me, ma)[12])   # 100 x the filter's uncertainty in distance (~1e-5 S)
+                for t, clear in ((lo, 0), (lo * (1 - 1e-9), 0), (lo * (1 - 1e-6), 0), (lo * (1 - 1e-3), 0), (hi, 0), (hi * (1 + 1e-6), 0),
+                                 (hi * (1 + 1e-3), 0), (hi + 0.1 * size + band, 1), (0.5 * lo, 2), (hi + size + band, 1)):
+                    T = base + t * d
+                    v = L.host_tri_filter_f32(f32(me["tri32"][a]), f32(ma["tri32"][b]), f32(_record13(R, T, me, ma)))
+                    truth = O.tri_intersect(P, Q, R, T)
+                    tri_checked += 1
+                    tri_wrong += (v == 0 and truth) or (v == 2 and not truth)
+                    tri_clear += clear == 1
+                    tri_settled += clear == 1 and v == 0
+                    tri_deep += clear == 2 and truth
+                    tri_certain += clear == 2 and truth and v == 2
+    assert obb_checked > 5000 and obb_wrong == 0, (obb_checked, obb_wrong)
+    assert obb_caught >= 0.9 * obb_apart, (obb_caught, obb_apart)
+    assert tri_checked > 5000 and tri_wrong == 0, (tri_checked, tri_wrong)
+    assert tri_settled >= 0.9 * tri_clear, (tri_settled, tri_clear)            # clearly apart: "separated"
+    assert tri_certain >= 0.25 * tri_deep, (tri_certain, tri_deep)            # crossing half-way in: a good part "certain contact"
+
+
 def test_empty_mesh_is_rejected(built):
     with pytest.raises(capi.MptccError):
         capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
