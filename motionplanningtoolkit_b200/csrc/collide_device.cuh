@@ -39,6 +39,7 @@ typedef unsigned long long u64;
 constexpr unsigned kPlanEnv = 1u << 23, kPlanSingle = 1u << 22, kPlanIdxMask = (1u << 22) - 1u;
 constexpr float kU = 5.9604645e-8f;  // 2^-24, fp32 unit round-off
 
+// [host-test:begin]  (fp64: pose decode and FCL's obbDisjoint, compared bit for bit with the oracle on the CPU)
 // ------------------------------------------------------------------------------------------------
 // fp64 helpers with FCL's evaluation order and no FMA contraction
 // ------------------------------------------------------------------------------------------------
@@ -263,6 +264,7 @@ __device__ __noinline__ bool exact_obb_disjoint(const double *__restrict__ rel, 
 #undef SUM4
 	return false;
 }
+// [host-test:end]
 
 struct D3 {
 	double x, y, z;

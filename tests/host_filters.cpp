@@ -1,13 +1,17 @@
-// host_filters.cpp -- TEST INFRASTRUCTURE: the fp32 filters of motionplanningtoolkit_b200/csrc/collide_device.cuh
-// (obb_disjoint_f32 of the fused and round-1 kernels, the three-valued tri_filter_f32 of every kernel) compiled for the
-// CPU.  tests/test_host_library.py copies the regions of the header between "[host-test:begin]" and "[host-test:end]"
+// host_filters.cpp -- TEST INFRASTRUCTURE: device functions of motionplanningtoolkit_b200/csrc/collide_device.cuh compiled
+// for the CPU: the fp32 filters (obb_disjoint_f32 of the fused and round-1 kernels, the three-valued tri_filter_f32 of every
+// kernel) and the fp64 restatement of FCL's pose decoding and obbDisjoint (decode_pose, exact_obb_disjoint).  tests/test_host_library.py copies the regions of the header between "[host-test:begin]" and "[host-test:end]"
 // into collide_filters_extracted.inc next to this file's copy; only the stand-ins below are not the header's own text.
 #include <cmath>
 #include <cstdint>
 
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 struct float4 { float x, y, z, w; };
+// round-to-nearest products and sums without contraction (this file is built with -ffp-contract=off)
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
 
 namespace mptcc {
 namespace {
@@ -17,6 +21,14 @@ constexpr float kU = 5.9604645e-8f;  // 2^-24 (collide_device.cuh)
 }  // namespace mptcc
 
 extern "C" {
+// pose record -> R (9), T (3), q (w x y z)
+void host_decode_pose(const double *rec, unsigned fmt, double *R, double *T, double *q4) {
+	mptcc::Quat q{1.0, 0.0, 0.0, 0.0};
+	mptcc::decode_pose(rec, fmt, R, T, q, true);
+	q4[0] = q.w; q4[1] = q.x; q4[2] = q.y; q4[3] = q.z;
+}
+// rel = R (9), T (3); n1, n2 = node64 records: axis (9), To (3), extent (3), size
+int host_exact_obb_disjoint(const double *rel, const double *n1, const double *n2) { return mptcc::exact_obb_disjoint(rel, n1, n2) ? 1 : 0; }
 // a, b: four float4 per node (node32 layout); rt13: R (9), T (3), S
 int host_obb_disjoint_f32(const float *a, const float *b, const float *rt13) {
 	using namespace mptcc;

@@ -211,7 +211,7 @@ def _host_filters(tmp_path):
     here = os.path.dirname(os.path.abspath(__file__))
     src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
     regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
-    assert len(regions) == 2 and "tri_filter_f32" in regions[1] and "obb_disjoint_f32" in regions[1]
+    assert len(regions) == 3 and "exact_obb_disjoint" in regions[0] and "tri_filter_f32" in regions[2] and "obb_disjoint_f32" in regions[2]
     (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
     cpp = tmp_path / "host_filters.cpp"
     cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
@@ -222,7 +222,77 @@ def _host_filters(tmp_path):
     for fn in (L.host_obb_disjoint_f32, L.host_tri_filter_f32):
         fn.restype = ctypes.c_int
         fn.argtypes = [f32p, f32p, f32p]
+    f64p = ctypes.POINTER(ctypes.c_double)
+    L.host_decode_pose.restype = None
+    L.host_decode_pose.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f64p]
+    L.host_exact_obb_disjoint.restype = ctypes.c_int
+    L.host_exact_obb_disjoint.argtypes = [f64p, f64p, f64p]
     return L
+
+
+def test_device_fp64_restatement_equals_the_oracle_bit_for_bit(built, tmp_path):
+    """decode_pose (fcl::Transform3f from a matrix / a quaternion, Quaternion3f::fromRotation / toRotation) and
+    exact_obb_disjoint (FCL's obbDisjoint with its operation order) as the kernels evaluate them, compiled for the CPU
+    from collide_device.cuh: the same bits as the oracle for every pose, and the same decision on box pairs one bit
+    before and one bit after touching."""
+    L = _host_filters(tmp_path)
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    rng = np.random.default_rng(424242)
+    # ---- poses: random rotations, the quaternion branches (trace <= 0 with each largest diagonal element), +-identity,
+    # unnormalised quaternions (FCL does not normalise), tiny and huge translations
+    quats = [np.array(q, float) for q in ([1, 0, 0, 0], [-1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1], [0.5, 0.5, 0.5, 0.5],
+                                           [2, 0, 0, 0], [1e-3, 1, 0, 0], [0.7, -0.1, 0.7, 0.1])]
+    for _ in range(3000):
+        q = rng.normal(size=4)
+        quats.append(q / np.linalg.norm(q) * (1.0 if rng.random() < 0.8 else rng.uniform(0.5, 2.0)))
+    for q in quats:
+        T = rng.normal(size=3) * 10.0 ** rng.integers(-6, 6)
+        tq7 = np.concatenate([T, q])
+        Ro, To, qo = O.pose_decode(tq7, O.POSE_TQ7)
+        R, T2, q2 = np.empty(9), np.empty(3), np.empty(4)
+        L.host_decode_pose(f64(tq7), 1, f64(R), f64(T2), f64(q2))
+        assert R.tobytes() == Ro.ravel().tobytes() and T2.tobytes() == To.tobytes(), q
+        rt12 = np.concatenate([Ro.ravel(), T])          # the matrix form of the same pose: q = fromRotation(R)
+        Ro2, To2, qo2 = O.pose_decode(rt12, O.POSE_RT12)
+        L.host_decode_pose(f64(rt12), 0, f64(R), f64(T2), f64(q2))
+        assert R.tobytes() == Ro2.ravel().tobytes() and q2.tobytes() == qo2.tobytes(), q
+    # the planar formats are the matrix format with R(0,0)=c R(0,1)=s R(1,0)=-s R(1,1)=c
+    for _ in range(200):
+        th = rng.uniform(-7, 7)
+        c, s_ = np.cos(th), np.sin(th)
+        x = rng.normal(size=3)
+        rt12 = np.array([c, s_, 0, -s_, c, 0, 0, 0, 1, *x])
+        Ro, To, qo = O.pose_decode(rt12, O.POSE_RT12)
+        R, T2, q2 = np.empty(9), np.empty(3), np.empty(4)
+        L.host_decode_pose(f64(np.array([*x, c, s_])), 3, f64(R), f64(T2), f64(q2))
+        assert R.tobytes() == Ro.ravel().tobytes() and T2.tobytes() == To.tobytes() and q2.tobytes() == qo.tobytes()
+        L.host_decode_pose(f64(x.copy()), 2, f64(R), f64(T2), f64(q2))
+        assert np.array_equal(R, np.eye(3).ravel()) and np.array_equal(q2, [1, 0, 0, 0]) and T2.tobytes() == x.tobytes()
+    # ---- obbDisjoint at the last bit
+    ma = _device_model(*meshio.agent_submesh(meshio.load_mptm("blimp"), "merge"))
+    me = _device_model(*sorted(meshio.environment_submeshes(meshio.load_mptm("divider")), key=lambda m: -len(m[1]))[0])
+    n64 = lambda nd, k: np.concatenate([nd["axis"][k].ravel(), nd["To"][k], nd["extent"][k], [float((nd["extent"][k] ** 2).sum())]])
+    checked = 0
+    for _ in range(600):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = scenes.quat_to_matrix(q[None])[0]
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        i, j = rng.integers(me["hb"].num_nodes), rng.integers(ma["hb"].num_nodes)
+        bE = (me["nd"]["axis"][i], me["nd"]["To"][i], me["nd"]["extent"][i])
+        bA = (ma["nd"]["axis"][j], ma["nd"]["To"][j], ma["nd"]["extent"][j])
+        base = bE[1] - R @ bA[1]
+        lo, hi = 0.0, 2.0 * (np.linalg.norm(bE[2]) + np.linalg.norm(bA[2])) + 1e-3
+        if not O.obb_overlap(R, base, bE, bA) or O.obb_overlap(R, base + hi * d, bE, bA):
+            continue
+        for _ in range(70):
+            mid = 0.5 * (lo + hi)
+            lo, hi = (mid, hi) if O.obb_overlap(R, base + mid * d, bE, bA) else (lo, mid)
+        for t in (0.0, lo * (1 - 1e-12), lo, hi, hi * (1 + 1e-12), 2 * hi):
+            T = base + t * d
+            rel = np.concatenate([R.ravel(), T])
+            assert bool(L.host_exact_obb_disjoint(f64(rel), f64(n64(me["nd"], i)), f64(n64(ma["nd"], j)))) == (not O.obb_overlap(R, T, bE, bA))
+            checked += 1
+    assert checked > 2000
 
 
 def _round_up_f32(x):
