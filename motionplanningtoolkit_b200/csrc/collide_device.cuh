@@ -630,6 +630,7 @@ struct WarpMem {
 	unsigned char *dead;   // [kCandCap] per pose slot of the batch: already in collision
 };
 
+// [host-test:begin]
 // relativeTransform(tf1, tf2): R = R1^T R2, T = R1^T (T2 - T1)  [FCL-recalled C.7]; element `idx`
 // (0..8 -> R row-major, 9..11 -> T).
 __device__ __forceinline__ double rel_element(const DevObject &ob, const double *R2, const double *T2, int idx) {
@@ -641,6 +642,7 @@ __device__ __forceinline__ double rel_element(const DevObject &ob, const double 
 	const double d0 = dsub(T2[0], ob.T[0]), d1 = dsub(T2[1], ob.T[1]), d2 = dsub(T2[2], ob.T[2]);
 	return ddot(ob.R[r], ob.R[3 + r], ob.R[6 + r], d0, d1, d2);
 }
+// [host-test:end]
 
 // Candidate records live in shared memory as 4 float4 (64 B).  Lanes fetch the SAME part k of DIFFERENT
 // records at once; with a plain layout all even (odd) candidates would hit the same 4 banks.  Part k of
@@ -724,6 +726,7 @@ struct SplitTrav {
 	}
 };
 
+// [host-test:begin]
 // Phase A for one lane: pose record -> world AABB of the link exactly as fcl::CollisionObject::computeAABB
 // [FCL-recalled C.5] (identity quaternion: translated tight box; else the sphere box around
 // q.transform(center) + T), stored component-major in `box` (stride 32 doubles) plus the outward-rounded
@@ -765,6 +768,7 @@ __device__ __forceinline__ void pose_world_box(const double *rec, uint32_t fmt, 
 		amax[k] = __double2float_ru(bmax[k]);
 	}
 }
+// [host-test:end]
 
 // Phase C2 for one candidate: fp64 relativeTransform of (object, pose) -> fp32 record in the recentred
 // frames: R (9), T (3), S, pose slot, node_base and tri_base of the object's model.

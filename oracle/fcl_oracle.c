@@ -861,6 +861,16 @@ static void relative_transform(const xform *t1, const xform *t2, mat3 *R, double
 	T[2] = tdot(&t1->R, 2, temp);
 }
 
+/* relativeTransform(tf1, tf2) of two pose records (tests: the device code's rel_element against it) */
+void orc_relative_transform(const double *rec1, int fmt1, const double *rec2, int fmt2, double *R, double *T) {
+	xform a, b;
+	mat3 m;
+	xform_decode(rec1, fmt1, &a);
+	xform_decode(rec2, fmt2, &b);
+	relative_transform(&a, &b, &m, T);
+	memcpy(R, m.m, sizeof(double) * 9);
+}
+
 /* ------------------------------------------------------------------------------------------- */
 /* StaticEnvironmentMeshHandler  (/root/reference/utilities/meshhandler.hpp:18-55)               */
 /* ------------------------------------------------------------------------------------------- */

@@ -99,6 +99,8 @@ int orc_obb_overlap(const double *R0, const double *T0, const double *axis1, con
 int orc_tri_intersect(const double *P /*[9]*/, const double *Q /*[9]*/, const double *R, const double *T);
 /* Transform helpers: fill R[9], T[3], q[4] from a pose record. */
 void orc_pose_decode(const double *rec, int pose_format, double *R, double *T, double *q);
+/* fcl::relativeTransform(tf1, tf2) of two pose records: R = R1^T R2, T = R1^T (T2 - T1) */
+void orc_relative_transform(const double *rec1, int fmt1, const double *rec2, int fmt2, double *R, double *T);
 /* CollisionObject::computeAABB for a model under a pose record. */
 void orc_object_aabb(const orc_model *m, const double *rec, int pose_format, double *aabb6);
 

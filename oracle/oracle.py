@@ -69,6 +69,8 @@ def lib():
         L.orc_tri_intersect.restype = C.c_int
         L.orc_tri_intersect.argtypes = [dp] * 4
         L.orc_pose_decode.argtypes = [dp, C.c_int, dp, dp, dp]
+        L.orc_relative_transform.restype = None
+        L.orc_relative_transform.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp]
         L.orc_object_aabb.argtypes = [vp, dp, C.c_int, dp]
         _LIB = L
     return _LIB
@@ -224,6 +226,13 @@ def obb_overlap(R0, T0, b1, b2):
 def tri_intersect(P, Q, R=np.eye(3), T=np.zeros(3)):
     a = [_f64(x) for x in (P, Q, R, T)]
     return bool(lib().orc_tri_intersect(*[_dp(x) for x in a]))
+
+
+def relative_transform(rec1, rec2, fmt1=POSE_RT12, fmt2=POSE_RT12):
+    """fcl::relativeTransform(tf1, tf2) of two pose records -> (R, T)."""
+    R = np.empty((3, 3)); T = np.empty(3)
+    lib().orc_relative_transform(_dp(_f64(rec1)), fmt1, _dp(_f64(rec2)), fmt2, _dp(R), _dp(T))
+    return R, T
 
 
 def pose_decode(rec, fmt=POSE_RT12):

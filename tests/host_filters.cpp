@@ -8,10 +8,18 @@
 #define __device__
 #define __forceinline__ inline
 #define __noinline__
+struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
+// double -> float rounded towards -inf / +inf
+static inline float __double2float_rd(double x) { const float f = (float)x; return (double)f <= x ? f : std::nextafterf(f, -INFINITY); }
+static inline float __double2float_ru(double x) { const float f = (float)x; return (double)f >= x ? f : std::nextafterf(f, INFINITY); }
 // round-to-nearest products and sums without contraction (this file is built with -ffp-contract=off)
 static inline double __dmul_rn(double a, double b) { return a * b; }
 static inline double __dadd_rn(double a, double b) { return a + b; }
+
+#include "device_layout.hpp"
 
 namespace mptcc {
 namespace {
@@ -26,6 +34,26 @@ void host_decode_pose(const double *rec, unsigned fmt, double *R, double *T, dou
 	mptcc::Quat q{1.0, 0.0, 0.0, 0.0};
 	mptcc::decode_pose(rec, fmt, R, T, q, true);
 	q4[0] = q.w; q4[1] = q.x; q4[2] = q.y; q4[3] = q.z;
+}
+// world AABB of a link (CollisionObject::computeAABB): model = aabb_min (3), aabb_max (3), aabb_center (3), aabb_radius
+void host_pose_world_box(const double *rec, unsigned fmt, const double *model10, double *box6, float *amin3, float *amax3) {
+	mptcc::DevModel m{};
+	for (int k = 0; k < 3; ++k) {
+		m.aabb_min[k] = model10[k];
+		m.aabb_max[k] = model10[3 + k];
+		m.aabb_center[k] = model10[6 + k];
+	}
+	m.aabb_radius = model10[9];
+	double box[6 * 32];
+	mptcc::pose_world_box(rec, fmt, m, box, amin3, amax3);
+	for (int k = 0; k < 6; ++k) box6[k] = box[k * 32];
+}
+// relativeTransform(tf1 = object (R1 9, T1 3), tf2 = pose (R2 9, T2 3)) -> R (9), T (3)
+void host_relative_transform(const double *R1, const double *T1, const double *R2, const double *T2, double *out12) {
+	mptcc::DevObject ob{};
+	for (int k = 0; k < 9; ++k) ob.R[k] = R1[k];
+	for (int k = 0; k < 3; ++k) ob.T[k] = T1[k];
+	for (int k = 0; k < 12; ++k) out12[k] = mptcc::rel_element(ob, R2, T2, k);
 }
 // rel = R (9), T (3); n1, n2 = node64 records: axis (9), To (3), extent (3), size
 int host_exact_obb_disjoint(const double *rel, const double *n1, const double *n2) { return mptcc::exact_obb_disjoint(rel, n1, n2) ? 1 : 0; }

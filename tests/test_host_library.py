@@ -211,12 +211,14 @@ def _host_filters(tmp_path):
     here = os.path.dirname(os.path.abspath(__file__))
     src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
     regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
-    assert len(regions) == 3 and "exact_obb_disjoint" in regions[0] and "tri_filter_f32" in regions[2] and "obb_disjoint_f32" in regions[2]
+    assert len(regions) == 5 and "exact_obb_disjoint" in regions[0] and "tri_filter_f32" in regions[2] and "obb_disjoint_f32" in regions[2]
+    assert "rel_element" in regions[3] and "pose_world_box" in regions[4]
     (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
     cpp = tmp_path / "host_filters.cpp"
     cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
     so = str(tmp_path / "host_filters.so")
-    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", so])
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-ffp-contract=off", "-shared", "-fPIC",
+                           "-I", os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc"), str(cpp), "-o", so])
     L = ctypes.CDLL(so)
     f32p = ctypes.POINTER(ctypes.c_float)
     for fn in (L.host_obb_disjoint_f32, L.host_tri_filter_f32):
@@ -227,7 +229,51 @@ def _host_filters(tmp_path):
     L.host_decode_pose.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f64p]
     L.host_exact_obb_disjoint.restype = ctypes.c_int
     L.host_exact_obb_disjoint.argtypes = [f64p, f64p, f64p]
+    L.host_pose_world_box.restype = None
+    L.host_pose_world_box.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f32p, f32p]
+    L.host_relative_transform.restype = None
+    L.host_relative_transform.argtypes = [f64p, f64p, f64p, f64p, f64p]
     return L
+
+
+def test_device_object_box_and_relative_transform_equal_the_oracle_bit_for_bit(built, tmp_path):
+    """pose_world_box (fcl::CollisionObject::computeAABB: translated tight box for an identity quaternion, sphere box around
+    the transformed centre otherwise) and rel_element (fcl::relativeTransform) as the kernels evaluate them, compiled for
+    the CPU from collide_device.cuh: the oracle's bits; the fp32 copy of the box the broadphase walks with contains it."""
+    L = _host_filters(tmp_path)
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    f32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rng = np.random.default_rng(9001)
+    for name, how in (("blimp", "merge"), ("blimp", "last"), ("unit_box", "last")):
+        v, t = meshio.agent_submesh(meshio.load_mptm(name), how)
+        om = O.Model(v, t)
+        box, ctr, rad = om.local_aabb()
+        model10 = np.concatenate([box, ctr, [rad]])
+        for k in range(1500):
+            T = rng.normal(size=3) * 10.0 ** rng.integers(-3, 4)
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            if k % 5 == 0:
+                q = np.array([1.0, 0, 0, 0]) if k % 10 == 0 else np.array([-1.0, 0, 0, 0])
+            for fmt_o, fmt_d, rec in ((O.POSE_TQ7, 1, np.concatenate([T, q])),
+                                      (O.POSE_RT12, 0, np.concatenate([O.pose_decode(np.concatenate([T, q]), O.POSE_TQ7)[0].ravel(), T])),
+                                      (O.POSE_RT12, 2, T.copy())):
+                want = om.object_aabb(np.concatenate([np.eye(3).ravel(), T]) if fmt_d == 2 else rec, fmt_o)
+                got, amin, amax = np.empty(6), np.empty(3, np.float32), np.empty(3, np.float32)
+                L.host_pose_world_box(f64(rec), fmt_d, f64(model10), f64(got), f32(amin), f32(amax))
+                assert got.tobytes() == want.tobytes(), (name, fmt_d, q)
+                assert np.all(amin.astype(np.float64) <= got[:3]) and np.all(amax.astype(np.float64) >= got[3:])
+                assert np.all(np.nextafter(amin, np.float32(np.inf)).astype(np.float64) > got[:3])
+    for _ in range(3000):
+        recs = []
+        for _ in range(2):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            T = rng.normal(size=3) * 10.0 ** rng.integers(-3, 4)
+            R, T_, _q = O.pose_decode(np.concatenate([T, q]), O.POSE_TQ7)
+            recs.append(np.concatenate([R.ravel(), T_]))
+        Ro, To = O.relative_transform(recs[0], recs[1])
+        out = np.empty(12)
+        L.host_relative_transform(f64(recs[0][:9].copy()), f64(recs[0][9:].copy()), f64(recs[1][:9].copy()), f64(recs[1][9:].copy()), f64(out))
+        assert out[:9].tobytes() == Ro.ravel().tobytes() and out[9:].tobytes() == To.tobytes()
 
 
 def test_device_fp64_restatement_equals_the_oracle_bit_for_bit(built, tmp_path):
