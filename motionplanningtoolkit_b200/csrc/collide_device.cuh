@@ -266,6 +266,7 @@ __device__ __noinline__ bool exact_obb_disjoint(const double *__restrict__ rel, 
 }
 // [host-test:end]
 
+// [host-test:begin]
 struct D3 {
 	double x, y, z;
 };
@@ -328,6 +329,7 @@ __device__ __noinline__ bool exact_tri_intersect_warp(const double *__restrict__
 	const bool separated = (lane < 17) && ((mn1 > mx2) || (mn2 > mx1));
 	return __ballot_sync(FULL, separated) == 0u;
 }
+// [host-test:end]
 
 // Replays FCL's collisionRecurse descent from (root, root) to the leaf pair holding primitives
 // (prim1, prim2) and evaluates every OBB test on the way in fp64 [FCL-recalled C.7, C.8].

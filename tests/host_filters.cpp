@@ -21,8 +21,18 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 
 #include "device_layout.hpp"
 
+// exact_tri_intersect_warp ends in one ballot over the 17 lanes that each test one axis: the stand-in records the calling
+// lane's predicate, host_exact_tri_intersect calls the function once per lane and forms the ballot itself
+static int g_lane = 0;
+static bool g_pred[32];
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+	g_pred[g_lane] = pred;
+	return 0u;
+}
+
 namespace mptcc {
 namespace {
+constexpr unsigned FULL = 0xffffffffu;
 constexpr float kU = 5.9604645e-8f;  // 2^-24 (collide_device.cuh)
 #include "collide_filters_extracted.inc"
 }  // namespace
@@ -54,6 +64,15 @@ void host_relative_transform(const double *R1, const double *T1, const double *R
 	for (int k = 0; k < 9; ++k) ob.R[k] = R1[k];
 	for (int k = 0; k < 3; ++k) ob.T[k] = T1[k];
 	for (int k = 0; k < 12; ++k) out12[k] = mptcc::rel_element(ob, R2, T2, k);
+}
+// Intersect::intersect_Triangle as the kernels evaluate it: rel = R (9), T (3); P, Q = 9 doubles each (model coordinates)
+int host_exact_tri_intersect(const double *rel, const double *P, const double *Q) {
+	unsigned ballot = 0u;
+	for (g_lane = 0; g_lane < 32; ++g_lane) {
+		(void)mptcc::exact_tri_intersect_warp(rel, P, Q, g_lane);
+		ballot |= g_pred[g_lane] ? 1u << g_lane : 0u;
+	}
+	return ballot == 0u ? 1 : 0;
 }
 // rel = R (9), T (3); n1, n2 = node64 records: axis (9), To (3), extent (3), size
 int host_exact_obb_disjoint(const double *rel, const double *n1, const double *n2) { return mptcc::exact_obb_disjoint(rel, n1, n2) ? 1 : 0; }

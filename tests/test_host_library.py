@@ -211,8 +211,8 @@ def _host_filters(tmp_path):
     here = os.path.dirname(os.path.abspath(__file__))
     src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
     regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
-    assert len(regions) == 5 and "exact_obb_disjoint" in regions[0] and "tri_filter_f32" in regions[2] and "obb_disjoint_f32" in regions[2]
-    assert "rel_element" in regions[3] and "pose_world_box" in regions[4]
+    assert len(regions) == 6 and "exact_obb_disjoint" in regions[0] and "exact_tri_intersect_warp" in regions[1]
+    assert "tri_filter_f32" in regions[3] and "obb_disjoint_f32" in regions[3] and "rel_element" in regions[4] and "pose_world_box" in regions[5]
     (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
     cpp = tmp_path / "host_filters.cpp"
     cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
@@ -229,6 +229,8 @@ def _host_filters(tmp_path):
     L.host_decode_pose.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f64p]
     L.host_exact_obb_disjoint.restype = ctypes.c_int
     L.host_exact_obb_disjoint.argtypes = [f64p, f64p, f64p]
+    L.host_exact_tri_intersect.restype = ctypes.c_int
+    L.host_exact_tri_intersect.argtypes = [f64p, f64p, f64p]
     L.host_pose_world_box.restype = None
     L.host_pose_world_box.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f32p, f32p]
     L.host_relative_transform.restype = None
@@ -339,6 +341,27 @@ def test_device_fp64_restatement_equals_the_oracle_bit_for_bit(built, tmp_path):
             assert bool(L.host_exact_obb_disjoint(f64(rel), f64(n64(me["nd"], i)), f64(n64(ma["nd"], j)))) == (not O.obb_overlap(R, T, bE, bA))
             checked += 1
     assert checked > 2000
+    # ---- Intersect::intersect_Triangle at the last bit (17 axes over 17 lanes, one ballot)
+    checked = 0
+    for _ in range(1500):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = scenes.quat_to_matrix(q[None])[0]
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        P = me["v"][me["t"][rng.integers(len(me["t"]))]]
+        Q = ma["v"][ma["t"][rng.integers(len(ma["t"]))]]
+        base = rng.dirichlet([1, 1, 1]) @ P - R @ (rng.dirichlet([1, 1, 1]) @ Q)
+        lo, hi = 0.0, 2.0 * (np.ptp(P, 0).max() + np.ptp(Q, 0).max()) + 1e-3
+        bisect = O.tri_intersect(P, Q, R, base) and not O.tri_intersect(P, Q, R, base + hi * d)
+        for _ in range(70 if bisect else 0):
+            mid = 0.5 * (lo + hi)
+            lo, hi = (mid, hi) if O.tri_intersect(P, Q, R, base + mid * d) else (lo, mid)
+        for t in ((0.0, lo * (1 - 1e-12), lo, hi, hi * (1 + 1e-12), 2 * hi) if bisect else (0.0, hi)):
+            T = base + t * d
+            rel = np.concatenate([R.ravel(), T])
+            Pc, Qc = np.ascontiguousarray(P.ravel()), np.ascontiguousarray(Q.ravel())
+            assert bool(L.host_exact_tri_intersect(f64(rel), f64(Pc), f64(Qc))) == O.tri_intersect(P, Q, R, T)
+            checked += 1
+    assert checked > 4000
 
 
 def _round_up_f32(x):
