@@ -180,6 +180,19 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value);
  * "agent_nodes", "env_nodes". */
 int mptcc_get_info(mptcc_ctx *ctx, const char *name, long *value);
 
+/* ---- host-side scene introspection (no GPU needed; used by the CPU test-suite) --------------- */
+/* A context WITHOUT devices: mptcc_set_environment / mptcc_set_agent build the host side of the scene as usual (OBB
+ * trees, object boxes, the broadphase cluster tree and grid); every check call fails with MPTCC_ERR_NO_DEVICE. */
+int mptcc_debug_create_host_only(mptcc_ctx **out);
+/* What the broadphase structures answer for one pose box (box6 = min xyz, max xyz), looked up the way the kernels do:
+ * *n_listed = objects the structure lists for the box (the grid cell's entries / the objects of the clusters the tree
+ * walk reaches); return value = how many of those overlap the box under fcl::AABB::overlap (closed intervals), their
+ * world boxes written to aabbs (6 doubles each, at most cap).  -1: the structure does not exist for this scene
+ * (multi-link agent or non-finite boxes: no grid); -2 (grid): the box cannot be looked up (not finite, or wider than
+ * a cell) -- the kernels then fall back to the tree. */
+int mptcc_debug_grid_lookup(mptcc_ctx *ctx, const double *box6, double *aabbs, uint32_t cap, uint32_t *n_listed);
+int mptcc_debug_tree_lookup(mptcc_ctx *ctx, const double *box6, double *aabbs, uint32_t cap, uint32_t *n_listed);
+
 /* ---- host-side BVH introspection (no GPU needed; used by the CPU test-suite) ----------------- */
 typedef struct mptcc_bvh mptcc_bvh;
 int mptcc_bvh_build(const mptcc_mesh *mesh, mptcc_bvh **out);

@@ -31,6 +31,7 @@ EXPORTS = [
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option", "mptcc_get_info",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
     "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb", "mptcc_bvh_get_quantised_nodes",
+    "mptcc_debug_create_host_only", "mptcc_debug_grid_lookup", "mptcc_debug_tree_lookup",
 ]
 
 
@@ -120,6 +121,11 @@ def load():
     L.mptcc_bvh_get_nodes.argtypes = [vp, dp, dp, dp, i32p, i32p, i32p]
     L.mptcc_bvh_get_primitive_indices.restype = None
     L.mptcc_bvh_get_primitive_indices.argtypes = [vp, u32p]
+    L.mptcc_debug_create_host_only.restype = C.c_int
+    L.mptcc_debug_create_host_only.argtypes = [C.POINTER(vp)]
+    for fn in (L.mptcc_debug_grid_lookup, L.mptcc_debug_tree_lookup):
+        fn.restype = C.c_int
+        fn.argtypes = [vp, dp, dp, C.c_uint32, u32p]
     L.mptcc_bvh_get_quantised_nodes.restype = C.c_int
     L.mptcc_bvh_get_quantised_nodes.argtypes = [vp, C.c_int, u32p, u32p, dp]
     L.mptcc_bvh_get_local_aabb.restype = None
@@ -303,6 +309,34 @@ class Checker:
 
     def set_option(self, name, value):
         self._check(self.lib.mptcc_set_option(self.h, name.encode(), int(value)))
+
+
+class HostScene(Checker):
+    """A context WITHOUT devices (mptcc_debug_create_host_only): set_environment / set_agent build the host side of the
+    scene; grid_lookup / tree_lookup return what the broadphase structures answer for one pose box.  Tests only."""
+
+    def __init__(self):
+        self.lib = load()
+        h = C.c_void_p()
+        rc = self.lib.mptcc_debug_create_host_only(C.byref(h))
+        if rc != OK:
+            raise MptccError(rc, "mptcc_debug_create_host_only")
+        self.h = h
+        self.n_links = 0
+
+    def _lookup(self, fn, box6, cap=4096):
+        box = np.ascontiguousarray(box6, dtype=np.float64)
+        out = np.zeros((cap, 6))
+        listed = C.c_uint32(0)
+        n = fn(self.h, _dp(box), _dp(out), cap, C.byref(listed))
+        return n, out[:max(0, min(n, cap))], listed.value
+
+    def grid_lookup(self, box6):
+        """(count or -1 / -2, world boxes of the overlapping listed objects [count, 6], objects listed for the cell)"""
+        return self._lookup(self.lib.mptcc_debug_grid_lookup, box6)
+
+    def tree_lookup(self, box6):
+        return self._lookup(self.lib.mptcc_debug_tree_lookup, box6)
 
 
 class HostBvh:

@@ -1688,6 +1688,79 @@ int mptcc_set_option(mptcc_ctx *ctx, const char *name, long value) {
 	return MPTCC_OK;
 }
 
+// ---- host-only scene introspection (tests): a context without devices and the broadphase structures' answers ------
+int mptcc_debug_create_host_only(mptcc_ctx **out) {
+	if (!out) return MPTCC_ERR_INVALID;
+	*out = new mptcc_ctx;  // no Device: set_environment / set_agent only build the host side, every check fails with NO_DEVICE
+	return MPTCC_OK;
+}
+
+static int overlapping_of(const mptcc_ctx *ctx, const double *box6, const std::vector<uint32_t> &listed, double *aabbs, uint32_t cap) {
+	int n = 0;
+	for (uint32_t oi : listed) {
+		const DevObject &o = ctx->objects_h[oi];
+		bool ov = true;  // fcl::AABB::overlap: closed intervals
+		for (int k = 0; k < 3; ++k) ov = ov && !(o.aabb[k] > box6[3 + k]) && !(o.aabb[3 + k] < box6[k]);
+		if (!ov) continue;
+		if ((uint32_t)n < cap && aabbs) std::memcpy(aabbs + 6 * (size_t)n, o.aabb, 48);
+		++n;
+	}
+	return n;
+}
+
+int mptcc_debug_grid_lookup(mptcc_ctx *ctx, const double *box6, double *aabbs, uint32_t cap, uint32_t *n_listed) {
+	if (!ctx || !box6) return MPTCC_ERR_INVALID;
+	if (n_listed) *n_listed = 0;
+	if (ctx->grid_cells_h.empty()) return -1;
+	// the look-up of broadphase_grid_kernel (split_kernels.cu): the cell of the box's minimum corner
+	int c[3];
+	for (int k = 0; k < 3; ++k) {
+		const double lo = box6[k], hi = box6[3 + k];
+		const int a = grid_cell(lo, ctx->grid_origin[k], ctx->grid_inv[k], ctx->grid_n[k]);
+		const int b = grid_cell(hi, ctx->grid_origin[k], ctx->grid_inv[k], ctx->grid_n[k]);
+		if (!(std::fabs(lo) <= 1.7e308) || !(std::fabs(hi) <= 1.7e308) || b - a > 1 || b < a) return -2;
+		c[k] = a;
+	}
+	const uint2 hdr = ctx->grid_cells_h[((size_t)c[0] * ctx->grid_n[1] + c[1]) * ctx->grid_n[2] + c[2]];
+	std::vector<uint32_t> listed;
+	for (uint32_t e = 0; e < hdr.y; ++e) listed.push_back((uint32_t)ctx->grid_entries_h[hdr.x + e].obj);
+	if (n_listed) *n_listed = hdr.y;
+	return overlapping_of(ctx, box6, listed, aabbs, cap);
+}
+
+int mptcc_debug_tree_lookup(mptcc_ctx *ctx, const double *box6, double *aabbs, uint32_t cap, uint32_t *n_listed) {
+	if (!ctx || !box6) return MPTCC_ERR_INVALID;
+	if (n_listed) *n_listed = 0;
+	if (ctx->bp_nodes_h.empty()) return -1;
+	// the walk of the fused kernel / broadphase_kernel (collide_device.cuh: pose_world_box's outward-rounded fp32 box,
+	// quantize_pose_box, bp_tree_step)
+	int qmin[3], qmax[3];
+	for (int k = 0; k < 3; ++k) {
+		float amin = (float)box6[k], amax = (float)box6[3 + k];
+		if ((double)amin > box6[k]) amin = std::nextafterf(amin, -INFINITY);
+		if ((double)amax < box6[3 + k]) amax = std::nextafterf(amax, INFINITY);
+		const float lo = (amin - ctx->bp_origin[k]) * ctx->bp_inv_cell[k], hi = (amax - ctx->bp_origin[k]) * ctx->bp_inv_cell[k];
+		qmin[k] = (int)std::floor(std::fmin(std::fmax(lo, -2.0f), 65538.0f)) - 1;
+		qmax[k] = (int)std::ceil(std::fmax(std::fmin(hi, 65538.0f), -2.0f)) + 1;
+	}
+	std::vector<uint32_t> listed;
+	const uint32_t nn = (uint32_t)ctx->bp_nodes_h.size();
+	for (uint32_t node = 0; node < nn;) {
+		const uint4 nd = ctx->bp_nodes_h[node];
+		const int lx = (int)(nd.x & 0xffffu), ly = (int)(nd.x >> 16), lz = (int)(nd.y & 0xffffu);
+		const int hx = (int)(nd.y >> 16), hy = (int)(nd.z & 0xffffu), hz = (int)(nd.z >> 16);
+		const bool ov = !(lx > qmax[0] || ly > qmax[1] || lz > qmax[2] || hx < qmin[0] || hy < qmin[1] || hz < qmin[2]);
+		const bool leaf = (nd.w >> 31) != 0u;
+		if (ov && leaf) {
+			const uint32_t cl = nd.w & 0x7fffffffu;
+			for (uint32_t o = cl * kClusterSize; o < std::min<size_t>(ctx->objects_h.size(), (size_t)(cl + 1) * kClusterSize); ++o) listed.push_back(o);
+		}
+		node = (leaf || ov) ? node + 1u : nd.w;
+	}
+	if (n_listed) *n_listed = (uint32_t)listed.size();
+	return overlapping_of(ctx, box6, listed, aabbs, cap);
+}
+
 // ---- host-only BVH introspection -------------------------------------------------------------------
 int mptcc_bvh_build(const mptcc_mesh *mesh, mptcc_bvh **out) {
 	if (!mesh || !out) return MPTCC_ERR_INVALID;

@@ -470,6 +470,54 @@ def test_fused_kernel_fp32_filters_are_one_sided_against_the_oracle(built, tmp_p
     assert tri_certain >= 0.25 * tri_deep, (tri_certain, tri_deep)            # crossing half-way in: a good part "certain contact"
 
 
+def test_broadphase_grid_and_tree_list_every_overlapping_object(built):
+    """The candidate set: for any pose, the objects whose world AABB overlaps the agent's (FCL's closed-interval
+    AABB::overlap, what the dynamic AABB tree reports) must all be in what the broadphase structures list for the pose box --
+    the grid cell of its minimum corner, and the clusters the threaded tree walk reaches.  Built on the host by a context
+    without devices, looked up the way the kernels do, compared with the oracle's object boxes."""
+    rng = np.random.default_rng(31337)
+    agent = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    om = O.Model(*agent)
+    for env, rot in ((scenes.synthetic_environment(160), None), (meshio.environment_submeshes(meshio.load_mptm("divider")), None),
+                     (meshio.environment_submeshes(meshio.load_mptm("divider")), (0.3, -0.2, 0.1, 0.9, 0.1, -0.3, 0.2))):
+        pose7 = (0, 0, 0, 1, 0, 0, 0) if rot is None else tuple(np.concatenate([rot[:3], np.array(rot[3:]) / np.linalg.norm(rot[3:])]))
+        hs = capi.HostScene()
+        hs.set_environment(env, pose7)
+        hs.set_agent([agent])
+        with pytest.raises(capi.MptccError):               # no device: nothing can be checked with it
+            hs.check_poses(np.zeros((1, 12)))
+        oenv = O.Environment([O.Model(v, t) for v, t in env], pose7)
+        boxes = np.array([oenv.object_aabb(i) for i in range(len(env))])
+        lo, hi = boxes[:, :3].min(0), boxes[:, 3:].max(0)
+        n_pairs = n_grid_listed = 0
+        for k in range(1500):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            if k % 7 == 0:
+                q = np.array([1.0, 0, 0, 0])               # identity quaternion: the tight box instead of the sphere box
+            T = rng.uniform(lo - 2.0, hi + 2.0)
+            if k % 3 == 0:                                  # ... and boxes that just touch an object's box
+                b = boxes[rng.integers(len(boxes))]
+                T = b[rng.integers(2) * 3:][:3] + rng.normal(size=3) * 0.5
+            pb = om.object_aabb(np.concatenate([T, q]), O.POSE_TQ7)
+            want = {tuple(b) for b in boxes if np.all(b[:3] <= pb[3:]) and np.all(b[3:] >= pb[:3])}
+            n_pairs += len(want)
+            ng, got_g, listed_g = hs.grid_lookup(pb)
+            nt, got_t, listed_t = hs.tree_lookup(pb)
+            assert nt >= 0 and {tuple(b) for b in got_t} == want, (k, nt, len(want))
+            assert ng == -2 or (ng >= 0 and {tuple(b) for b in got_g} == want), (k, ng, len(want))
+            assert ng != -2                                  # finite poses inside the scene are always grid-addressable
+            n_grid_listed += listed_g
+        assert n_pairs > 500 and n_grid_listed >= n_pairs
+        # an exactly touching box (closed intervals) is a candidate; a box one ulp away is not
+        b = boxes[0]
+        touch = np.concatenate([[b[3], b[1], b[2]], [b[3] + 0.5, b[4], b[5]]])
+        away = touch.copy(); away[0] = np.nextafter(b[3], np.inf)
+        assert tuple(b) in {tuple(x) for x in hs.tree_lookup(touch)[1]} and tuple(b) not in {tuple(x) for x in hs.tree_lookup(away)[1]}
+        g = hs.grid_lookup(touch)
+        assert g[0] == -2 or tuple(b) in {tuple(x) for x in g[1]}
+        hs.close()
+
+
 def test_empty_mesh_is_rejected(built):
     with pytest.raises(capi.MptccError):
         capi.HostBvh(np.zeros((0, 3)), np.zeros((0, 3), np.uint32))
