@@ -66,6 +66,43 @@ unsigned host_pair_disjoint_q(const uint32_t *s, const uint32_t *c0, const uint3
 	float2 d2;
 	return pair_disjoint<true>(f, C2, S.v3, d2);
 }
+// the same step on 64-byte fp32 nodes (np3 / np2 with qnode = 0): s, c0, c1 = four float4 each (node32 layout)
+static mptcc::Node node_of(const float *p) {
+	const float4 *q = reinterpret_cast<const float4 *>(p);
+	return mptcc::Node{q[0], q[1], q[2], q[3]};
+}
+unsigned host_pair_disjoint_f32(const float *s, const float *c0, const float *c1, const float *rec16, int env_side) {
+	using namespace mptcc;
+	const Node S = node_of(s);
+	const Node2 C2 = pack_nodes(node_of(c0), node_of(c1));
+	const float4 r0{rec16[0], rec16[1], rec16[2], rec16[3]}, r1{rec16[4], rec16[5], rec16[6], rec16[7]};
+	const float4 r2{rec16[8], rec16[9], rec16[10], rec16[11]}, r3{rec16[12], rec16[13], rec16[14], rec16[15]};
+	const StepFrame f = step_frame(r0, r1, r2, r3, env_side != 0, S);
+	float2 d2;
+	return pair_disjoint<false>(f, C2, S.v3, d2);
+}
+// the scalar 15-axis test of the np2 kernel (child_disjoint / sat15) on the two children, fp32 nodes or quantised nodes
+unsigned host_child_disjoint(const void *s, const void *c0, const void *c1, const float *rec16, int env_side, int quantised) {
+	using namespace mptcc;
+	Node S, C[2];
+	if (quantised) {
+		const uint32_t *w[3] = {static_cast<const uint32_t *>(s), static_cast<const uint32_t *>(c0), static_cast<const uint32_t *>(c1)};
+		Node *dst[3] = {&S, &C[0], &C[1]};
+		for (int k = 0; k < 3; ++k) *dst[k] = node_decode(uint4{w[k][0], w[k][1], w[k][2], w[k][3]}, uint4{w[k][4], w[k][5], w[k][6], w[k][7]});
+	} else {
+		S = node_of(static_cast<const float *>(s));
+		C[0] = node_of(static_cast<const float *>(c0));
+		C[1] = node_of(static_cast<const float *>(c1));
+	}
+	const float4 r0{rec16[0], rec16[1], rec16[2], rec16[3]}, r1{rec16[4], rec16[5], rec16[6], rec16[7]};
+	const float4 r2{rec16[8], rec16[9], rec16[10], rec16[11]}, r3{rec16[12], rec16[13], rec16[14], rec16[15]};
+	const StepFrame f = step_frame(r0, r1, r2, r3, env_side != 0, S);
+	float d2;
+	unsigned m = 0u;
+	for (int k = 0; k < 2; ++k)
+		m |= (quantised ? child_disjoint<true>(f, C[k], S.v3, d2) : child_disjoint<false>(f, C[k], S.v3, d2)) ? 1u << k : 0u;
+	return m;
+}
 // the scalar decode and the two-wide decode must agree: returns the largest difference over axes, centres and extents
 float host_decode_difference(const uint32_t *a, const uint32_t *b) {
 	using namespace mptcc;

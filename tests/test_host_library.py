@@ -140,6 +140,10 @@ def _host_sat(tmp_path):
     L.host_pair_disjoint_q.argtypes = [u32p, u32p, u32p, f32p, ctypes.c_int]
     L.host_decode_difference.restype = ctypes.c_float
     L.host_decode_difference.argtypes = [u32p, u32p]
+    L.host_pair_disjoint_f32.restype = ctypes.c_uint
+    L.host_pair_disjoint_f32.argtypes = [f32p, f32p, f32p, f32p, ctypes.c_int]
+    L.host_child_disjoint.restype = ctypes.c_uint
+    L.host_child_disjoint.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, f32p, ctypes.c_int, ctypes.c_int]
     return L
 
 
@@ -147,7 +151,9 @@ def test_fp32_obb_filter_is_one_sided_against_the_oracle(built, tmp_path):
     """The narrowphase's fast pass (quantised nodes, child-frame two-wide SAT on 11 axes, margins of DESIGN.md section 6),
     compiled for the CPU from the kernel's own header, against FCL's fp64 obbDisjoint as the oracle restates it: on box
     pairs pushed to the edge of touching, "certainly disjoint" must never be said of a pair FCL finds overlapping -- in
-    either descent direction -- and the filter must still catch nearly all pairs that are clearly apart."""
+    either descent direction -- and the filter must still catch nearly all pairs that are clearly apart.  The same for the
+    variants the options select: the two-wide test on 64-byte fp32 nodes (qnode = 0) and the scalar 15-axis test of the np2
+    kernel on either node format."""
     L = _host_sat(tmp_path)
     u32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
     f32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
@@ -157,9 +163,12 @@ def test_fp32_obb_filter_is_one_sided_against_the_oracle(built, tmp_path):
     hbA = capi.HostBvh(av, at)
     wA, devA, ctrA, okA = hbA.quantised_nodes(True)
     ndA = hbA.nodes()
-    wrong = caught = apart = checked = 0
+    n32A = _device_model(av, at)["node32"]
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    wrong = caught = apart = checked = wrong_variants = 0
     for ev, et in envs:
         hbE = capi.HostBvh(ev, et)
+        n32E = _device_model(ev, et)["node32"]
         wE, devE, ctrE, okE = hbE.quantised_nodes(False)
         ndE = hbE.nodes()
         assert okA and okE
@@ -195,14 +204,25 @@ def test_fp32_obb_filter_is_one_sided_against_the_oracle(built, tmp_path):
                 # children = environment nodes i, i2 against the agent node j; then children = agent nodes j, j2 against i
                 m_env = L.host_pair_disjoint_q(u32(wA[devA[j]].copy()), u32(wE[devE[i]].copy()), u32(wE[devE[i2]].copy()), f32(rec), 1)
                 m_ag = L.host_pair_disjoint_q(u32(wE[devE[i]].copy()), u32(wA[devA[j]].copy()), u32(wA[devA[j2]].copy()), f32(rec), 0)
+                truth = {}
                 for said_disjoint, (x, y) in ((m_env & 1, (i, j)), (m_env & 2, (i2, j)), (m_ag & 1, (i, j)), (m_ag & 2, (i, j2))):
-                    overlap = O.obb_overlap(R, T, bE(x), bA(y))
+                    overlap = truth[(x, y)] = O.obb_overlap(R, T, bE(x), bA(y))
                     checked += 1
                     wrong += bool(said_disjoint) and overlap
                     if (x, y) == (i, j) and t >= hi * 1.05:
                         apart += 1
                         caught += bool(said_disjoint)
-    assert checked > 20000 and wrong == 0, (checked, wrong)
+                # fp32 nodes two-wide, then the scalar 15-axis test on fp32 and on quantised nodes
+                sA, sE = np.ascontiguousarray(n32A[j]), np.ascontiguousarray(n32E[i])
+                cE, cE2 = np.ascontiguousarray(n32E[i]), np.ascontiguousarray(n32E[i2])
+                cA, cA2 = np.ascontiguousarray(n32A[j]), np.ascontiguousarray(n32A[j2])
+                qa, qa2, qe, qe2 = (wA[devA[j]].copy(), wA[devA[j2]].copy(), wE[devE[i]].copy(), wE[devE[i2]].copy())
+                for m1, m2 in ((L.host_pair_disjoint_f32(f32(sA), f32(cE), f32(cE2), f32(rec), 1), L.host_pair_disjoint_f32(f32(sE), f32(cA), f32(cA2), f32(rec), 0)),
+                               (L.host_child_disjoint(vp(sA), vp(cE), vp(cE2), f32(rec), 1, 0), L.host_child_disjoint(vp(sE), vp(cA), vp(cA2), f32(rec), 0, 0)),
+                               (L.host_child_disjoint(vp(qa), vp(qe), vp(qe2), f32(rec), 1, 1), L.host_child_disjoint(vp(qe), vp(qa), vp(qa2), f32(rec), 0, 1))):
+                    for said_disjoint, key in ((m1 & 1, (i, j)), (m1 & 2, (i2, j)), (m2 & 1, (i, j)), (m2 & 2, (i, j2))):
+                        wrong_variants += bool(said_disjoint) and truth[key]
+    assert checked > 20000 and wrong == 0 and wrong_variants == 0, (checked, wrong, wrong_variants)
     assert caught >= 0.9 * apart, (caught, apart)             # (5 % and 50 % beyond touching along d: the filter is not vacuous)
 
 
