@@ -772,6 +772,7 @@ __device__ __forceinline__ void pose_world_box(const double *rec, uint32_t fmt, 
 }
 // [host-test:end]
 
+// [host-test:begin]
 // Phase C2 for one candidate: fp64 relativeTransform of (object, pose) -> fp32 record in the recentred
 // frames: R (9), T (3), S, pose slot, node_base and tri_base of the object's model.
 __device__ __forceinline__ void make_candidate_record(const KernelParams &p, const double *pose_rec, const DevObject &ob,
@@ -876,6 +877,7 @@ __device__ __forceinline__ bool make_candidate_record2(const KernelParams &p, co
 	decode_pose(pose_rec, p.pose_format, R2, T2, q, false);
 	return make_candidate_record2_rt(p, R2, T2, ob, m2, rec, rel64, base, cert);
 }
+// [host-test:end]
 
 // Pose box -> the integer grid of the broadphase tree (device_layout.hpp), rounded outward by one extra cell
 // (the fp32 evaluation of (x - origin) * inv_cell is off by < 0.02 cells).  Non-finite boxes keep the old

@@ -12,6 +12,9 @@ struct float2 { float x, y; };
 struct float4 { float x, y, z, w; };
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
+static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+static inline uint2 make_uint2(uint32_t x, uint32_t y) { return uint2{x, y}; }
+static inline float __uint_as_float(uint32_t u) { float f; __builtin_memcpy(&f, &u, 4); return f; }
 // double -> float rounded towards -inf / +inf
 static inline float __double2float_rd(double x) { const float f = (float)x; return (double)f <= x ? f : std::nextafterf(f, -INFINITY); }
 static inline float __double2float_ru(double x) { const float f = (float)x; return (double)f >= x ? f : std::nextafterf(f, INFINITY); }
@@ -57,6 +60,34 @@ void host_pose_world_box(const double *rec, unsigned fmt, const double *model10,
 	double box[6 * 32];
 	mptcc::pose_world_box(rec, fmt, m, box, amin3, amax3);
 	for (int k = 0; k < 6; ++k) box6[k] = box[k * 32];
+}
+// The candidate record of the np2 / np3 pipeline as the broadphase kernel builds it (make_candidate_record2): obj13 = the
+// object's R (9), T (3) and its identity flag; m1 = the object's model (ctr 3, rinf, cmax1, esum), m2 = the agent's (ctr 3,
+// r2, cmax1, esum).  Out: rec16 = R (9), Tc (3), Tinv (3), S; rel12 = FCL's fp64 relative transform; the path-certificate
+// threshold.  Returns 1 if the pose passed the rigidity test.
+int host_candidate_record2(const double *obj13, const double *m1v, const double *m2v, const double *pose, unsigned fmt, float *rec16,
+                           double *rel12, float *cert) {
+	using namespace mptcc;
+	DevObject ob{};
+	for (int k = 0; k < 9; ++k) ob.R[k] = obj13[k];
+	for (int k = 0; k < 3; ++k) ob.T[k] = obj13[9 + k];
+	ob.identity = obj13[12] != 0.0 ? 1u : 0u;
+	ob.model = 0;
+	DevModel m1{}, m2{};
+	for (int k = 0; k < 3; ++k) {
+		m1.ctr[k] = m1v[k];
+		m2.ctr[k] = m2v[k];
+	}
+	m1.rinf = (float)m1v[3]; m1.cmax1 = m1v[4]; m1.esum = m1v[5];
+	m2.r2 = (float)m2v[3]; m2.cmax1 = m2v[4]; m2.esum = m2v[5];
+	KernelParams p{};
+	p.env.models = &m1;
+	p.pose_format = fmt;
+	float4 rec[4];
+	uint2 base;
+	const bool rigid = make_candidate_record2(p, pose, ob, m2, rec, rel12, base, cert);
+	__builtin_memcpy(rec16, rec, 64);
+	return rigid ? 1 : 0;
 }
 // relativeTransform(tf1 = object (R1 9, T1 3), tf2 = pose (R2 9, T2 3)) -> R (9), T (3)
 void host_relative_transform(const double *R1, const double *T1, const double *R2, const double *T2, double *out12) {

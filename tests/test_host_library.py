@@ -231,8 +231,9 @@ def _host_filters(tmp_path):
     here = os.path.dirname(os.path.abspath(__file__))
     src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
     regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
-    assert len(regions) == 6 and "exact_obb_disjoint" in regions[0] and "exact_tri_intersect_warp" in regions[1]
+    assert len(regions) == 7 and "exact_obb_disjoint" in regions[0] and "exact_tri_intersect_warp" in regions[1]
     assert "tri_filter_f32" in regions[3] and "obb_disjoint_f32" in regions[3] and "rel_element" in regions[4] and "pose_world_box" in regions[5]
+    assert "make_candidate_record2_rt" in regions[6]
     (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
     cpp = tmp_path / "host_filters.cpp"
     cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
@@ -251,6 +252,8 @@ def _host_filters(tmp_path):
     L.host_exact_obb_disjoint.argtypes = [f64p, f64p, f64p]
     L.host_exact_tri_intersect.restype = ctypes.c_int
     L.host_exact_tri_intersect.argtypes = [f64p, f64p, f64p]
+    L.host_candidate_record2.restype = ctypes.c_int
+    L.host_candidate_record2.argtypes = [f64p, f64p, f64p, f64p, ctypes.c_uint, f32p, f64p, f32p]
     L.host_pose_world_box.restype = None
     L.host_pose_world_box.argtypes = [f64p, ctypes.c_uint, f64p, f64p, f32p, f32p]
     L.host_relative_transform.restype = None
@@ -488,6 +491,54 @@ def test_fused_kernel_fp32_filters_are_one_sided_against_the_oracle(built, tmp_p
     assert tri_checked > 5000 and tri_wrong == 0, (tri_checked, tri_wrong)
     assert tri_settled >= 0.9 * tri_clear, (tri_settled, tri_clear)            # clearly apart: "separated"
     assert tri_certain >= 0.25 * tri_deep, (tri_certain, tri_deep)            # crossing half-way in: a good part "certain contact"
+
+
+def test_candidate_record_of_the_broadphase_kernel(built, tmp_path):
+    """make_candidate_record2 (collide_device.cuh) compiled for the CPU: the fp64 relative transform it passes on is the
+    oracle's relativeTransform bit for bit (for an object at the identity: the pose itself), the fp32 record is that
+    transform in the recentred frames rounded once (R, Tc) with the inverse translation, the triangle-filter scale and the
+    path-certificate threshold on the safe side, and poses that are not rigid are flagged."""
+    L = _host_filters(tmp_path)
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    f32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rng = np.random.default_rng(5150)
+    ulp = lambda x: np.abs(np.nextafter(np.float32(x), np.float32(np.inf)) - np.float32(x)).astype(np.float64)
+    for k in range(4000):
+        ident = k % 2 == 0
+        q1 = np.array([1.0, 0, 0, 0]) if ident else rng.normal(size=4)
+        q1 /= np.linalg.norm(q1)
+        T1 = np.zeros(3) if ident else rng.normal(size=3) * 5
+        q2 = rng.normal(size=4); q2 /= np.linalg.norm(q2)
+        T2 = rng.normal(size=3) * 10.0 ** rng.integers(-2, 3)
+        R1, _, _ = O.pose_decode(np.concatenate([T1, q1]), O.POSE_TQ7)
+        c1, c2 = rng.normal(size=3) * 3, rng.normal(size=3)
+        rinf, r2 = abs(rng.normal()) * 2 + 0.1, abs(rng.normal()) * 2 + 0.1
+        m1v = np.array([*c1, np.float32(rinf), 3.0, 2.0]); m2v = np.array([*c2, np.float32(r2), 1.5, 0.7])
+        obj13 = np.array([*R1.ravel(), *T1, 1.0 if ident else 0.0])
+        pose = np.concatenate([T2, q2])
+        rec, rel, cert = np.empty(16, np.float32), np.empty(12), np.empty(1, np.float32)
+        rigid = L.host_candidate_record2(f64(obj13), f64(m1v), f64(m2v), f64(pose), 1, f32(rec), f64(rel), f32(cert))
+        Ro, To = O.relative_transform(np.concatenate([T1, q1]), pose, O.POSE_TQ7, O.POSE_TQ7)
+        assert rigid == 1 and np.array_equal(rel[:9], Ro.ravel()) and np.array_equal(rel[9:], To)
+        assert np.array_equal(rec[:9], Ro.ravel().astype(np.float32))
+        tc = Ro @ c2 + To - c1
+        assert np.all(np.abs(rec[9:12].astype(np.float64) - tc) <= ulp(tc) + 1e-15 * np.abs(tc).max())
+        ti = -(Ro.T @ tc)
+        assert np.all(np.abs(rec[12:15].astype(np.float64) - ti) <= ulp(ti) + 4e-15 * np.abs(tc).sum())
+        tinf = np.abs(rec[9:12]).max()
+        assert rec[15] >= max(5.01 * np.float32(r2) + 4.0 * tinf, np.float32(rinf)) + np.float32(rinf) * (1 - 1e-6)
+        mag = np.abs(tc).sum() + np.abs(c1).sum() + 1.75 * np.abs(c2).sum() + 3.0 + 1.5 + 2.0 + 0.7
+        assert cert[0] >= 1e-5 * mag
+        # the records the filter tests above build in numpy are this record
+        r16 = np.concatenate([Ro.ravel(), tc, ti, [0.0]]).astype(np.float32)
+        assert np.all(np.abs(r16[:15].astype(np.float64) - rec[:15].astype(np.float64)) <= ulp(r16[:15]) + 1e-12)
+    # not rigid: a scaled, a sheared and a NaN rotation block (RT12 records)
+    for bad in (np.eye(3) * (1 + 1e-9), np.array([[1, 1e-8, 0], [0, 1, 0], [0, 0, 1.0]]), np.full((3, 3), np.nan)):
+        pose = np.concatenate([bad.ravel(), [0.1, 0.2, 0.3]])
+        rec, rel, cert = np.empty(16, np.float32), np.empty(12), np.empty(1, np.float32)
+        obj13 = np.array([*np.eye(3).ravel(), 0, 0, 0, 1.0])
+        assert L.host_candidate_record2(f64(obj13), f64(np.array([0, 0, 0, 1.0, 1, 1])), f64(np.array([0, 0, 0, 1.0, 1, 1])), f64(pose), 0,
+                                        f32(rec), f64(rel), f32(cert)) == 0
 
 
 def test_broadphase_grid_and_tree_list_every_overlapping_object(built):
