@@ -1,5 +1,13 @@
 """CPU tests of libmptcc's host side: the C ABI surface, the host BVH builder (must be bit-identical to
-the oracle's restatement of FCL's builder), failure modes without a GPU, and the sharding helpers."""
+the oracle's restatement of FCL's builder), failure modes without a GPU, and the sharding helpers.
+
+Device code without a device: the arithmetic of the kernels -- pose decoding, object boxes, relative transform, candidate
+record, the exact fp64 OBB and triangle tests, the fp32 OBB and triangle filters, the quantised-node fast pass -- lives in
+headers (csrc/collide_device.cuh between [host-test:begin] / [host-test:end], csrc/np_sat.cuh) that tests/host_filters.cpp
+and tests/host_sat.cpp compile for the CPU with stand-ins for the CUDA types; those functions are compared with the oracle
+here (bit for bit where they restate FCL, for one-sidedness where they are conservative filters), and the broadphase grid
+and cluster tree are built by a context without devices and checked for completeness.  What only runs on the GPU -- the
+traversal itself -- is covered by the -m gpu tests."""
 import ctypes
 import os
 import re
