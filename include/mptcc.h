@@ -210,6 +210,10 @@ void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out);
  * could be quantised within the bounds of DESIGN.md section 6, 0 if the pack would fall back to fp32 nodes, -1 on
  * bad arguments. */
 int mptcc_bvh_get_quantised_nodes(const mptcc_bvh *b, int breadth_first, uint32_t *words, uint32_t *device_id, double *ctr3);
+/* The arrays of the exact pass for this model (csrc/device_layout.hpp): node64 [n][16] (FCL's OBB verbatim + size, device
+ * numbering) and anc [num_tris][*depth] (root-to-leaf node chain per triangle, unused levels 0xffffffff); either may be
+ * NULL.  Returns 0, -1 on bad arguments. */
+int mptcc_bvh_get_exact_arrays(const mptcc_bvh *b, int breadth_first, double *node64, uint32_t *anc, uint32_t *depth);
 /* aabb6 = min xyz, max xyz */
 void mptcc_bvh_get_local_aabb(const mptcc_bvh *b, double *aabb6, double *center3, double *radius);
 

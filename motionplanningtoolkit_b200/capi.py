@@ -30,7 +30,7 @@ EXPORTS = [
     "mptcc_synchronize", "mptcc_alloc_pinned", "mptcc_free_pinned", "mptcc_enable_counters",
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option", "mptcc_get_info",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
-    "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb", "mptcc_bvh_get_quantised_nodes",
+    "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb", "mptcc_bvh_get_quantised_nodes", "mptcc_bvh_get_exact_arrays",
     "mptcc_debug_create_host_only", "mptcc_debug_grid_lookup", "mptcc_debug_tree_lookup",
 ]
 
@@ -126,6 +126,8 @@ def load():
     for fn in (L.mptcc_debug_grid_lookup, L.mptcc_debug_tree_lookup):
         fn.restype = C.c_int
         fn.argtypes = [vp, dp, dp, C.c_uint32, u32p]
+    L.mptcc_bvh_get_exact_arrays.restype = C.c_int
+    L.mptcc_bvh_get_exact_arrays.argtypes = [vp, C.c_int, dp, u32p, u32p]
     L.mptcc_bvh_get_quantised_nodes.restype = C.c_int
     L.mptcc_bvh_get_quantised_nodes.argtypes = [vp, C.c_int, u32p, u32p, dp]
     L.mptcc_bvh_get_local_aabb.restype = None
@@ -382,6 +384,16 @@ class HostBvh:
         if rc < 0:
             raise MptccError(rc, "mptcc_bvh_get_quantised_nodes")
         return words, dev, ctr, bool(rc)
+
+    def exact_arrays(self, breadth_first=False):
+        """(node64 [n, 16], anc [num_tris, depth]): what the exact pass reads for this model."""
+        u32 = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint32))
+        depth = C.c_uint32(0)
+        self.lib.mptcc_bvh_get_exact_arrays(self.h, int(breadth_first), None, None, C.byref(depth))
+        node64 = np.zeros((self.num_nodes, 16)); anc = np.zeros((self.nt, depth.value), np.uint32)
+        if self.lib.mptcc_bvh_get_exact_arrays(self.h, int(breadth_first), _dp(node64), u32(anc), C.byref(depth)) != 0:
+            raise MptccError(ERR_INVALID, "mptcc_bvh_get_exact_arrays")
+        return node64, anc
 
     def primitive_indices(self):
         out = np.empty(self.nt, np.uint32)

@@ -331,6 +331,7 @@ __device__ __noinline__ bool exact_tri_intersect_warp(const double *__restrict__
 }
 // [host-test:end]
 
+// [host-test:begin]
 // Replays FCL's collisionRecurse descent from (root, root) to the leaf pair holding primitives
 // (prim1, prim2) and evaluates every OBB test on the way in fp64 [FCL-recalled C.7, C.8].
 // Returns true iff none of them reports "disjoint", i.e. iff FCL's traversal reaches that leaf pair.
@@ -387,6 +388,7 @@ __device__ __noinline__ bool exact_path_reaches(const KernelParams &p, const Dev
 	}
 	return !disjoint_any;
 }
+// [host-test:end]
 
 // ------------------------------------------------------------------------------------------------
 // fp32 conservative tests (hot path)

@@ -1815,6 +1815,17 @@ int mptcc_bvh_get_quantised_nodes(const mptcc_bvh *b, int breadth_first, uint32_
 	return pk.q_ok ? 1 : 0;
 }
 
+int mptcc_bvh_get_exact_arrays(const mptcc_bvh *b, int breadth_first, double *node64, uint32_t *anc, uint32_t *depth) {
+	if (!b || !depth) return -1;
+	HostPack pk;
+	pk.add(b->b, breadth_first != 0);
+	const DevModel &m = pk.models[0];
+	*depth = m.depth;
+	if (node64) std::memcpy(node64, pk.node64.data() + 16 * (size_t)m.node_base, sizeof(double) * 16 * b->b.num_nodes());
+	if (anc) std::memcpy(anc, pk.anc.data() + m.anc_base, sizeof(uint32_t) * (size_t)m.num_tris * m.depth);
+	return 0;
+}
+
 void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out) {
 	std::memcpy(out, b->b.primitive_indices.data(), sizeof(uint32_t) * b->b.primitive_indices.size());
 }

@@ -807,6 +807,9 @@ typedef struct {
 	double T[3];
 	int num_contacts; /* CollisionResult::numContacts(), num_max_contacts = 1, enable_contact = false */
 	orc_counters *ctr;
+	/* test probe (orc_path_reaches): the traversal does not test triangles or stop, it only notes whether it reaches the
+	 * leaf pair of these two primitives */
+	int probe, probe_prim1, probe_prim2, probe_hit;
 } trav;
 
 static void collision_recurse(trav *tv, int b1, int b2) {
@@ -817,6 +820,10 @@ static void collision_recurse(trav *tv, int b1, int b2) {
 	if (l1 && l2) {
 		tv->ctr->n_bv_tests++;
 		if (!obb_overlap(&tv->R, tv->T, n1, n2)) return;
+		if (tv->probe) {
+			if (-(n1->first_child + 1) == tv->probe_prim1 && -(n2->first_child + 1) == tv->probe_prim2) tv->probe_hit = 1;
+			return;
+		}
 		/* meshCollisionOrientedNodeLeafTesting, enable_contact == false */
 		tv->ctr->n_leaf_tests++;
 		const uint32_t *t1 = tv->m1->tri + 3 * (size_t)(-(n1->first_child + 1));
@@ -859,6 +866,26 @@ static void relative_transform(const xform *t1, const xform *t2, mat3 *R, double
 	T[0] = tdot(&t1->R, 0, temp);
 	T[1] = tdot(&t1->R, 1, temp);
 	T[2] = tdot(&t1->R, 2, temp);
+}
+
+/* Does collisionRecurse on (m1, m2) under x1 = R x2 + T reach the leaf pair holding triangles (prim1, prim2), i.e. do all
+ * the OBB tests on FCL's way down to it report an overlap?  (tests: the device code's path replay against it) */
+int orc_path_reaches(const orc_model *m1, const orc_model *m2, const double *R, const double *T, int prim1, int prim2) {
+	trav tv;
+	orc_counters c;
+	memset(&c, 0, sizeof c);
+	tv.m1 = m1;
+	tv.m2 = m2;
+	memcpy(tv.R.m, R, sizeof(double) * 9);
+	memcpy(tv.T, T, sizeof(double) * 3);
+	tv.num_contacts = 0;
+	tv.ctr = &c;
+	tv.probe = 1;
+	tv.probe_prim1 = prim1;
+	tv.probe_prim2 = prim2;
+	tv.probe_hit = 0;
+	collision_recurse(&tv, 0, 0);
+	return tv.probe_hit;
 }
 
 /* relativeTransform(tf1, tf2) of two pose records (tests: the device code's rel_element against it) */
@@ -934,6 +961,7 @@ static int collision_callback(cdata *cd, int env_obj, int agent_obj) {
 		tv.m1 = cd->env->models[env_obj];
 		tv.m2 = cd->links[agent_obj % cd->n_links];
 		tv.num_contacts = cd->num_contacts;
+		tv.probe = 0;
 		tv.ctr = cd->ctr;
 		cd->ctr->n_obj_pairs++;
 		relative_transform(&cd->env->tf[env_obj], &cd->agent_tf[agent_obj], &tv.R, tv.T);
@@ -1044,6 +1072,7 @@ int orc_self_collision(int n_links, orc_model *const *links, const double *pose_
 			tv.m1 = links[a];
 			tv.m2 = links[b];
 			tv.num_contacts = 0;
+			tv.probe = 0;
 			tv.ctr = ctr;
 			ctr->n_obj_pairs++;
 			relative_transform(&tf[a], &tf[b], &tv.R, tv.T);

@@ -99,6 +99,8 @@ int orc_obb_overlap(const double *R0, const double *T0, const double *axis1, con
 int orc_tri_intersect(const double *P /*[9]*/, const double *Q /*[9]*/, const double *R, const double *T);
 /* Transform helpers: fill R[9], T[3], q[4] from a pose record. */
 void orc_pose_decode(const double *rec, int pose_format, double *R, double *T, double *q);
+/* 1 iff collisionRecurse on (m1, m2) under x1 = R x2 + T reaches the leaf pair of triangles (prim1, prim2) */
+int orc_path_reaches(const orc_model *m1, const orc_model *m2, const double *R, const double *T, int prim1, int prim2);
 /* fcl::relativeTransform(tf1, tf2) of two pose records: R = R1^T R2, T = R1^T (T2 - T1) */
 void orc_relative_transform(const double *rec1, int fmt1, const double *rec2, int fmt2, double *R, double *T);
 /* CollisionObject::computeAABB for a model under a pose record. */

@@ -69,6 +69,8 @@ def lib():
         L.orc_tri_intersect.restype = C.c_int
         L.orc_tri_intersect.argtypes = [dp] * 4
         L.orc_pose_decode.argtypes = [dp, C.c_int, dp, dp, dp]
+        L.orc_path_reaches.restype = C.c_int
+        L.orc_path_reaches.argtypes = [vp, vp, dp, dp, C.c_int, C.c_int]
         L.orc_relative_transform.restype = None
         L.orc_relative_transform.argtypes = [dp, C.c_int, dp, C.c_int, dp, dp]
         L.orc_object_aabb.argtypes = [vp, dp, C.c_int, dp]
@@ -226,6 +228,11 @@ def obb_overlap(R0, T0, b1, b2):
 def tri_intersect(P, Q, R=np.eye(3), T=np.zeros(3)):
     a = [_f64(x) for x in (P, Q, R, T)]
     return bool(lib().orc_tri_intersect(*[_dp(x) for x in a]))
+
+
+def path_reaches(m1, m2, R, T, prim1, prim2):
+    """Does FCL's collisionRecurse on (m1, m2) under x1 = R x2 + T reach the leaf pair of triangles (prim1, prim2)?"""
+    return bool(lib().orc_path_reaches(m1.h, m2.h, _dp(_f64(R)), _dp(_f64(T)), int(prim1), int(prim2)))
 
 
 def relative_transform(rec1, rec2, fmt1=POSE_RT12, fmt2=POSE_RT12):

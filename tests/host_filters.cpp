@@ -24,14 +24,58 @@ static inline double __dadd_rn(double a, double b) { return a + b; }
 
 #include "device_layout.hpp"
 
-// exact_tri_intersect_warp ends in one ballot over the 17 lanes that each test one axis: the stand-in records the calling
-// lane's predicate, host_exact_tri_intersect calls the function once per lane and forms the ballot itself
-static int g_lane = 0;
-static bool g_pred[32];
-static inline unsigned __ballot_sync(unsigned, bool pred) {
-	g_pred[g_lane] = pred;
-	return 0u;
+// ---- warp-synchronous device functions on the CPU -------------------------------------------------------------------
+// A converged warp is replayed lane by lane: every warp intrinsic is an "exchange site"; in pass n each lane runs from the
+// start up to site n, leaves its operand there and stops (exception), so after the pass site n holds all 32 operands and
+// pass n + 1 can read it.  The functions tested have warp-uniform control flow, i.e. every lane passes the same sites.
+#include <array>
+#include <cstring>
+#include <vector>
+namespace simt {
+struct Stop {};
+static int lane = 0, site = 0, ready = 0;
+static std::vector<std::array<uint64_t, 32>> table;
+static inline int exchange(uint64_t mine) {
+	const int s = site++;
+	if ((int)table.size() <= s) table.resize((size_t)s + 1);
+	table[(size_t)s][(size_t)lane] = mine;
+	if (s >= ready) throw Stop{};
+	return s;
 }
+template <class F>
+static void run_warp(F f) {  // f(lane) is called until every lane runs to its end
+	table.clear();
+	for (ready = 0;; ++ready) {
+		bool done = true;
+		for (lane = 0; lane < 32; ++lane) {
+			site = 0;
+			try {
+				f(lane);
+			} catch (const Stop &) {
+				done = false;
+			}
+		}
+		if (done) return;
+	}
+}
+}  // namespace simt
+static inline unsigned __ballot_sync(unsigned, bool pred) {
+	const int s = simt::exchange(pred ? 1u : 0u);
+	unsigned b = 0u;
+	for (int l = 0; l < 32; ++l) b |= simt::table[(size_t)s][(size_t)l] ? 1u << l : 0u;
+	return b;
+}
+static inline bool __any_sync(unsigned m, bool pred) { return __ballot_sync(m, pred) != 0u; }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src) {
+	uint64_t bits = 0;
+	std::memcpy(&bits, &v, sizeof v);
+	const int s = simt::exchange(bits);
+	T out;
+	std::memcpy(&out, &simt::table[(size_t)s][(size_t)(src & 31)], sizeof out);
+	return out;
+}
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 namespace mptcc {
 namespace {
@@ -98,12 +142,30 @@ void host_relative_transform(const double *R1, const double *T1, const double *R
 }
 // Intersect::intersect_Triangle as the kernels evaluate it: rel = R (9), T (3); P, Q = 9 doubles each (model coordinates)
 int host_exact_tri_intersect(const double *rel, const double *P, const double *Q) {
-	unsigned ballot = 0u;
-	for (g_lane = 0; g_lane < 32; ++g_lane) {
-		(void)mptcc::exact_tri_intersect_warp(rel, P, Q, g_lane);
-		ballot |= g_pred[g_lane] ? 1u << g_lane : 0u;
-	}
-	return ballot == 0u ? 1 : 0;
+	bool res[32];
+	simt::run_warp([&](int lane) { res[lane] = mptcc::exact_tri_intersect_warp(rel, P, Q, lane); });
+	for (int l = 1; l < 32; ++l)
+		if (res[l] != res[0]) return -1;  // (a warp-wide answer)
+	return res[0] ? 1 : 0;
+}
+// exact_path_reaches: does FCL's descent reach the leaf pair of triangles (prim1, prim2)?  node64 / anc: the model's
+// exact-pass arrays (mptcc_bvh_get_exact_arrays), depth = levels per ancestor chain.
+int host_exact_path_reaches(const double *rel, const double *node64_1, const uint32_t *anc1, unsigned depth1, const double *node64_2,
+                            const uint32_t *anc2, unsigned depth2, unsigned prim1, unsigned prim2) {
+	using namespace mptcc;
+	KernelParams p{};
+	p.env.node64 = node64_1;
+	p.env.anc = anc1;
+	p.agent.node64 = node64_2;
+	p.agent.anc = anc2;
+	DevModel m1{}, m2{};
+	m1.depth = depth1;
+	m2.depth = depth2;
+	bool res[32];
+	simt::run_warp([&](int lane) { res[lane] = exact_path_reaches(p, m1, m2, rel, prim1, prim2, lane); });
+	for (int l = 1; l < 32; ++l)
+		if (res[l] != res[0]) return -1;
+	return res[0] ? 1 : 0;
 }
 // rel = R (9), T (3); n1, n2 = node64 records: axis (9), To (3), extent (3), size
 int host_exact_obb_disjoint(const double *rel, const double *n1, const double *n2) { return mptcc::exact_obb_disjoint(rel, n1, n2) ? 1 : 0; }

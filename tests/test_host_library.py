@@ -239,9 +239,9 @@ def _host_filters(tmp_path):
     here = os.path.dirname(os.path.abspath(__file__))
     src = open(os.path.join(here, "..", "motionplanningtoolkit_b200", "csrc", "collide_device.cuh")).read()
     regions = re.findall(r"// \[host-test:begin\].*?\n(.*?)// \[host-test:end\]", src, flags=re.S)
-    assert len(regions) == 7 and "exact_obb_disjoint" in regions[0] and "exact_tri_intersect_warp" in regions[1]
-    assert "tri_filter_f32" in regions[3] and "obb_disjoint_f32" in regions[3] and "rel_element" in regions[4] and "pose_world_box" in regions[5]
-    assert "make_candidate_record2_rt" in regions[6]
+    assert len(regions) == 8 and "exact_obb_disjoint" in regions[0] and "exact_tri_intersect_warp" in regions[1] and "exact_path_reaches" in regions[2]
+    assert "tri_filter_f32" in regions[4] and "obb_disjoint_f32" in regions[4] and "rel_element" in regions[5] and "pose_world_box" in regions[6]
+    assert "make_candidate_record2_rt" in regions[7]
     (tmp_path / "collide_filters_extracted.inc").write_text("\n".join(regions))
     cpp = tmp_path / "host_filters.cpp"
     cpp.write_text(open(os.path.join(here, "host_filters.cpp")).read())
@@ -260,6 +260,9 @@ def _host_filters(tmp_path):
     L.host_exact_obb_disjoint.argtypes = [f64p, f64p, f64p]
     L.host_exact_tri_intersect.restype = ctypes.c_int
     L.host_exact_tri_intersect.argtypes = [f64p, f64p, f64p]
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    L.host_exact_path_reaches.restype = ctypes.c_int
+    L.host_exact_path_reaches.argtypes = [f64p, f64p, u32p, ctypes.c_uint, f64p, u32p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
     L.host_candidate_record2.restype = ctypes.c_int
     L.host_candidate_record2.argtypes = [f64p, f64p, f64p, f64p, ctypes.c_uint, f32p, f64p, f32p]
     L.host_pose_world_box.restype = None
@@ -499,6 +502,41 @@ def test_fused_kernel_fp32_filters_are_one_sided_against_the_oracle(built, tmp_p
     assert tri_checked > 5000 and tri_wrong == 0, (tri_checked, tri_wrong)
     assert tri_settled >= 0.9 * tri_clear, (tri_settled, tri_clear)            # clearly apart: "separated"
     assert tri_certain >= 0.25 * tri_deep, (tri_certain, tri_deep)            # crossing half-way in: a good part "certain contact"
+
+
+def test_device_path_replay_equals_the_oracles_traversal(built, tmp_path):
+    """exact_path_reaches (the replay of FCL's root-to-leaf OBB tests for one triangle pair: two ancestor chains merged under
+    firstOverSecond with warp shuffles, 32 fp64 tests per round) run on the CPU by replaying a converged warp lane by lane
+    (tests/host_filters.cpp), against the oracle's own collisionRecurse with a probe on that leaf pair -- for triangle
+    pairs that touch (the case the kernels replay), with the agent pushed out until the path breaks."""
+    L = _host_filters(tmp_path)
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    u32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+    rng = np.random.default_rng(86)
+    av, at = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    ev, et = sorted(meshio.environment_submeshes(meshio.load_mptm("divider")), key=lambda m: -len(m[1]))[0]
+    hbA, hbE = capi.HostBvh(av, at), capi.HostBvh(ev, et)
+    n64A, ancA = hbA.exact_arrays(True)                     # the agent's device nodes are numbered breadth-first
+    n64E, ancE = hbE.exact_arrays(False)
+    oA, oE = O.Model(av, at), O.Model(ev, et)
+    av, ev, at, et = np.asarray(av, float), np.asarray(ev, float), np.asarray(at), np.asarray(et)
+    reached = broken = 0
+    for _ in range(120):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = scenes.quat_to_matrix(q[None])[0]
+        p1, p2 = int(rng.integers(len(et))), int(rng.integers(len(at)))
+        P, Q = ev[et[p1]], av[at[p2]]
+        base = rng.dirichlet([1, 1, 1]) @ P - R @ (rng.dirichlet([1, 1, 1]) @ Q)      # the two triangles share a point
+        d = rng.normal(size=3); d /= np.linalg.norm(d)
+        for t in (0.0, 1e-3, 0.05, 0.3, 1.0, 3.0):
+            T = base + t * d
+            rel = np.concatenate([R.ravel(), T])
+            got = L.host_exact_path_reaches(f64(rel), f64(n64E), u32(ancE), ancE.shape[1], f64(n64A), u32(ancA), ancA.shape[1], p1, p2)
+            want = O.path_reaches(oE, oA, R, T, p1, p2)
+            assert got == int(want), (p1, p2, t, got, want)
+            reached += want
+            broken += not want
+    assert reached > 100 and broken > 100, (reached, broken)
 
 
 def test_candidate_record_of_the_broadphase_kernel(built, tmp_path):
