@@ -214,6 +214,9 @@ int mptcc_bvh_get_quantised_nodes(const mptcc_bvh *b, int breadth_first, uint32_
  * numbering) and anc [num_tris][*depth] (root-to-leaf node chain per triangle, unused levels 0xffffffff); either may be
  * NULL.  Returns 0, -1 on bad arguments. */
 int mptcc_bvh_get_exact_arrays(const mptcc_bvh *b, int breadth_first, double *node64, uint32_t *anc, uint32_t *depth);
+/* What the path certificate uses of this model: mu_chain [num_tris] (may be NULL) and model6 = the
+ * recentring origin (3), cmax1 = max |To|_1 over the nodes, esum = max sum of extents over the nodes, r2. */
+int mptcc_bvh_get_certificate_data(const mptcc_bvh *b, float *mu_chain, double *model6);
 /* aabb6 = min xyz, max xyz */
 void mptcc_bvh_get_local_aabb(const mptcc_bvh *b, double *aabb6, double *center3, double *radius);
 

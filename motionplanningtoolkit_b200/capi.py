@@ -31,6 +31,7 @@ EXPORTS = [
     "mptcc_get_counters", "mptcc_reset_counters", "mptcc_last_kernel_ms", "mptcc_last_phase_ms", "mptcc_set_option", "mptcc_get_info",
     "mptcc_bvh_build", "mptcc_bvh_free", "mptcc_bvh_num_nodes", "mptcc_bvh_depth", "mptcc_bvh_get_nodes",
     "mptcc_bvh_get_primitive_indices", "mptcc_bvh_get_local_aabb", "mptcc_bvh_get_quantised_nodes", "mptcc_bvh_get_exact_arrays",
+    "mptcc_bvh_get_certificate_data",
     "mptcc_debug_create_host_only", "mptcc_debug_grid_lookup", "mptcc_debug_tree_lookup",
 ]
 
@@ -126,6 +127,8 @@ def load():
     for fn in (L.mptcc_debug_grid_lookup, L.mptcc_debug_tree_lookup):
         fn.restype = C.c_int
         fn.argtypes = [vp, dp, dp, C.c_uint32, u32p]
+    L.mptcc_bvh_get_certificate_data.restype = C.c_int
+    L.mptcc_bvh_get_certificate_data.argtypes = [vp, C.POINTER(C.c_float), dp]
     L.mptcc_bvh_get_exact_arrays.restype = C.c_int
     L.mptcc_bvh_get_exact_arrays.argtypes = [vp, C.c_int, dp, u32p, u32p]
     L.mptcc_bvh_get_quantised_nodes.restype = C.c_int
@@ -394,6 +397,13 @@ class HostBvh:
         if self.lib.mptcc_bvh_get_exact_arrays(self.h, int(breadth_first), _dp(node64), u32(anc), C.byref(depth)) != 0:
             raise MptccError(ERR_INVALID, "mptcc_bvh_get_exact_arrays")
         return node64, anc
+
+    def certificate_data(self):
+        """(mu_chain [num_tris], dict(ctr, cmax1, esum, r2)): what the path certificate uses of this model."""
+        mu = np.zeros(self.nt, np.float32); m6 = np.zeros(6)
+        if self.lib.mptcc_bvh_get_certificate_data(self.h, mu.ctypes.data_as(C.POINTER(C.c_float)), _dp(m6)) != 0:
+            raise MptccError(ERR_INVALID, "mptcc_bvh_get_certificate_data")
+        return mu, dict(ctr=m6[:3].copy(), cmax1=m6[3], esum=m6[4], r2=m6[5])
 
     def primitive_indices(self):
         out = np.empty(self.nt, np.uint32)

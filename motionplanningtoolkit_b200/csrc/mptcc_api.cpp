@@ -1826,6 +1826,21 @@ int mptcc_bvh_get_exact_arrays(const mptcc_bvh *b, int breadth_first, double *no
 	return 0;
 }
 
+int mptcc_bvh_get_certificate_data(const mptcc_bvh *b, float *mu_chain, double *model6) {
+	if (!b || !model6) return -1;
+	HostPack pk;
+	pk.add(b->b, false);
+	const DevModel &m = pk.models[0];
+	if (mu_chain) std::memcpy(mu_chain, pk.mu_chain.data(), sizeof(float) * m.num_tris);
+	model6[0] = m.ctr[0];
+	model6[1] = m.ctr[1];
+	model6[2] = m.ctr[2];
+	model6[3] = m.cmax1;
+	model6[4] = m.esum;
+	model6[5] = (double)m.r2;
+	return 0;
+}
+
 void mptcc_bvh_get_primitive_indices(const mptcc_bvh *b, uint32_t *out) {
 	std::memcpy(out, b->b.primitive_indices.data(), sizeof(uint32_t) * b->b.primitive_indices.size());
 }

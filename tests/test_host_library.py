@@ -539,6 +539,43 @@ def test_device_path_replay_equals_the_oracles_traversal(built, tmp_path):
     assert reached > 100 and broken > 100, (reached, broken)
 
 
+def test_path_certificate_implies_fcl_reaches_the_pair(built, tmp_path):
+    """DESIGN.md section 7 on the CPU: where the kernels skip the path replay of a contact -- min(mu_chain) of the two
+    triangles >= the candidate's threshold, both as the library computes them -- FCL's traversal (the oracle's, with a probe on
+    the leaf pair) does reach that pair.  Checked on triangle pairs of the fixtures that share a point (most of them are
+    certified: the test is not vacuous)."""
+    L = _host_filters(tmp_path)
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    f32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    rng = np.random.default_rng(4711)
+    av, at = meshio.agent_submesh(meshio.load_mptm("blimp"), "merge")
+    certified = contacts = 0
+    for ev, et in sorted(meshio.environment_submeshes(meshio.load_mptm("divider")), key=lambda m: -len(m[1]))[:2] + scenes.synthetic_environment(1):
+        hbA, hbE = capi.HostBvh(av, at), capi.HostBvh(ev, et)
+        muA, cA = hbA.certificate_data()
+        muE, cE = hbE.certificate_data()
+        oA, oE = O.Model(av, at), O.Model(ev, et)
+        va, ve, ta, te = np.asarray(av, float), np.asarray(ev, float), np.asarray(at), np.asarray(et)
+        m1v = np.array([*cE["ctr"], 1.0, cE["cmax1"], cE["esum"]]); m2v = np.array([*cA["ctr"], cA["r2"], cA["cmax1"], cA["esum"]])
+        obj13 = np.array([*np.eye(3).ravel(), 0, 0, 0, 1.0])
+        for k in range(250):
+            q = rng.normal(size=4); q /= np.linalg.norm(q)
+            R = scenes.quat_to_matrix(q[None])[0]
+            p1, p2 = int(rng.integers(len(te))), int(rng.integers(len(ta)))
+            P, Q = ve[te[p1]], va[ta[p2]]
+            T = rng.dirichlet([1, 1, 1]) @ P - R @ (rng.dirichlet([1, 1, 1]) @ Q)
+            if not O.tri_intersect(P, Q, R, T):
+                continue
+            contacts += 1
+            rec, rel, cert = np.empty(16, np.float32), np.empty(12), np.empty(1, np.float32)
+            pose = np.concatenate([R.ravel(), T])
+            assert L.host_candidate_record2(f64(obj13), f64(m1v), f64(m2v), f64(pose), 0, f32(rec), f64(rel), f32(cert)) == 1
+            if min(muE[p1], muA[p2]) >= cert[0]:
+                certified += 1
+                assert O.path_reaches(oE, oA, R, T, p1, p2), (p1, p2)
+    assert contacts > 400 and certified > 0.8 * contacts, (contacts, certified)
+
+
 def test_candidate_record_of_the_broadphase_kernel(built, tmp_path):
     """make_candidate_record2 (collide_device.cuh) compiled for the CPU: the fp64 relative transform it passes on is the
     oracle's relativeTransform bit for bit (for an object at the identity: the pose itself), the fp32 record is that
