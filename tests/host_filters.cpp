@@ -133,6 +133,29 @@ int host_candidate_record2(const double *obj13, const double *m1v, const double 
 	__builtin_memcpy(rec16, rec, 64);
 	return rigid ? 1 : 0;
 }
+// The record of the fused kernel / round-1 pipeline (make_candidate_record): rec13 = R (9), Tc (3), S.
+void host_candidate_record(const double *obj13, const double *m1v, const double *m2v, const double *pose, unsigned fmt, float *rec13) {
+	using namespace mptcc;
+	DevObject ob{};
+	for (int k = 0; k < 9; ++k) ob.R[k] = obj13[k];
+	for (int k = 0; k < 3; ++k) ob.T[k] = obj13[9 + k];
+	ob.identity = obj13[12] != 0.0 ? 1u : 0u;
+	DevModel m1{}, m2{};
+	for (int k = 0; k < 3; ++k) {
+		m1.ctr[k] = m1v[k];
+		m2.ctr[k] = m2v[k];
+	}
+	m1.rinf = (float)m1v[3];
+	m2.r2 = (float)m2v[3];
+	KernelParams p{};
+	p.env.models = &m1;
+	p.pose_format = fmt;
+	float4 rec[4];
+	make_candidate_record(p, pose, ob, m2, 0u, rec);
+	const float *f = reinterpret_cast<const float *>(rec);
+	for (int k = 0; k < 12; ++k) rec13[k] = f[k];
+	rec13[12] = f[12];
+}
 // relativeTransform(tf1 = object (R1 9, T1 3), tf2 = pose (R2 9, T2 3)) -> R (9), T (3)
 void host_relative_transform(const double *R1, const double *T1, const double *R2, const double *T2, double *out12) {
 	mptcc::DevObject ob{};

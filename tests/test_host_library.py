@@ -263,6 +263,8 @@ def _host_filters(tmp_path):
     u32p = ctypes.POINTER(ctypes.c_uint32)
     L.host_exact_path_reaches.restype = ctypes.c_int
     L.host_exact_path_reaches.argtypes = [f64p, f64p, u32p, ctypes.c_uint, f64p, u32p, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]
+    L.host_candidate_record.restype = None
+    L.host_candidate_record.argtypes = [f64p, f64p, f64p, f64p, ctypes.c_uint, f32p]
     L.host_candidate_record2.restype = ctypes.c_int
     L.host_candidate_record2.argtypes = [f64p, f64p, f64p, f64p, ctypes.c_uint, f32p, f64p, f32p]
     L.host_pose_world_box.restype = None
@@ -615,6 +617,19 @@ def test_candidate_record_of_the_broadphase_kernel(built, tmp_path):
         # the records the filter tests above build in numpy are this record
         r16 = np.concatenate([Ro.ravel(), tc, ti, [0.0]]).astype(np.float32)
         assert np.all(np.abs(r16[:15].astype(np.float64) - rec[:15].astype(np.float64)) <= ulp(r16[:15]) + 1e-12)
+    # the record of the fused kernel, as the filter tests above build it in numpy (_record13)
+    ma = _device_model(*meshio.agent_submesh(meshio.load_mptm("blimp"), "merge"))
+    me = _device_model(*meshio.environment_submeshes(meshio.load_mptm("divider"))[3])
+    for _ in range(500):
+        q = rng.normal(size=4); q /= np.linalg.norm(q)
+        R = scenes.quat_to_matrix(q[None])[0]
+        T = rng.normal(size=3) * 10.0 ** rng.integers(-2, 3)
+        rec13 = np.empty(13, np.float32)
+        L.host_candidate_record(f64(np.array([*np.eye(3).ravel(), 0, 0, 0, 1.0])), f64(np.array([*me["ctr"], me["rinf"], 0, 0])),
+                                f64(np.array([*ma["ctr"], ma["r2"], 0, 0])), f64(np.concatenate([R.ravel(), T])), 0, f32(rec13))
+        want = _record13(R, T, me, ma)
+        assert np.array_equal(rec13[:9], want[:9]) and np.all(np.abs(rec13[9:12].astype(np.float64) - want[9:12]) <= ulp(want[9:12]))
+        assert abs(float(rec13[12]) - float(want[12])) <= 4 * ulp(want[12])
     # not rigid: a scaled, a sheared and a NaN rotation block (RT12 records)
     for bad in (np.eye(3) * (1 + 1e-9), np.array([[1, 1e-8, 0], [0, 1, 0], [0, 0, 1.0]]), np.full((3, 3), np.nan)):
         pose = np.concatenate([bad.ravel(), [0.1, 0.2, 0.3]])
